@@ -1,0 +1,99 @@
+/*
+ * x3_search.h -- device-level C ABI of the B200 forward-window match search.
+ *
+ * This is the FFI surface a host program binds (C, cgo, ctypes ...): plain
+ * pointers and sizes, no C++ or torch types.  It computes, for every position p
+ * of a zero-padded input buffer, what the histogram loop of the reference
+ * find_best_match() computes on its stack (reference backend.c:58-74) and the
+ * threshold selection that follows it (reference backend.c:76-78,92,99):
+ *
+ *   H[p][i]  = min(255, #{ d in [1, W-33] : x[p..p+i] == x[p+d..p+d+i] }), i = 0..31
+ *   Lstar[p] = 0 if t <= 0 or H[p][0] < 2, else #{ i : H[p][i] > min(t, H[p][0]-1) }
+ *
+ * The dictionary-dependent filter (reference backend.c:79-90) is NOT here; it is
+ * applied on the host by find_best_match() in x3_backend.h.
+ *
+ * All functions return X3S_OK (0) or a negative error code; x3s_last_error()
+ * describes the last failure of the calling thread.  There is no CPU fallback:
+ * without a CUDA device every compute entry point fails with X3S_ERR_CUDA.
+ */
+#ifndef X3_SEARCH_H
+#define X3_SEARCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define X3S_OK            0
+#define X3S_ERR_CUDA     (-1) /* CUDA runtime / driver failure, or no device */
+#define X3S_ERR_ARG      (-2) /* bad argument */
+#define X3S_ERR_UNSUPP   (-3) /* parameter outside what the kernels implement */
+
+#define X3S_MAX_MATCH_LEN 32  /* reference backend.h:7-10 */
+#define X3S_MAX_T        254  /* u8 cells saturate at 255; lossless while t <= 254 */
+
+/* kernel variants */
+#define X3S_KERNEL_DEFAULT   0 /* the tuned production kernel (bit-sliced diagonals) */
+#define X3S_KERNEL_NAIVE     1 /* one thread per position, byte loop; cross-check only */
+#define X3S_KERNEL_BITSLICED 2
+
+typedef struct x3s_timing {
+	double h2d_ms;    /* host -> device copies (max over GPUs) */
+	double kernel_ms; /* search kernels (max over GPUs), CUDA events */
+	double d2h_ms;    /* device -> host copies of Lstar (and H) */
+	double total_ms;  /* wall time of the whole call */
+	int    gpus;      /* GPUs actually used */
+	int    launches;  /* kernel launches issued */
+} x3s_timing;
+
+/* Number of visible CUDA devices (0 when there is none or no driver). */
+int x3s_device_count(void);
+
+const char *x3s_last_error(void);
+
+/* Library / build description, e.g. "x3-b200 search sm_100a". */
+const char *x3s_version(void);
+
+/*
+ * Bytes of device memory that must be readable behind d_x for a search over
+ * n_positions with window W: the data, the W bytes of padding the reference
+ * allocates (reference x3.c:579,590) and the tile round-up slack of the kernels.
+ * Bytes at index >= n_positions + W are read but never influence a result.
+ */
+size_t x3s_required_bytes(size_t n_positions, size_t W);
+
+/*
+ * Search over a buffer that is already resident on `device`.
+ *   d_x      device pointer, 16-byte aligned, x3s_required_bytes() readable
+ *   d_lstar  device pointer, n_positions bytes (may not be NULL)
+ *   d_H      device pointer, n_positions*32 bytes, or NULL (production mode)
+ *   stream   cudaStream_t as void* (NULL = default stream); the call is
+ *            asynchronous with respect to the host
+ */
+int x3s_search_device(int device, const void *d_x, size_t n_positions, size_t W, int t,
+                      void *d_lstar, void *d_H, void *stream, int variant);
+
+/*
+ * Search over a host buffer x[0 .. n+W) (n data bytes then W zero bytes, the
+ * layout of the reference's iptr, x3.c:579-591).  Positions are partitioned into
+ * `ngpus` contiguous ranges, each shipped with its trailing window halo; results
+ * land in lstar[n] (and H[n*32] when H != NULL).  ngpus <= 0 means "all visible".
+ * Synchronous.  Device and staging buffers are cached between calls.
+ */
+int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int variant,
+                    void *lstar, void *H, x3s_timing *timing);
+
+/* Pinned host memory helpers (so FFI callers can avoid pageable copies). */
+void *x3s_host_alloc(size_t bytes);
+void  x3s_host_free(void *p);
+
+/* Frees every cached device/staging buffer. */
+void x3s_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* X3_SEARCH_H */

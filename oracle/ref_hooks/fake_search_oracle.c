@@ -1,0 +1,41 @@
+/*
+ * fake_search_oracle.c -- TEST INFRASTRUCTURE.  An oracle-backed stand-in for
+ * the device layer (include/x3_search.h), used ONLY to prove on a CPU-only
+ * machine that the histogram/filter split of the backend shim reproduces the
+ * reference stream.  It is linked into oracle/_ref/x3_ref_*_cpuoracle and never
+ * into the product library or the product x3 binary.
+ */
+#include "x3_search.h"
+#include "x3_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+int x3s_device_count(void) { return 0; }
+const char *x3s_last_error(void) { return "fake_search_oracle"; }
+const char *x3s_version(void) { return "oracle-backed fake (tests only)"; }
+size_t x3s_required_bytes(size_t n, size_t W) { return n + W; }
+void *x3s_host_alloc(size_t bytes) { return malloc(bytes); }
+void x3s_host_free(void *p) { free(p); }
+void x3s_release(void) {}
+
+int x3s_search_device(int device, const void *d_x, size_t n, size_t W, int t, void *d_lstar, void *d_H,
+                      void *stream, int variant)
+{
+	(void)device; (void)d_x; (void)n; (void)W; (void)t; (void)d_lstar; (void)d_H; (void)stream; (void)variant;
+	return X3S_ERR_CUDA;
+}
+
+int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int variant, void *lstar, void *H,
+                    x3s_timing *timing)
+{
+	(void)ngpus; (void)variant;
+	if (t > X3S_MAX_T) {
+		return X3S_ERR_UNSUPP;
+	}
+	x3o_table_fast((const uint8_t *)x, n + W, 0, n, W, t, (uint8_t *)H, NULL, (uint8_t *)lstar);
+	if (timing != NULL) {
+		memset(timing, 0, sizeof(*timing));
+	}
+	return X3S_OK;
+}

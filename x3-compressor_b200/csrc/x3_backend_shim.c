@@ -1,0 +1,192 @@
+/*
+ * x3_backend_shim.c -- the nine symbols of the reference's backend.h
+ * (reference backend.h:20-31, backend.c:8-100) on top of the GPU search.
+ *
+ * Split:
+ *   a1 histogram loop   backend.c:58-74   -> GPU, all positions at once
+ *   a2 selection        backend.c:76-78   -> GPU epilogue, Lstar[p]
+ *   a3 dictionary filter backend.c:79-90  -> here, per call, live dictionary
+ *
+ * C99, no CUDA types.  Talks to the device layer only through x3_search.h.
+ */
+#define _POSIX_C_SOURCE 200809L
+#include "x3_backend.h"
+#include "x3_search.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+/* reference backend.c:8,21,33,34 */
+static size_t g_forward_window = 8 * 1024;
+static int g_max_match_count = 15;
+static size_t g_factor1 = 4;
+static size_t g_factor2 = 0;
+
+void set_forward_window(size_t n) { g_forward_window = n; }
+size_t get_forward_window(void) { return g_forward_window; }
+void set_max_match_count(int n) { g_max_match_count = n; }
+int get_max_match_count(void) { return g_max_match_count; }
+size_t get_magic_factor1(void) { return g_factor1; }
+void set_magic_factor1(size_t factor) { g_factor1 = factor; }
+size_t get_magic_factor2(void) { return g_factor2; }
+void set_magic_factor2(size_t factor) { g_factor2 = factor; }
+
+/* Dictionary queries (reference dict.c:105-130, dict.c:159-162).  A C host that
+ * links its dict.c next to this shim provides them as ordinary symbols; the
+ * weak declarations let the shared library load in hosts that register
+ * callbacks instead. */
+extern size_t dict_find_match(const char *p) __attribute__((weak));
+extern size_t dict_get_len_by_index(size_t index) __attribute__((weak));
+
+static x3_dict_find_fn g_dict_find = NULL;
+static x3_dict_len_fn g_dict_len = NULL;
+
+void x3_backend_set_dict(x3_dict_find_fn find, x3_dict_len_fn len)
+{
+	g_dict_find = find;
+	g_dict_len = len;
+}
+
+static const char *g_base = NULL;
+static size_t g_isize = 0;
+static uint8_t *g_lstar = NULL;
+static uint8_t *g_table = NULL;
+static double g_prepare_ms = 0.0;
+
+static void die(const char *what)
+{
+	fprintf(stderr, "x3 search backend: %s\n", what);
+	abort();
+}
+
+void x3_search_release(void)
+{
+	free(g_lstar);
+	free(g_table);
+	g_lstar = NULL;
+	g_table = NULL;
+	g_base = NULL;
+	g_isize = 0;
+}
+
+void x3_search_prepare(const char *base, size_t isize)
+{
+	struct timespec t0, t1;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
+
+	x3_search_release();
+
+	int ngpus = 0;
+	const char *env = getenv("X3_GPUS");
+	if (env != NULL) {
+		ngpus = atoi(env);
+	}
+	int variant = X3S_KERNEL_DEFAULT;
+	env = getenv("X3_SEARCH_KERNEL");
+	if (env != NULL) {
+		variant = atoi(env);
+	}
+	env = getenv("X3_SEARCH_TABLE");
+	const int want_table = env != NULL && atoi(env) != 0;
+
+	g_lstar = malloc(isize > 0 ? isize : 1);
+	if (g_lstar == NULL) {
+		die("out of memory");
+	}
+	if (want_table) {
+		g_table = malloc(isize > 0 ? isize * MAX_MATCH_LEN : 1);
+		if (g_table == NULL) {
+			die("out of memory");
+		}
+	}
+
+	if (isize > 0) {
+		/* backend.c:76: the selection loop never runs for t <= 0 */
+		int t = g_max_match_count;
+		if (t < 0) {
+			t = 0;
+		}
+		int rc = x3s_search_host(base, isize, g_forward_window, t, ngpus, variant, g_lstar, g_table, NULL);
+		if (rc != X3S_OK) {
+			die(x3s_last_error());
+		}
+	}
+
+	g_base = base;
+	g_isize = isize;
+
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	g_prepare_ms = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+}
+
+double x3_search_prepare_ms(void)
+{
+	return g_prepare_ms;
+}
+
+void x3_search_table(const uint8_t **H, const uint8_t **Lstar, size_t *n)
+{
+	if (H != NULL) {
+		*H = g_table;
+	}
+	if (Lstar != NULL) {
+		*Lstar = g_lstar;
+	}
+	if (n != NULL) {
+		*n = g_isize;
+	}
+}
+
+/* replaces reference backend.c:56-100 */
+size_t find_best_match(char *p)
+{
+	if (g_base == NULL) {
+		die("find_best_match() before x3_search_prepare()");
+	}
+	if (p < g_base || (size_t)(p - g_base) >= g_isize) {
+		die("find_best_match(): pointer outside the prepared buffer");
+	}
+
+	x3_dict_find_fn find = g_dict_find != NULL ? g_dict_find : dict_find_match;
+	x3_dict_len_fn len = g_dict_len != NULL ? g_dict_len : dict_get_len_by_index;
+
+	/* Lstar = number of i with count[i] > tc*, the only tc the reference's loop
+	 * nest returns from (count is non-increasing in i and i == 0 is never
+	 * filtered).  0 stands for "return 1 without looking at the dictionary". */
+	const int lstar = g_lstar[p - g_base];
+
+	for (int i = lstar - 1; i >= 0; --i) {
+		/* backend.c:79-83 */
+		if (i >= 2 && g_factor1 > 0) {
+			if (find == NULL || len == NULL) {
+				die("no dictionary queries available (link dict.c or call x3_backend_set_dict)");
+			}
+			const size_t m = find(p + i);
+			if (m != (size_t)-1 && len(m) * g_factor1 > (size_t)(i + 1)) {
+				continue;
+			}
+		}
+		/* backend.c:84-90; int arithmetic as in the reference */
+		if (i >= 1 && g_factor2 > 0) {
+			if (find == NULL || len == NULL) {
+				die("no dictionary queries available (link dict.c or call x3_backend_set_dict)");
+			}
+			int skip = 0;
+			for (int o = 1; o <= i; ++o) {
+				const size_t m = find(p + o);
+				if (m != (size_t)-1 && ((int)len(m) - o) * (int)g_factor2 > i + 1) {
+					skip = 1;
+					break;
+				}
+			}
+			if (skip) {
+				continue;
+			}
+		}
+		return (size_t)i + 1; /* backend.c:92 */
+	}
+
+	return 1; /* backend.c:99 */
+}

@@ -1,0 +1,328 @@
+/*
+ * x3_search_api.cu -- C ABI of the B200 match search (include/x3_search.h).
+ *
+ * Host-side plumbing only: device discovery, cached device/staging buffers,
+ * halo-sharded multi-GPU dispatch (contiguous position
+ * ranges, trailing halo of W-2 bytes, no exchange step) and the copies either
+ * side of the kernels in x3_search_kernels.cu.  No CPU implementation of the
+ * search exists in this library: without a device every entry point fails.
+ */
+#include "x3_search.h"
+#include "x3_search_kernels.cuh"
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+#define CU_TRY(expr)                                                                              \
+	do {                                                                                          \
+		cudaError_t e_ = (expr);                                                                  \
+		if (e_ != cudaSuccess) {                                                                  \
+			return fail(X3S_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),     \
+			            __FILE__, __LINE__);                                                      \
+		}                                                                                         \
+	} while (0)
+
+struct DevState {
+	bool inited = false;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	uint8_t *d_x = nullptr;
+	size_t cap_x = 0;
+	uint8_t *d_l = nullptr;
+	size_t cap_l = 0;
+	uint8_t *d_h = nullptr;
+	size_t cap_h = 0;
+};
+
+std::mutex g_mu;
+std::vector<DevState> g_dev;
+bool g_kernel_inited[64] = {false};
+
+int ensure_kernel_init(int device)
+{
+	if (device < 0 || device >= 64) {
+		return fail(X3S_ERR_ARG, "device index %d out of range", device);
+	}
+	if (!g_kernel_inited[device]) {
+		CU_TRY(x3k_init_device());
+		g_kernel_inited[device] = true;
+	}
+	return X3S_OK;
+}
+
+int grow(uint8_t **ptr, size_t *cap, size_t need)
+{
+	if (need <= *cap) {
+		return X3S_OK;
+	}
+	if (*ptr != nullptr) {
+		CU_TRY(cudaFree(*ptr));
+		*ptr = nullptr;
+		*cap = 0;
+	}
+	CU_TRY(cudaMalloc((void **)ptr, need));
+	*cap = need;
+	return X3S_OK;
+}
+
+int check_params(size_t W, int t)
+{
+	if (t > X3S_MAX_T) {
+		return fail(X3S_ERR_UNSUPP, "max match count %d exceeds %d (u8 table cells)", t, X3S_MAX_T);
+	}
+	if (W > ((size_t)1 << 31)) {
+		return fail(X3S_ERR_UNSUPP, "forward window %zu exceeds 2^31", W);
+	}
+	return X3S_OK;
+}
+
+uint32_t distances(size_t W)
+{
+	/* reference backend.c:66: s in [p+1, p+W-33] */
+	return W > X3S_MAX_MATCH_LEN + 1 ? (uint32_t)(W - X3S_MAX_MATCH_LEN - 1) : 0u;
+}
+
+} /* namespace */
+
+extern "C" {
+
+int x3s_device_count(void)
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		(void)cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+const char *x3s_last_error(void)
+{
+	return g_err;
+}
+
+const char *x3s_version(void)
+{
+	return "x3-b200 search 0.1 (sm_100a; kernels: bitsliced, naive)";
+}
+
+size_t x3s_required_bytes(size_t n_positions, size_t W)
+{
+	return x3k_required_bytes(n_positions, W);
+}
+
+int x3s_search_device(int device, const void *d_x, size_t n_positions, size_t W, int t, void *d_lstar,
+                      void *d_H, void *stream, int variant)
+{
+	int rc = check_params(W, t);
+	if (rc != X3S_OK) {
+		return rc;
+	}
+	if (d_x == nullptr || d_lstar == nullptr) {
+		return fail(X3S_ERR_ARG, "null device pointer");
+	}
+	if (((uintptr_t)d_x & 15) != 0) {
+		return fail(X3S_ERR_ARG, "d_x must be 16-byte aligned");
+	}
+	if (d_H != nullptr && ((uintptr_t)d_H & 31) != 0) {
+		return fail(X3S_ERR_ARG, "d_H must be 32-byte aligned");
+	}
+	CU_TRY(cudaSetDevice(device));
+	rc = ensure_kernel_init(device);
+	if (rc != X3S_OK) {
+		return rc;
+	}
+	X3SearchParams prm;
+	prm.x = (const uint8_t *)d_x;
+	prm.n = n_positions;
+	prm.D = distances(W);
+	prm.t = t;
+	prm.lstar = (uint8_t *)d_lstar;
+	prm.H = (uint8_t *)d_H;
+	CU_TRY(x3k_launch(variant, prm, (cudaStream_t)stream, nullptr));
+	return X3S_OK;
+}
+
+int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int variant, void *lstar, void *H,
+                    x3s_timing *timing)
+{
+	const auto wall0 = std::chrono::steady_clock::now();
+	int rc = check_params(W, t);
+	if (rc != X3S_OK) {
+		return rc;
+	}
+	if (x == nullptr || (lstar == nullptr && n > 0)) {
+		return fail(X3S_ERR_ARG, "null host pointer");
+	}
+	const int ndev = x3s_device_count();
+	if (ndev <= 0) {
+		return fail(X3S_ERR_CUDA, "no CUDA device visible (the search has no CPU fallback)");
+	}
+	int G = ngpus <= 0 ? ndev : (ngpus < ndev ? ngpus : ndev);
+	if ((size_t)G > n / 4096 + 1) {
+		G = (int)(n / 4096 + 1); /* do not shard tiny inputs */
+	}
+
+	std::lock_guard<std::mutex> lock(g_mu);
+	if ((int)g_dev.size() < ndev) {
+		g_dev.resize(ndev);
+	}
+
+	/* contiguous position ranges [a_g, b_g), 16-byte aligned starts */
+	std::vector<size_t> a(G + 1);
+	for (int g = 0; g <= G; ++g) {
+		size_t cut = (size_t)((unsigned __int128)n * g / G);
+		cut &= ~(size_t)4095;
+		a[g] = g == G ? n : cut;
+	}
+
+	int launches = 0;
+	const size_t total = n + W; /* bytes the caller guarantees behind x */
+	for (int g = 0; g < G; ++g) {
+		DevState &ds = g_dev[g];
+		const size_t np = a[g + 1] - a[g];
+		if (np == 0) {
+			continue;
+		}
+		CU_TRY(cudaSetDevice(g));
+		rc = ensure_kernel_init(g);
+		if (rc != X3S_OK) {
+			return rc;
+		}
+		if (!ds.inited) {
+			CU_TRY(cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking));
+			for (int i = 0; i < 4; ++i) {
+				CU_TRY(cudaEventCreate(&ds.ev[i]));
+			}
+			ds.inited = true;
+		}
+		const size_t need = x3k_required_bytes(np, W);
+		rc = grow(&ds.d_x, &ds.cap_x, need);
+		if (rc != X3S_OK) {
+			return rc;
+		}
+		rc = grow(&ds.d_l, &ds.cap_l, np);
+		if (rc != X3S_OK) {
+			return rc;
+		}
+		if (H != nullptr) {
+			rc = grow(&ds.d_h, &ds.cap_h, np * 32);
+			if (rc != X3S_OK) {
+				return rc;
+			}
+		}
+		/* slice + trailing halo: position p reads x[p .. p+W-2] (backend.c:66-74) */
+		size_t have = np + W;
+		if (a[g] + have > total) {
+			have = total - a[g];
+		}
+		CU_TRY(cudaEventRecord(ds.ev[0], ds.stream));
+		CU_TRY(cudaMemcpyAsync(ds.d_x, (const uint8_t *)x + a[g], have, cudaMemcpyHostToDevice, ds.stream));
+		if (need > have) {
+			CU_TRY(cudaMemsetAsync(ds.d_x + have, 0, need - have, ds.stream));
+		}
+		CU_TRY(cudaEventRecord(ds.ev[1], ds.stream));
+		X3SearchParams prm;
+		prm.x = ds.d_x;
+		prm.n = np;
+		prm.D = distances(W);
+		prm.t = t;
+		prm.lstar = ds.d_l;
+		prm.H = H != nullptr ? ds.d_h : nullptr;
+		CU_TRY(x3k_launch(variant, prm, ds.stream, &launches));
+		CU_TRY(cudaEventRecord(ds.ev[2], ds.stream));
+		CU_TRY(cudaMemcpyAsync((uint8_t *)lstar + a[g], ds.d_l, np, cudaMemcpyDeviceToHost, ds.stream));
+		if (H != nullptr) {
+			CU_TRY(cudaMemcpyAsync((uint8_t *)H + a[g] * 32, ds.d_h, np * 32, cudaMemcpyDeviceToHost,
+			                       ds.stream));
+		}
+		CU_TRY(cudaEventRecord(ds.ev[3], ds.stream));
+	}
+
+	x3s_timing tm;
+	memset(&tm, 0, sizeof(tm));
+	tm.gpus = G;
+	tm.launches = launches;
+	for (int g = 0; g < G; ++g) {
+		if (a[g + 1] == a[g]) {
+			continue;
+		}
+		DevState &ds = g_dev[g];
+		CU_TRY(cudaSetDevice(g));
+		CU_TRY(cudaStreamSynchronize(ds.stream));
+		float ms = 0.f;
+		CU_TRY(cudaEventElapsedTime(&ms, ds.ev[0], ds.ev[1]));
+		if (ms > tm.h2d_ms) tm.h2d_ms = ms;
+		CU_TRY(cudaEventElapsedTime(&ms, ds.ev[1], ds.ev[2]));
+		if (ms > tm.kernel_ms) tm.kernel_ms = ms;
+		CU_TRY(cudaEventElapsedTime(&ms, ds.ev[2], ds.ev[3]));
+		if (ms > tm.d2h_ms) tm.d2h_ms = ms;
+	}
+	tm.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+	if (timing != nullptr) {
+		*timing = tm;
+	}
+	return X3S_OK;
+}
+
+void *x3s_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+		(void)cudaGetLastError();
+		fail(X3S_ERR_CUDA, "cudaMallocHost(%zu) failed", bytes);
+		return nullptr;
+	}
+	return p;
+}
+
+void x3s_host_free(void *p)
+{
+	if (p != nullptr) {
+		cudaFreeHost(p);
+	}
+}
+
+void x3s_release(void)
+{
+	std::lock_guard<std::mutex> lock(g_mu);
+	for (size_t g = 0; g < g_dev.size(); ++g) {
+		DevState &ds = g_dev[g];
+		if (!ds.inited && ds.d_x == nullptr) {
+			continue;
+		}
+		if (cudaSetDevice((int)g) != cudaSuccess) {
+			continue;
+		}
+		cudaFree(ds.d_x);
+		cudaFree(ds.d_l);
+		cudaFree(ds.d_h);
+		if (ds.inited) {
+			for (int i = 0; i < 4; ++i) {
+				cudaEventDestroy(ds.ev[i]);
+			}
+			cudaStreamDestroy(ds.stream);
+		}
+		ds = DevState();
+	}
+}
+
+} /* extern "C" */

@@ -1,0 +1,30 @@
+/*
+ * x3_search_kernels.cuh -- internal interface between the C-ABI layer
+ * (x3_search_api.cu) and the sm_100a kernels (x3_search_kernels.cu).
+ */
+#ifndef X3_SEARCH_KERNELS_CUH
+#define X3_SEARCH_KERNELS_CUH
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+struct X3SearchParams {
+	const uint8_t *x;      /* padded input on the device, 16-byte aligned */
+	unsigned long long n;  /* positions to search: [0, n) */
+	uint32_t D;            /* number of distances: W > 33 ? W - 33 : 0 (backend.c:66) */
+	int t;                 /* g_max_match_count (backend.c:21) */
+	uint8_t *lstar;        /* n bytes */
+	uint8_t *H;            /* n*32 bytes or NULL */
+};
+
+/* Worst-case bytes a kernel reads behind x for n positions and window W. */
+size_t x3k_required_bytes(size_t n, size_t W);
+
+/* Launches the chosen variant on `stream`.  Returns the CUDA error of the launch. */
+cudaError_t x3k_launch(int variant, const X3SearchParams &prm, cudaStream_t stream, int *launches);
+
+/* One-time per-device setup (opt-in shared memory size). */
+cudaError_t x3k_init_device(void);
+
+#endif
