@@ -86,6 +86,13 @@ int x3s_search_device(int device, const void *d_x, size_t n_positions, size_t W,
 int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int variant,
                     void *lstar, void *H, x3s_timing *timing);
 
+/*
+ * Restricts x3s_search_host() to the given CUDA device ordinals, in this order
+ * (count <= 0 restores "devices 0 .. ngpus-1").  One process per GPU launchers
+ * (torchrun) call it with their LOCAL_RANK.
+ */
+int x3s_set_devices(const int *ids, int count);
+
 /* Pinned host memory helpers (so FFI callers can avoid pageable copies). */
 void *x3s_host_alloc(size_t bytes);
 void  x3s_host_free(void *p);

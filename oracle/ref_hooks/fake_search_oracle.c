@@ -18,6 +18,7 @@ size_t x3s_required_bytes(size_t n, size_t W) { return n + W; }
 void *x3s_host_alloc(size_t bytes) { return malloc(bytes); }
 void x3s_host_free(void *p) { free(p); }
 void x3s_release(void) {}
+int x3s_set_devices(const int *ids, int count) { (void)ids; (void)count; return X3S_OK; }
 
 int x3s_search_device(int device, const void *d_x, size_t n, size_t W, int t, void *d_lstar, void *d_H,
                       void *stream, int variant)

@@ -1,0 +1,191 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI,
+against the oracle on the same seeded inputs, against the golden fixtures, and -- at
+BASELINE.json's full sizes -- through size-independent properties."""
+import ctypes as C
+import hashlib
+import json
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+ROOT = Path(__file__).resolve().parent.parent
+REF = ROOT / "oracle" / "_ref"
+GOLD = np.load(ROOT / "tests" / "golden" / "fbm_golden.npz")
+KATS = json.loads((ROOT / "tests" / "golden" / "streams.json").read_text())
+
+
+def _inputs(corpus, kind, n):
+    rng = np.random.Generator(np.random.PCG64(n + len(kind)))
+    if kind == "text":
+        return np.frombuffer(corpus.generate("C1", n), dtype=np.uint8)
+    if kind == "binary":
+        return np.frombuffer(corpus.generate("C4", n), dtype=np.uint8)
+    if kind == "mix":
+        return np.frombuffer(corpus.generate("C5", n), dtype=np.uint8)
+    if kind == "zeros":
+        return np.zeros(n, dtype=np.uint8)
+    if kind == "period":
+        return (np.arange(n) % 7).astype(np.uint8)
+    if kind == "rand2":
+        return rng.integers(0, 2, n).astype(np.uint8)
+    if kind == "rand256":
+        return rng.integers(0, 256, n).astype(np.uint8)
+    raise KeyError(kind)
+
+
+def _assert_same(pkg, data, W, t, variant):
+    lstar, H, _ = pkg.search_host(data, W=W, t=t, ngpus=1, variant=variant, want_table=True)
+    H_ref, ls_ref = ol.table(data, W, t)
+    if not np.array_equal(H, H_ref):
+        bad = int(np.argmax((H != H_ref).any(axis=1)))
+        raise AssertionError(f"H differs first at p={bad} (n={len(data)} W={W} t={t} variant={variant}):\n"
+                             f" got {H[bad].tolist()}\n ref {H_ref[bad].tolist()}")
+    assert np.array_equal(lstar, ls_ref), f"Lstar differs first at p={int(np.argmax(lstar != ls_ref))}"
+
+
+@pytest.mark.parametrize("variant", [2, 1])
+@pytest.mark.parametrize("kind,n", [("text", 20000), ("binary", 9001), ("mix", 12345), ("zeros", 5000),
+                                    ("period", 4097), ("rand2", 3968), ("rand256", 3969), ("text", 1),
+                                    ("text", 31), ("text", 33)])
+def test_table_equals_oracle_default_flags(pkg, corpus, variant, kind, n):
+    _assert_same(pkg, _inputs(corpus, kind, n), 8192, 15, variant)
+
+
+@pytest.mark.parametrize("variant", [2, 1])
+@pytest.mark.parametrize("W", [0, 1, 33, 34, 35, 64, 65, 100, 1024, 4096, 8191, 8193, 10000, 8192 + 8192, 17000,
+                               65536])
+def test_table_equals_oracle_window_sweep(pkg, corpus, variant, W):
+    data = _inputs(corpus, "text", 6000)
+    _assert_same(pkg, data, W, 15, variant)
+    _assert_same(pkg, _inputs(corpus, "rand2", 4500), W, 3, variant)
+
+
+@pytest.mark.parametrize("t", [-1 + 1, 1, 2, 3, 15, 16, 64, 200, 254])
+def test_table_equals_oracle_threshold_sweep(pkg, corpus, t):
+    _assert_same(pkg, _inputs(corpus, "mix", 9000), 2048, t, 2)
+    _assert_same(pkg, _inputs(corpus, "zeros", 3000), 1024, t, 2)
+
+
+def test_empty_and_rejected_inputs(pkg):
+    ls, H, _ = pkg.search_host(np.zeros(0, dtype=np.uint8), W=8192, t=15, want_table=True)
+    assert len(ls) == 0 and H.shape == (0, 32)
+    with pytest.raises(pkg.X3SearchError) as ei:
+        pkg.search_host(np.zeros(100, dtype=np.uint8), W=8192, t=255)
+    assert ei.value.code == pkg.X3S_ERR_UNSUPP
+
+
+@pytest.mark.parametrize("key", [k for k in GOLD.files if k.startswith("fbm_") and k.endswith("_empty")])
+def test_backend_mirror_matches_golden_empty_dict(pkg, key):
+    """find_best_match() through the backend.h mirror == the reference's recorded values."""
+    parts = key.split("_")
+    name, W, t, f1, f2 = parts[1], int(parts[2][1:]), int(parts[3][1:]), int(parts[4][1:]), int(parts[5][1:])
+    data = GOLD[f"in_{name}"]
+    b = pkg.Backend()
+    b.set_forward_window(W); b.set_max_match_count(t); b.set_magic_factor1(f1); b.set_magic_factor2(f2)
+    no_find = ol.DICT_FIND_FN(lambda p: (1 << 64) - 1)
+    no_len = ol.DICT_LEN_FN(lambda i: 0)
+    b.set_dict(C.cast(no_find, C.c_void_p), C.cast(no_len, C.c_void_p))
+    try:
+        b.prepare(data)
+        got = np.array([b.find_best_match(p) for p in range(len(data))], dtype=np.uint8)
+    finally:
+        b.release()
+        b.set_dict(None, None)
+        b.set_forward_window(8192); b.set_max_match_count(15); b.set_magic_factor1(4); b.set_magic_factor2(0)
+    assert np.array_equal(got, GOLD[key])
+
+
+@pytest.mark.skipif(not ol.have_ref(), reason="oracle/_ref not shipped")
+def test_backend_mirror_matches_golden_live_dict(pkg):
+    """Same with a populated dictionary: the filter (backend.c:79-90) runs against the
+    compiled reference's dict.c, the histogram/selection come from the GPU."""
+    R = ol.ref()
+    data = GOLD["in_text3k"]
+    x0 = ol.padded(data, 8192)
+    if R.dict_get_elems() == 0:
+        R.dict_enlarge()
+        for off, ln in GOLD["dict_entries"]:
+            assert ol.ref_dict_insert(x0, int(off), int(ln))
+    b = pkg.Backend()
+    b.set_dict(C.cast(R.dict_find_match, C.c_void_p), C.cast(R.dict_get_len_by_index, C.c_void_p))
+    try:
+        for key in [k for k in GOLD.files if k.endswith("_dict") and k.startswith("fbm_")]:
+            parts = key.split("_")
+            W, t, f1, f2 = int(parts[2][1:]), int(parts[3][1:]), int(parts[4][1:]), int(parts[5][1:])
+            b.set_forward_window(W); b.set_max_match_count(t); b.set_magic_factor1(f1); b.set_magic_factor2(f2)
+            b.prepare(data)
+            got = np.array([b.find_best_match(p) for p in range(len(data))], dtype=np.uint8)
+            assert np.array_equal(got, GOLD[key]), key
+    finally:
+        b.release()
+        b.set_dict(None, None)
+        b.set_forward_window(8192); b.set_max_match_count(15); b.set_magic_factor1(4); b.set_magic_factor2(0)
+
+
+def test_full_size_c2_properties(pkg, corpus):
+    """C2 at BASELINE.json's full size (10 192 446 B): the two independent kernels agree
+    bit for bit, a sampled band equals the oracle, and halo sharding is invisible
+    (searching a slice with its trailing halo reproduces the same rows)."""
+    data = np.frombuffer(corpus.generate("C2"), dtype=np.uint8)
+    assert len(data) == 10_192_446
+    W, t = 8192, 15
+    ls_bs, _, tm = pkg.search_host(data, W=W, t=t, variant=2)
+    ls_nv, _, _ = pkg.search_host(data, W=W, t=t, variant=1)
+    assert np.array_equal(ls_bs, ls_nv)
+    for a in (0, 5_000_000, len(data) - 30000):
+        _, ls_ref = ol.table(data, W, t, p0=a, p1=a + 30000)
+        assert np.array_equal(ls_bs[a:a + 30000], ls_ref)
+    # sharding property: rows [a, b) from the slice [a, b + W) with zero padding after the data
+    a, bnd = 3_000_000 + 4096, 3_000_000 + 4096 + 250_000
+    sl = data[a:bnd + W]
+    ls_sl, _, _ = pkg.search_host(sl, W=W, t=t, variant=2)
+    assert np.array_equal(ls_sl[: bnd - a], ls_bs[a:bnd])
+    # checksum of the whole table pinned across variants
+    assert hashlib.sha256(ls_bs.tobytes()).hexdigest() == hashlib.sha256(ls_nv.tobytes()).hexdigest()
+
+
+def test_multi_gpu_sharding_equals_single(pkg, corpus):
+    """x3s_search_host with ngpus > 1 (all visible GPUs) returns the single-GPU table."""
+    data = np.frombuffer(corpus.generate("C5", 3_000_000), dtype=np.uint8)
+    one, _, _ = pkg.search_host(data, W=8192, t=15, ngpus=1)
+    many, _, tm = pkg.search_host(data, W=8192, t=15, ngpus=0)
+    assert np.array_equal(one, many)
+
+
+@pytest.mark.skipif(not (REF / "x3_ref_dropin").exists(), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("case", ["C1:60000:", "C4:30000:", "C5:40000:-n 3 -t 7", "C2:20000:-t 50 -w 32",
+                                  "C1:60000:-m 1 -n 1", "C5:40000:-x"])
+def test_reference_host_over_gpu_backend_matches_kat(case, corpus, tmp_path):
+    """Drop-in proof: the UNMODIFIED reference host pass (x3.c, dict.c, ac.c ...) linked
+    against libx3b200.so emits the reference's stream byte for byte."""
+    name, size, flags = case.split(":")
+    src = tmp_path / "in.bin"
+    src.write_bytes(corpus.generate(name, int(size)))
+    out = tmp_path / "out.x3"
+    r = subprocess.run([str(REF / "x3_ref_dropin"), "-zf", *flags.split(), str(src), str(out)],
+                       stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    s = out.read_bytes()
+    assert (len(s), hashlib.sha256(s).hexdigest()) == (KATS[case]["len"], KATS[case]["sha256"])
+    subprocess.run([str(REF / "x3_ref"), "-df", str(out), str(tmp_path / "back")], check=True,
+                   stderr=subprocess.DEVNULL)
+    assert (tmp_path / "back").read_bytes() == src.read_bytes()
+
+
+@pytest.mark.skipif(not (REF / "x3_ref_check").exists(), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("flags", ["", "-m 1 -n 1", "-t 3 -w 1"])
+def test_every_call_equals_reference_on_gpu(flags, corpus, tmp_path):
+    """Interposition harness over the GPU backend: every find_best_match() call of a real
+    compress() compared with the compiled reference function, live dictionary."""
+    src = tmp_path / "in.bin"
+    src.write_bytes(corpus.generate("C1", 120000))
+    r = subprocess.run([str(REF / "x3_ref_check"), "-zf", *flags.split(), str(src), str(tmp_path / "o.x3")],
+                       stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert "mismatches 0" in r.stderr

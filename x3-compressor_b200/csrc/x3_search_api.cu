@@ -54,6 +54,7 @@ struct DevState {
 
 std::mutex g_mu;
 std::vector<DevState> g_dev;
+std::vector<int> g_ids; /* device ordinals for x3s_search_host; empty = 0..n-1 */
 bool g_kernel_inited[64] = {false};
 
 int ensure_kernel_init(int device)
@@ -172,18 +173,19 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 	if (x == nullptr || (lstar == nullptr && n > 0)) {
 		return fail(X3S_ERR_ARG, "null host pointer");
 	}
-	const int ndev = x3s_device_count();
-	if (ndev <= 0) {
+	const int nvis = x3s_device_count();
+	if (nvis <= 0) {
 		return fail(X3S_ERR_CUDA, "no CUDA device visible (the search has no CPU fallback)");
 	}
+	const int ndev = g_ids.empty() ? nvis : (int)g_ids.size();
 	int G = ngpus <= 0 ? ndev : (ngpus < ndev ? ngpus : ndev);
 	if ((size_t)G > n / 4096 + 1) {
 		G = (int)(n / 4096 + 1); /* do not shard tiny inputs */
 	}
 
 	std::lock_guard<std::mutex> lock(g_mu);
-	if ((int)g_dev.size() < ndev) {
-		g_dev.resize(ndev);
+	if ((int)g_dev.size() < nvis) {
+		g_dev.resize(nvis);
 	}
 
 	/* contiguous position ranges [a_g, b_g), 16-byte aligned starts */
@@ -197,13 +199,14 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 	int launches = 0;
 	const size_t total = n + W; /* bytes the caller guarantees behind x */
 	for (int g = 0; g < G; ++g) {
-		DevState &ds = g_dev[g];
+		const int dev = g_ids.empty() ? g : g_ids[g];
+		DevState &ds = g_dev[dev];
 		const size_t np = a[g + 1] - a[g];
 		if (np == 0) {
 			continue;
 		}
-		CU_TRY(cudaSetDevice(g));
-		rc = ensure_kernel_init(g);
+		CU_TRY(cudaSetDevice(dev));
+		rc = ensure_kernel_init(dev);
 		if (rc != X3S_OK) {
 			return rc;
 		}
@@ -265,8 +268,9 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 		if (a[g + 1] == a[g]) {
 			continue;
 		}
-		DevState &ds = g_dev[g];
-		CU_TRY(cudaSetDevice(g));
+		const int dev = g_ids.empty() ? g : g_ids[g];
+		DevState &ds = g_dev[dev];
+		CU_TRY(cudaSetDevice(dev));
 		CU_TRY(cudaStreamSynchronize(ds.stream));
 		float ms = 0.f;
 		CU_TRY(cudaEventElapsedTime(&ms, ds.ev[0], ds.ev[1]));
@@ -280,6 +284,23 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 	if (timing != nullptr) {
 		*timing = tm;
 	}
+	return X3S_OK;
+}
+
+int x3s_set_devices(const int *ids, int count)
+{
+	std::lock_guard<std::mutex> lock(g_mu);
+	const int nvis = x3s_device_count();
+	if (count <= 0 || ids == nullptr) {
+		g_ids.clear();
+		return X3S_OK;
+	}
+	for (int i = 0; i < count; ++i) {
+		if (ids[i] < 0 || ids[i] >= nvis) {
+			return fail(X3S_ERR_ARG, "device ordinal %d not visible (%d devices)", ids[i], nvis);
+		}
+	}
+	g_ids.assign(ids, ids + count);
 	return X3S_OK;
 }
 
