@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""bench.py -- the x3 forward-window match search on B200, one JSON line per run.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one pass of the hot path (histogram loop + threshold
+selection of the reference find_best_match, backend.c:58-78) over one batch:
+BASELINE.json configs[1], the 10 192 446-byte dickens-shaped synthetic text with the
+default flags (-t 15 -w 8).  One position = one input byte = one unit.
+
+  value     positions searched per second (MB/s, 1e6 B), input already resident in HBM,
+            CUDA events around the kernel launches only, max over ranks
+  e2e       the same through the C ABI a host binds (x3s_search_host: pinned host
+            buffers in, Lstar out; H2D + kernel + D2H inside the timed region)
+  roofline  dominant kernel against the measured HBM peak (algorithmic bytes:
+            2 B/position + the window halo) -- the path is integer-issue bound, so
+            `pair_tests_per_s` and `alu_lane_ops_frac` are reported beside it
+  cpu_baseline / --impl reference
+            the UNMODIFIED reference find_best_match (oracle/_ref/libx3ref.so, compiled
+            from /root/reference by oracle/Makefile) timed on the host cores over a
+            bounded sample of the same positions (falls back to the oracle port when
+            oracle/_ref was not shipped).  Nothing under oracle/ is on the product path.
+
+N > 1: launched by torchrun, one rank per GPU; rank r searches member r of a
+concatenation of N dickens-shaped members (its 10 MB of positions plus the trailing
+window halo taken from member r+1), no data-path collective: "scaling": "weak".
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+WORKLOAD = "C2"
+MEMBER_BYTES = 10_192_446
+W_BYTES = 8192
+T_COUNT = 15
+METRIC = "match_search_throughput"
+UNIT = "MB/s"
+# lane-level ALU-pipe instructions the production kernel spends per byte-pair test
+# (counted from the SASS of the interior loop)
+ALU_OPS_PER_PAIR = None  # filled from x3s_kernel_info when the library reports it
+
+
+def member(corpus, r: int) -> np.ndarray:
+    """Member r of the weak-scaling input: member 0 is exactly config C2."""
+    if r == 0:
+        return np.frombuffer(corpus.generate("C2"), dtype=np.uint8)
+    return np.frombuffer(corpus.text(MEMBER_BYTES, seed=2 + 1000 * r, vocab=30000, para=True), dtype=np.uint8)
+
+
+def padded_member(corpus, r: int, world: int) -> np.ndarray:
+    """Positions of member r followed by its trailing halo (head of member r+1, or the
+    reference's zero padding after the last member, x3.c:579,590)."""
+    body = member(corpus, r)
+    out = np.zeros(len(body) + W_BYTES, dtype=np.uint8)
+    out[: len(body)] = body
+    if r + 1 < world:
+        out[len(body):] = member(corpus, r + 1)[:W_BYTES]
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [ln for (ts, ln) in self.lines if t0 - 0.05 <= ts <= t1 + 0.15] or [ln for (_, ln) in self.lines]
+        for ln in rows:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------
+# CPU arm: the compiled reference (or the oracle port) over a bounded sample
+# ----------------------------------------------------------------------------------------
+class CpuSearch:
+    """find_best_match over sample positions of one padded buffer, on `cores` threads."""
+
+    def __init__(self):
+        import oracle_lib as ol  # checker / baseline only -- never on the product path
+        self.ol = ol
+        self.ora = ol.oracle()
+        if ol.have_ref():
+            self.kind = "reference"
+            R = ol.ref()
+            R.set_forward_window(W_BYTES)
+            R.set_max_match_count(T_COUNT)
+            R.set_magic_factor1(4)
+            R.set_magic_factor2(0)
+            self.fn = C.cast(R.find_best_match, C.c_void_p)
+        else:
+            self.kind = "port"
+            self.fn = None
+        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+    def _one(self, x: np.ndarray, i0: int, i1: int, stride: int):
+        if self.fn is not None:
+            self.ora.x3o_call_range(self.fn, x.ctypes.data, i0, i1, stride)
+        else:
+            # oracle port of backend.c:56-100 with an empty dictionary
+            for i in range(i0, i1, stride):
+                self.ora.x3o_find_best_match(x.ctypes.data + i, W_BYTES, T_COUNT, 4, 0, None, None)
+
+    def run(self, x: np.ndarray, n: int, positions: int, threads: int) -> float:
+        """Searches `positions` positions spread evenly over [0, n); returns seconds."""
+        stride = max(1, n // max(1, positions))
+        span = stride * positions
+        per = (span // threads // stride + 1) * stride
+        thr = []
+        t0 = time.perf_counter()
+        for k in range(threads):
+            i0, i1 = k * per, min(n, (k + 1) * per, span)
+            if i0 >= i1:
+                continue
+            th = threading.Thread(target=self._one, args=(x, i0, i1, stride))
+            th.start()
+            thr.append(th)
+        for th in thr:
+            th.join()
+        return time.perf_counter() - t0
+
+    def calibrate(self, x: np.ndarray, n: int) -> float:
+        """positions per second per core (short probe)"""
+        probe = 2000 if self.fn is not None else 200
+        dt = self.run(x, n, probe, 1)
+        return probe / dt
+
+
+def positions_done(n: int, positions: int) -> int:
+    stride = max(1, n // max(1, positions))
+    span = min(n, stride * positions)
+    return (span + stride - 1) // stride
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import __graft_entry__ as g
+    corpus = g.load_submodule("corpus")
+    cpu = CpuSearch()
+    x = padded_member(corpus, 0, 1)
+    n = MEMBER_BYTES
+    rate1 = cpu.calibrate(x, n)
+    total_steps = args.steps + args.warmup
+    per_step_s = max(0.5, min(6.0, 150.0 / max(1, total_steps)))
+    positions = int(max(cpu.cores * 64, min(n, rate1 * cpu.cores * per_step_s)))
+    for _ in range(args.warmup):
+        cpu.run(x, n, positions, cpu.cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu.run(x, n, positions, cpu.cores)
+    done = positions_done(n, positions)
+    value = done * args.steps / t / 1e6
+    sample = (f"{done} of {n} positions per step (every {max(1, n // positions)}th), unmodified reference "
+              f"find_best_match, empty dictionary, {cpu.cores} threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: 10 192 446 B dickens-shaped text, -t 15 -w 8 (BASELINE.json configs[1])",
+                   "window_bytes": W_BYTES, "max_match_count": T_COUNT},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import __graft_entry__ as g
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    pkg = g.load_package()  # raises if lib/libx3b200.so is missing: there is no fallback
+    corpus = g.load_submodule("corpus")
+    if not torch.cuda.is_available() or pkg.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device visible (the search has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pkg.set_devices([local])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = MEMBER_BYTES
+    x_host = padded_member(corpus, rank, world)
+    need = pkg.required_bytes(n, W_BYTES)
+
+    # ---- (1) device-resident: events around the kernel launches only -------------------
+    d_x = torch.zeros(need, dtype=torch.uint8, device=dev)
+    d_x[: len(x_host)].copy_(torch.from_numpy(x_host))
+    d_l = torch.empty(n, dtype=torch.uint8, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+    launches = 0
+
+    def step_device():
+        pkg.search_device(local, d_x.data_ptr(), n, W_BYTES, T_COUNT, d_l.data_ptr(), None, stream.cuda_stream)
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    t_wall0 = time.time()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for (e0, e1) in ev:
+        flush.fill_(1)               # L2 flush between timed iterations, outside the event pair
+        e0.record(stream)
+        step_device()
+        e1.record(stream)
+        launches += 1
+    barrier()
+    dev_ms = sum(e0.elapsed_time(e1) for (e0, e1) in ev)
+    lstar_dev = d_l.cpu().numpy()
+
+    # ---- (2) end to end through the C ABI with host buffers ----------------------------
+    L = pkg.lib()
+    hx = L.x3s_host_alloc(len(x_host))
+    hl = L.x3s_host_alloc(n)
+    if not hx or not hl:
+        raise SystemExit("x3s_host_alloc failed")
+    C.memmove(hx, x_host.ctypes.data, len(x_host))
+    tm = pkg.Timing()
+
+    def step_host():
+        rc = L.x3s_search_host(hx, n, W_BYTES, T_COUNT, 1, pkg.KERNEL_DEFAULT, hl, None, C.byref(tm))
+        if rc != 0:
+            raise SystemExit("x3s_search_host: " + L.x3s_last_error().decode())
+        return tm.launches
+
+    for _ in range(max(3, args.warmup)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_launches = 0
+    for _ in range(args.steps):
+        e2e_launches += step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1)
+    lstar_host = np.ctypeslib.as_array(C.cast(hl, C.POINTER(C.c_uint8)), shape=(n,)).copy()
+    if not np.array_equal(lstar_host, lstar_dev):
+        raise SystemExit("bench.py: device-resident and host-buffer runs disagree")
+    L.x3s_host_free(hx)
+    L.x3s_host_free(hl)
+
+    # ---- max over ranks ----------------------------------------------------------------
+    if dist is not None:
+        tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_s = float(tt[0]), float(tt[1])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    ms_per_step = dev_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+    e2e_value = world * n * args.steps / e2e_s / 1e6
+    D = W_BYTES - 33
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak = float(json.loads(peaks_file.read_text())["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
+    algo_bytes = 2 * n + (W_BYTES - 2)      # 1 B read + 1 B written per position + halo
+    achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
+    pair_tests = n * D / (ms_per_step * 1e-3)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "x3_lcp_bitsliced_kernel",
+                "algorithmic_bytes_per_launch": algo_bytes,
+                "note": "integer-issue bound, not HBM bound (SURVEY.md 8(d)); see pair_tests_per_s",
+                "pair_tests_per_s": pair_tests}
+    prof = ROOT / "profiles" / "traffic.json"
+    if prof.exists():
+        try:
+            pj = json.loads(prof.read_text())
+            roofline["traffic"] = pj.get("dram_bytes_per_launch")
+            roofline["traffic_source"] = pj.get("source")
+        except (ValueError, OSError):
+            pass
+
+    # ---- CPU baseline on the box's host cores (rank 0, N = 1 only) ----------------------
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = CpuSearch()
+        rate1 = cpu.calibrate(x_host, n)
+        positions = int(min(n, max(cpu.cores * 64, rate1 * cpu.cores * 12.0)))
+        dt = cpu.run(x_host, n, positions, cpu.cores)
+        done = positions_done(n, positions)
+        cpu_baseline = {"value": done / dt / 1e6, "unit": UNIT, "cores": cpu.cores, "kind": cpu.kind,
+                        "sample": f"{done} of {n} positions (every {max(1, n // positions)}th) of the same input, "
+                                  f"find_best_match with an empty dictionary, {dt:.1f} s on {cpu.cores} threads",
+                        "per_core_positions_per_s": rate1}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: 10 192 446 B dickens-shaped text per GPU, -t 15 -w 8 "
+                               "(BASELINE.json configs[1]); one position = one byte",
+                   "window_bytes": W_BYTES, "max_match_count": T_COUNT, "positions_per_gpu": n,
+                   "l2": "flushed between timed steps (256 MiB fill, outside the event pairs)",
+                   "sharding": "contiguous position ranges with trailing window halo, no collective"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(len(x_host)) * world,
+                "d2h_bytes_per_step": int(n) * world, "ms_per_step": e2e_s / args.steps * 1e3,
+                "api": "x3s_search_host (include/x3_search.h), pinned host buffers"},
+        "gpu_launches": launches + e2e_launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
