@@ -36,9 +36,11 @@ extern "C" {
 #define X3S_MAX_T        254  /* u8 cells saturate at 255; lossless while t <= 254 */
 
 /* kernel variants */
-#define X3S_KERNEL_DEFAULT   0 /* the tuned production kernel (bit-sliced diagonals) */
+#define X3S_KERNEL_DEFAULT   0 /* the production kernel: "stream" (fast path when t <= 15 and no H) */
 #define X3S_KERNEL_NAIVE     1 /* one thread per position, byte loop; cross-check only */
-#define X3S_KERNEL_BITSLICED 2
+#define X3S_KERNEL_BITSLICED 2 /* first bit-sliced version (thread-private u8 histograms); kept for comparison */
+#define X3S_KERNEL_STREAM    3 /* same as DEFAULT */
+#define X3S_KERNEL_STREAM_FULL 4 /* stream kernel, u8 counters forced (what H != NULL or t > 15 selects) */
 
 typedef struct x3s_timing {
 	double h2d_ms;    /* host -> device copies (max over GPUs) */

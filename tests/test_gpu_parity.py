@@ -47,9 +47,14 @@ def _assert_same(pkg, data, W, t, variant):
         raise AssertionError(f"H differs first at p={bad} (n={len(data)} W={W} t={t} variant={variant}):\n"
                              f" got {H[bad].tolist()}\n ref {H_ref[bad].tolist()}")
     assert np.array_equal(lstar, ls_ref), f"Lstar differs first at p={int(np.argmax(lstar != ls_ref))}"
+    if variant in (0, 3):
+        # production mode (no table): t <= 15 takes the saturating fast path of the stream kernel
+        lstar2, _, _ = pkg.search_host(data, W=W, t=t, ngpus=1, variant=variant, want_table=False)
+        assert np.array_equal(lstar2, ls_ref), (f"Lstar (no-table mode) differs first at "
+                                                f"p={int(np.argmax(lstar2 != ls_ref))} (n={len(data)} W={W} t={t})")
 
 
-@pytest.mark.parametrize("variant", [2, 1])
+@pytest.mark.parametrize("variant", [0, 2, 1])
 @pytest.mark.parametrize("kind,n", [("text", 20000), ("binary", 9001), ("mix", 12345), ("zeros", 5000),
                                     ("period", 4097), ("rand2", 3968), ("rand256", 3969), ("text", 1),
                                     ("text", 31), ("text", 33)])
@@ -57,7 +62,7 @@ def test_table_equals_oracle_default_flags(pkg, corpus, variant, kind, n):
     _assert_same(pkg, _inputs(corpus, kind, n), 8192, 15, variant)
 
 
-@pytest.mark.parametrize("variant", [2, 1])
+@pytest.mark.parametrize("variant", [0, 2, 1])
 @pytest.mark.parametrize("W", [0, 1, 33, 34, 35, 64, 65, 100, 1024, 4096, 8191, 8193, 10000, 8192 + 8192, 17000,
                                65536])
 def test_table_equals_oracle_window_sweep(pkg, corpus, variant, W):
@@ -68,8 +73,9 @@ def test_table_equals_oracle_window_sweep(pkg, corpus, variant, W):
 
 @pytest.mark.parametrize("t", [-1 + 1, 1, 2, 3, 15, 16, 64, 200, 254])
 def test_table_equals_oracle_threshold_sweep(pkg, corpus, t):
-    _assert_same(pkg, _inputs(corpus, "mix", 9000), 2048, t, 2)
-    _assert_same(pkg, _inputs(corpus, "zeros", 3000), 1024, t, 2)
+    for variant in (0, 2):
+        _assert_same(pkg, _inputs(corpus, "mix", 9000), 2048, t, variant)
+        _assert_same(pkg, _inputs(corpus, "zeros", 3000), 1024, t, variant)
 
 
 def test_empty_and_rejected_inputs(pkg):
@@ -135,16 +141,20 @@ def test_full_size_c2_properties(pkg, corpus):
     data = np.frombuffer(corpus.generate("C2"), dtype=np.uint8)
     assert len(data) == 10_192_446
     W, t = 8192, 15
-    ls_bs, _, tm = pkg.search_host(data, W=W, t=t, variant=2)
-    ls_nv, _, _ = pkg.search_host(data, W=W, t=t, variant=1)
+    ls_bs, _, tm = pkg.search_host(data, W=W, t=t, variant=0)      # stream kernel, fast path
+    ls_nv, _, _ = pkg.search_host(data, W=W, t=t, variant=1)       # naive byte loop
     assert np.array_equal(ls_bs, ls_nv)
+    ls_full, _, _ = pkg.search_host(data, W=W, t=t, variant=4)     # stream kernel, u8 counters
+    assert np.array_equal(ls_bs, ls_full)
+    ls_v1, _, _ = pkg.search_host(data, W=W, t=t, variant=2)       # first bit-sliced kernel
+    assert np.array_equal(ls_bs, ls_v1)
     for a in (0, 5_000_000, len(data) - 30000):
         _, ls_ref = ol.table(data, W, t, p0=a, p1=a + 30000)
         assert np.array_equal(ls_bs[a:a + 30000], ls_ref)
     # sharding property: rows [a, b) from the slice [a, b + W) with zero padding after the data
     a, bnd = 3_000_000 + 4096, 3_000_000 + 4096 + 250_000
     sl = data[a:bnd + W]
-    ls_sl, _, _ = pkg.search_host(sl, W=W, t=t, variant=2)
+    ls_sl, _, _ = pkg.search_host(sl, W=W, t=t, variant=0)
     assert np.array_equal(ls_sl[: bnd - a], ls_bs[a:bnd])
     # checksum of the whole table pinned across variants
     assert hashlib.sha256(ls_bs.tobytes()).hexdigest() == hashlib.sha256(ls_nv.tobytes()).hexdigest()

@@ -52,6 +52,16 @@ struct DevState {
 	size_t cap_h = 0;
 };
 
+/* Per-device scratch of the stream kernel (tile counter + deep histogram rows).
+ * One search is in flight per device at a time: launches on other streams are
+ * ordered behind the previous one through `last`. */
+struct Scratch {
+	unsigned int *counter = nullptr;
+	uint8_t *deep = nullptr;
+	cudaEvent_t last = nullptr;
+};
+Scratch g_scratch[64];
+
 std::mutex g_mu;
 std::vector<DevState> g_dev;
 std::vector<int> g_ids; /* device ordinals for x3s_search_host; empty = 0..n-1 */
@@ -64,8 +74,25 @@ int ensure_kernel_init(int device)
 	}
 	if (!g_kernel_inited[device]) {
 		CU_TRY(x3k_init_device());
+		Scratch &sc = g_scratch[device];
+		CU_TRY(cudaMalloc((void **)&sc.counter, 256));
+		CU_TRY(cudaMalloc((void **)&sc.deep, (size_t)x3k_stream_max_grid() * X3K_DEEP_BYTES_PER_CTA));
+		CU_TRY(cudaEventCreateWithFlags(&sc.last, cudaEventDisableTiming));
 		g_kernel_inited[device] = true;
 	}
+	return X3S_OK;
+}
+
+/* fills the scratch fields and launches behind the device's previous search */
+int launch_on(int device, int variant, X3SearchParams &prm, cudaStream_t stream, int *launches)
+{
+	Scratch &sc = g_scratch[device];
+	prm.tile_counter = sc.counter;
+	prm.deep = sc.deep;
+	prm.ntiles = 0;
+	CU_TRY(cudaStreamWaitEvent(stream, sc.last, 0));
+	CU_TRY(x3k_launch(variant, prm, stream, launches));
+	CU_TRY(cudaEventRecord(sc.last, stream));
 	return X3S_OK;
 }
 
@@ -122,7 +149,7 @@ const char *x3s_last_error(void)
 
 const char *x3s_version(void)
 {
-	return "x3-b200 search 0.1 (sm_100a; kernels: bitsliced, naive)";
+	return "x3-b200 search 0.2 (sm_100a; kernels: stream, bitsliced, naive)";
 }
 
 size_t x3s_required_bytes(size_t n_positions, size_t W)
@@ -158,8 +185,7 @@ int x3s_search_device(int device, const void *d_x, size_t n_positions, size_t W,
 	prm.t = t;
 	prm.lstar = (uint8_t *)d_lstar;
 	prm.H = (uint8_t *)d_H;
-	CU_TRY(x3k_launch(variant, prm, (cudaStream_t)stream, nullptr));
-	return X3S_OK;
+	return launch_on(device, variant, prm, (cudaStream_t)stream, nullptr);
 }
 
 int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int variant, void *lstar, void *H,
@@ -250,7 +276,10 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 		prm.t = t;
 		prm.lstar = ds.d_l;
 		prm.H = H != nullptr ? ds.d_h : nullptr;
-		CU_TRY(x3k_launch(variant, prm, ds.stream, &launches));
+		rc = launch_on(dev, variant, prm, ds.stream, &launches);
+		if (rc != X3S_OK) {
+			return rc;
+		}
 		CU_TRY(cudaEventRecord(ds.ev[2], ds.stream));
 		CU_TRY(cudaMemcpyAsync((uint8_t *)lstar + a[g], ds.d_l, np, cudaMemcpyDeviceToHost, ds.stream));
 		if (H != nullptr) {
@@ -343,6 +372,13 @@ void x3s_release(void)
 			cudaStreamDestroy(ds.stream);
 		}
 		ds = DevState();
+		if (g < 64 && g_kernel_inited[g]) {
+			cudaFree(g_scratch[g].counter);
+			cudaFree(g_scratch[g].deep);
+			cudaEventDestroy(g_scratch[g].last);
+			g_scratch[g] = Scratch();
+			g_kernel_inited[g] = false;
+		}
 	}
 }
 

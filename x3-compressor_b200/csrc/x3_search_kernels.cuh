@@ -16,7 +16,18 @@ struct X3SearchParams {
 	int t;                 /* g_max_match_count (backend.c:21) */
 	uint8_t *lstar;        /* n bytes */
 	uint8_t *H;            /* n*32 bytes or NULL */
+	/* stream kernel only (owned by the API layer, one set per device) */
+	unsigned int *tile_counter; /* dynamic tile scheduler, zeroed before each launch */
+	uint8_t *deep;              /* X3K_DEEP_BYTES_PER_CTA bytes per resident CTA */
+	unsigned int ntiles;
 };
+
+/* Scratch the stream kernel needs: the grid it will be launched with and the
+ * bytes of `deep` histogram rows behind it (32 B per position of a resident tile). */
+#define X3K_STREAM_TILE 1984
+#define X3K_DEEP_BYTES_PER_CTA ((size_t)X3K_STREAM_TILE * 32)
+int x3k_stream_grid(unsigned long long n);
+int x3k_stream_max_grid(void); /* valid after x3k_init_device() */
 
 /* Worst-case bytes a kernel reads behind x for n positions and window W. */
 size_t x3k_required_bytes(size_t n, size_t W);

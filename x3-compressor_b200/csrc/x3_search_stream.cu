@@ -1,0 +1,545 @@
+/*
+ * x3_search_stream.cu -- "stream" kernel: the production forward-window
+ * LCP-histogram search for sm_100a.
+ *
+ * Computes what reference backend.c:58-78 computes (see include/x3_search.h):
+ *   count[p][i] = #{ d in [1, D] : LCP32(p, p+d) >= i+1 },  D = W - 33
+ *   Lstar[p]    = threshold selection over count[p][*]
+ *
+ * The work is N*D byte-pair tests and is bound by the integer ALU pipe, so the
+ * kernel is organised around ALU instructions per pair, not around bytes:
+ *
+ *   - Bit-plane input.  A tile of the input is staged with one TMA bulk copy
+ *     (cp.async.bulk + mbarrier) and transposed into 8 bit-planes; one LOP3 then
+ *     compares 32 byte pairs of one plane, 8 LOP3 give the match word
+ *     E_d[w] = (x[p] == x[p+d]) for the 32 positions p of plane word w.
+ *   - One warp = one independent worker (a 32-thread CTA, 8 resident per SM):
+ *     no CTA-wide barrier exists in the search loop, so a warp that is busy with
+ *     the rare-event path never stalls its neighbours, and the 2 warps that
+ *     share an SM sub-partition fill each other's latency.
+ *   - Distance d = 32 m + r.  For each r the warp materialises the window planes
+ *     shifted by r bits once in shared memory (8 funnel shifts per plane word,
+ *     amortised over all 62 position words), so the inner loop over m has no
+ *     alignment shifts at all: 2 LDS.128 bring the next shifted word, which
+ *     serves both position words of the thread.
+ *   - Each lane owns 2 consecutive position words (64 positions): the match word
+ *     of word 1 is the run continuation of word 0, the neighbour lane supplies
+ *     the continuation of word 1 with one SHFL.  Lane 31 is a helper that owns
+ *     no positions.
+ *   - Levels LCP >= 1 and >= 2 are counted for all 32 positions at once in
+ *     bit-sliced counters fed by a 16-input carry-save adder tree
+ *     (~1.9 LOP3 per input).
+ *   - Levels LCP >= 3 are rare (0.35 % of pairs on text): such match words go to
+ *     a per-lane queue in shared memory and are drained in batches into exact-LCP
+ *     histograms: LCP 3..8 (3..5) packed into one shared-memory word per position,
+ *     deeper ones in a lazily initialised per-position row of global scratch that
+ *     stays in L2.  A position whose LCP-32 bin reaches the cap is masked out of
+ *     the queue filter, so long zero/periodic runs stop generating events.
+ *   - Persistent CTAs fetch tiles from an atomic counter (no tail wave).
+ *
+ * Two instantiations:
+ *   <4,5>  FAST: t <= 15, every counter saturates at 16 (lossless for Lstar because
+ *          the selection only evaluates count > tc with tc <= t, backend.c:78)
+ *   <8,8>  FULL: u8 counters saturating at 255, any t <= 254, exact H rows
+ */
+#include "x3_search_device.cuh"
+
+namespace {
+
+template <int CB, int HB>
+struct SCfg {
+	static constexpr int OWN = 62;                 /* position words per warp: 31 lanes x 2 */
+	static constexpr int NWORD = 64;               /* + the helper lane's two words */
+	static constexpr int P = OWN * 32;             /* positions per tile */
+	static constexpr int MCH = 128;                /* 32-distance blocks per window chunk */
+	static constexpr int NPW = NWORD + MCH + 1;    /* plane words staged per chunk */
+	static constexpr int NSR = NWORD + MCH;        /* shifted plane words per r */
+	static constexpr int NSH = HB == 5 ? 6 : 3;    /* LCP levels kept in the shared word: 3 .. 2+NSH */
+	static constexpr int NDEEP = 30 - NSH;         /* LCP levels kept in the global row: 3+NSH .. 32 */
+	static constexpr uint32_t CAP = HB == 5 ? 16u : 255u;
+	static constexpr uint32_t FMASK = (1u << HB) - 1u;
+	static constexpr int QCAP = 24;                /* queue slots per lane */
+
+	static constexpr size_t OFF_PW = 0;
+	static constexpr size_t OFF_SR = OFF_PW + (size_t)NPW * 32;   /* also the byte staging buffer */
+	static constexpr size_t OFF_HIST = OFF_SR + (size_t)NPW * 32;
+	static constexpr size_t OFF_Q = OFF_HIST + (size_t)64 * 32 * 4;
+	static constexpr size_t OFF_BAR = OFF_Q + (size_t)QCAP * 32 * 8;
+	static constexpr size_t SMEM = OFF_BAR + 16;
+};
+
+static_assert(SCfg<4, 5>::P == X3K_STREAM_TILE, "tile size");
+
+/* Bit-sliced counter over 32 positions fed by a 16-input carry-save tree. */
+template <int CB>
+struct Tree {
+	uint32_t c[CB];
+	uint32_t sat;
+	uint32_t h[4];
+};
+
+__device__ __forceinline__ uint32_t maj3(uint32_t a, uint32_t b, uint32_t c)
+{
+	return (a & b) | (a & c) | (b & c);
+}
+
+template <int CB>
+__device__ __forceinline__ void tree_clear(Tree<CB> &T)
+{
+#pragma unroll
+	for (int j = 0; j < CB; ++j) {
+		T.c[j] = 0;
+	}
+	T.sat = 0;
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		T.h[j] = 0;
+	}
+}
+
+/* input number i (0..15, compile-time after unrolling) of a 16-input block */
+template <int CB>
+__device__ __forceinline__ void tree_add(Tree<CB> &T, uint32_t v, int i)
+{
+	if ((i & 1) == 0) {
+		T.h[0] = v;
+		return;
+	}
+	uint32_t x = maj3(T.c[0], T.h[0], v);
+	T.c[0] ^= T.h[0] ^ v;
+	if ((i & 3) == 1) {
+		T.h[1] = x;
+		return;
+	}
+	uint32_t y = maj3(T.c[1], T.h[1], x);
+	T.c[1] ^= T.h[1] ^ x;
+	if ((i & 7) == 3) {
+		T.h[2] = y;
+		return;
+	}
+	x = maj3(T.c[2], T.h[2], y);
+	T.c[2] ^= T.h[2] ^ y;
+	if ((i & 15) == 7) {
+		T.h[3] = x;
+		return;
+	}
+	y = maj3(T.c[3], T.h[3], x);
+	T.c[3] ^= T.h[3] ^ x;
+	/* y carries weight 16 */
+#pragma unroll
+	for (int j = 4; j < CB; ++j) {
+		const uint32_t tcar = T.c[j] & y;
+		T.c[j] ^= y;
+		y = tcar;
+	}
+	T.sat |= y;
+}
+
+template <int CB>
+__device__ __forceinline__ uint32_t tree_value(const Tree<CB> &T, int b)
+{
+	uint32_t v = 0;
+#pragma unroll
+	for (int j = 0; j < CB; ++j) {
+		v |= ((T.c[j] >> b) & 1u) << j;
+	}
+	return ((T.sat >> b) & 1u) ? (CB == 4 ? 16u : 255u) : v;
+}
+
+/* match word of 32 byte pairs; na[] holds the COMPLEMENTED planes of the owned word,
+ * so every plane is one LOP3: e &= (na ^ b) */
+__device__ __forceinline__ uint32_t eq8(const uint32_t (&na)[8], const uint32_t (&b)[8])
+{
+	uint32_t e = na[0] ^ b[0];
+#pragma unroll
+	for (int j = 1; j < 8; ++j) {
+		e &= na[j] ^ b[j];
+	}
+	return e;
+}
+
+__device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b)
+{
+	asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b));
+}
+
+__device__ __forceinline__ void load_word(const uint4 *base, int k, uint32_t (&w)[8])
+{
+	const uint4 lo = base[2 * k], hi = base[2 * k + 1];
+	w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w;
+	w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
+}
+
+/*
+ * Drains the lane's queue of (E, E_next) match words into the exact-LCP
+ * histograms.  One flattened loop: every iteration either fetches the lane's next
+ * entry or retires one set bit of its LCP>=3 word, so lanes stay busy until their
+ * own work runs out.  Returns the updated "done" masks (x: word 0, y: word 1).
+ */
+template <int CB, int HB>
+__device__ __noinline__ uint2 st_drain(const uint2 *q, uint32_t n0, uint32_t n1, uint32_t *hist,
+                                       uint8_t *deep_tile, int lane, uint2 done)
+{
+	using C = SCfg<CB, HB>;
+	/* word-0 entries sit in slots 0 .. n0-1, word-1 entries in slots QCAP-1 .. QCAP-n1 */
+	uint32_t s = 0, R = 0, e = 0, eh = 0, j = 0;
+	const uint32_t qn = n0 + n1;
+	for (;;) {
+		if (R == 0) {
+			if (s >= qn) {
+				break;
+			}
+			j = s >= n0 ? 1u : 0u;
+			const uint32_t slot = j ? (uint32_t)C::QCAP - 1u - (s - n0) : s;
+			const uint2 en = q[slot * 32 + lane];
+			++s;
+			e = en.x;
+			eh = en.y;
+			R = e & __funnelshift_r(e, eh, 1) & __funnelshift_r(e, eh, 2) & ~(j ? done.y : done.x);
+			continue;
+		}
+		const int b = __ffs(R) - 1;
+		R &= R - 1;
+		const uint32_t v = __funnelshift_r(e, eh, b);
+		const uint32_t run = (v == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~v) - 1);
+		const uint32_t idx = ((j * 32 + b) * 32) + lane;
+		const uint32_t word = hist[idx];
+		if (run < 3u + C::NSH) {
+			const uint32_t sh = HB * (run - 3u);
+			if (((word >> sh) & C::FMASK) < C::CAP) {
+				hist[idx] = word + (1u << sh);
+			}
+		} else {
+			uint8_t *row = deep_tile + ((size_t)(lane * 64 + j * 32 + b)) * 32;
+			if ((word >> 31) == 0) {
+				uint4 *r4 = reinterpret_cast<uint4 *>(row);
+				r4[0] = make_uint4(0, 0, 0, 0);
+				r4[1] = make_uint4(0, 0, 0, 0);
+				hist[idx] = word | 0x80000000u;
+			}
+			const uint32_t k = run - (3u + C::NSH);
+			const uint32_t cv = row[k];
+			if (cv < C::CAP) {
+				row[k] = (uint8_t)(cv + 1);
+				if (run == 32u && cv + 1 == C::CAP) {
+					if (j) {
+						done.y |= 1u << b;
+					} else {
+						done.x |= 1u << b;
+					}
+				}
+			}
+		}
+	}
+	return done;
+}
+
+/* State a lane carries through the search loop. */
+template <int CB>
+struct LaneState {
+	uint32_t A0[8], A1[8]; /* COMPLEMENTED planes of the two owned position words */
+	Tree<CB> T[4];         /* [word 0 L>=1, word 0 L>=2, word 1 L>=1, word 1 L>=2] */
+	uint2 done;
+	uint32_t q0, q1;       /* shared-space byte address of the next free slot of the word-0 queue (grows
+	                        * up) and of the word-1 queue (grows down) */
+};
+
+template <int CB, int HB>
+__device__ __forceinline__ void st_flush(LaneState<CB> &st, uint2 *q, uint32_t *hist, uint8_t *deep_tile, int lane)
+{
+	using C = SCfg<CB, HB>;
+	const uint32_t lo = smem_u32(q + lane), hi = smem_u32(q + (C::QCAP - 1) * 32 + lane);
+	const uint32_t n0 = (st.q0 - lo) / 256u;
+	const uint32_t n1 = (hi - st.q1) / 256u;
+	/* the helper lane owns no positions: its entries are dropped */
+	st.done = st_drain<CB, HB>(q, lane == 31 ? 0u : n0, lane == 31 ? 0u : n1, hist, deep_tile, lane, st.done);
+	st.q0 = lo;
+	st.q1 = hi;
+}
+
+/*
+ * 16 consecutive distance blocks mm0 .. mm0+15 (chunk relative) at a fixed r.
+ * MASKED: blocks outside [vlo, vhi] contribute nothing (d = 0 or d > D).
+ */
+template <int CB, int HB, bool MASKED>
+__device__ __forceinline__ void st_group16(LaneState<CB> &st, const uint4 *sr, uint2 *q, uint32_t *hist,
+                                           uint8_t *deep_tile, int lane, int wA, int mm0, int vlo, int vhi)
+{
+	using C = SCfg<CB, HB>;
+	uint32_t S0[8], S1[8];
+	load_word(sr, wA + mm0, S0);
+#pragma unroll
+	for (int i = 0; i < 16; ++i) {
+		load_word(sr, wA + 1 + mm0 + i, S1);
+		uint32_t e0 = eq8(st.A0, S0);
+		uint32_t e1 = eq8(st.A1, S1);
+		if (MASKED) {
+			const bool valid = (mm0 + i >= vlo) && (mm0 + i <= vhi);
+			e0 = valid ? e0 : 0u;
+			e1 = valid ? e1 : 0u;
+		}
+		const uint32_t en = __shfl_down_sync(FULL_MASK, e0, 1);
+		const uint32_t r20 = e0 & __funnelshift_r(e0, e1, 1);
+		const uint32_t r21 = e1 & __funnelshift_r(e1, en, 1);
+		const uint32_t r30 = r20 & __funnelshift_r(e0, e1, 2) & ~st.done.x;
+		const uint32_t r31 = r21 & __funnelshift_r(e1, en, 2) & ~st.done.y;
+		tree_add(st.T[0], e0, i);
+		tree_add(st.T[1], r20, i);
+		tree_add(st.T[2], e1, i);
+		tree_add(st.T[3], r21, i);
+		if (r30 != 0) {
+			sts64(st.q0, e0, e1);
+			st.q0 += 256;
+		}
+		if (r31 != 0) {
+			sts64(st.q1, e1, en);
+			st.q1 -= 256;
+		}
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			S0[j] = S1[j];
+		}
+		if ((i & 7) == 7) {
+			/* 8 more blocks can push 8 entries at each end */
+			if (__any_sync(FULL_MASK, st.q1 - st.q0 < 256u * 15u)) {
+				st_flush<CB, HB>(st, q, hist, deep_tile, lane);
+			}
+		}
+	}
+}
+
+template <int CB, int HB>
+__global__ void __launch_bounds__(32, 8) x3_lcp_stream_kernel(X3SearchParams prm)
+{
+	using C = SCfg<CB, HB>;
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint4 *pw = reinterpret_cast<uint4 *>(smem + C::OFF_PW);
+	uint4 *sr = reinterpret_cast<uint4 *>(smem + C::OFF_SR);
+	uint8_t *stage = smem + C::OFF_SR;
+	uint32_t *hist = reinterpret_cast<uint32_t *>(smem + C::OFF_HIST);
+	uint2 *q = reinterpret_cast<uint2 *>(smem + C::OFF_Q);
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+
+	const int lane = threadIdx.x;
+	const int wA = 2 * lane;
+	const uint32_t D = prm.D;
+	const uint32_t MB = D / 32 + 1; /* distance blocks m = 0 .. D/32 */
+	const uint32_t nchunks = (MB + C::MCH - 1) / C::MCH;
+	uint8_t *deep_tile = prm.deep + (size_t)blockIdx.x * X3K_DEEP_BYTES_PER_CTA;
+
+	if (lane == 0) {
+		mbar_init(bar, 1);
+	}
+	__syncwarp();
+	uint32_t phase = 0;
+
+	for (;;) {
+		unsigned int tile = 0;
+		if (lane == 0) {
+			tile = atomicAdd(prm.tile_counter, 1u);
+		}
+		tile = __shfl_sync(FULL_MASK, tile, 0);
+		if (tile >= prm.ntiles) {
+			break;
+		}
+		const unsigned long long p0 = (unsigned long long)tile * C::P;
+
+		LaneState<CB> st;
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			tree_clear(st.T[k]);
+		}
+		st.done = make_uint2(0, 0);
+		st.q0 = smem_u32(q + lane);
+		st.q1 = smem_u32(q + (C::QCAP - 1) * 32 + lane);
+		for (int i = lane; i < 64 * 32; i += 32) {
+			hist[i] = 0;
+		}
+
+		for (uint32_t c = 0; c < nchunks; ++c) {
+			/* ---- stage the chunk's bytes and transpose them into bit-planes ---- */
+			__syncwarp();
+			if (lane == 0) {
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				mbar_expect_tx(bar, C::NPW * 32);
+				tma_load_1d(stage, prm.x + p0 + 32ull * C::MCH * c, C::NPW * 32, bar);
+			}
+			mbar_wait(bar, phase);
+			phase ^= 1;
+			for (int k = 0; k < C::NPW; ++k) {
+				const uint32_t byte = stage[32 * k + lane];
+				uint32_t bal[8];
+#pragma unroll
+				for (int j = 0; j < 8; ++j) {
+					bal[j] = __ballot_sync(FULL_MASK, (byte >> j) & 1u);
+				}
+				if (lane == 0) {
+					pw[2 * k] = make_uint4(bal[0], bal[1], bal[2], bal[3]);
+				}
+				if (lane == 1) {
+					pw[2 * k + 1] = make_uint4(bal[4], bal[5], bal[6], bal[7]);
+				}
+			}
+			__syncwarp();
+			if (c == 0) {
+				load_word(pw, wA, st.A0);
+				load_word(pw, wA + 1, st.A1);
+#pragma unroll
+				for (int j = 0; j < 8; ++j) {
+					st.A0[j] = ~st.A0[j];
+					st.A1[j] = ~st.A1[j];
+				}
+			}
+
+			for (int r = 0; r < 32; ++r) {
+				/* valid chunk-relative blocks: d = 32 (MCH c + mm) + r in [1, D] */
+				if (D < (uint32_t)r) {
+					break;
+				}
+				const int vlo = (c == 0 && r == 0) ? 1 : 0;
+				const long long hi = (long long)((D - (uint32_t)r) / 32) - (long long)C::MCH * c;
+				const int vhi = hi >= C::MCH ? C::MCH - 1 : (int)hi;
+				if (vhi < vlo) {
+					continue;
+				}
+				/* ---- window planes shifted by r bits ---- */
+				__syncwarp();
+				for (int k = lane; k < C::NSR; k += 32) {
+					uint32_t a[8], b[8];
+					load_word(pw, k, a);
+					load_word(pw, k + 1, b);
+					uint32_t s[8];
+#pragma unroll
+					for (int j = 0; j < 8; ++j) {
+						s[j] = __funnelshift_r(a[j], b[j], r);
+					}
+					sr[2 * k] = make_uint4(s[0], s[1], s[2], s[3]);
+					sr[2 * k + 1] = make_uint4(s[4], s[5], s[6], s[7]);
+				}
+				__syncwarp();
+
+				for (int g = 0; g < C::MCH / 16; ++g) {
+					const int mm0 = 16 * g;
+					if (mm0 > vhi || mm0 + 15 < vlo) {
+						continue;
+					}
+					if (mm0 >= vlo && mm0 + 15 <= vhi) {
+						st_group16<CB, HB, false>(st, sr, q, hist, deep_tile, lane, wA, mm0, vlo, vhi);
+					} else {
+						st_group16<CB, HB, true>(st, sr, q, hist, deep_tile, lane, wA, mm0, vlo, vhi);
+					}
+				}
+			}
+		}
+
+		st_flush<CB, HB>(st, q, hist, deep_tile, lane);
+		__syncwarp();
+
+		/* ---- epilogue: counts -> Lstar (and the 32-bin row) ---- */
+		if (lane != 31) {
+			const unsigned long long pbase = p0 + 64ull * lane;
+#pragma unroll 1
+			for (int jb = 0; jb < 64; ++jb) {
+				const int j = jb >> 5, b = jb & 31;
+				const unsigned long long p = pbase + jb;
+				if (p >= prm.n) {
+					break;
+				}
+				const uint32_t word = hist[jb * 32 + lane];
+				uint32_t cnt[32];
+				uint32_t acc = 0;
+				if (word >> 31) {
+					const uint4 *r4 = reinterpret_cast<const uint4 *>(deep_tile + ((size_t)(lane * 64 + jb)) * 32);
+					const uint4 lo = r4[0], hi = r4[1];
+					const uint32_t rw[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+					for (int L = 32; L >= 3 + C::NSH; --L) {
+						const int k = L - 3 - C::NSH;
+						acc = min(acc + ((rw[k >> 2] >> (8 * (k & 3))) & 0xffu), C::CAP);
+						cnt[L - 1] = acc;
+					}
+				} else {
+#pragma unroll
+					for (int L = 32; L >= 3 + C::NSH; --L) {
+						cnt[L - 1] = 0;
+					}
+				}
+#pragma unroll
+				for (int L = 2 + C::NSH; L >= 3; --L) {
+					acc = min(acc + ((word >> (HB * (L - 3))) & C::FMASK), C::CAP);
+					cnt[L - 1] = acc;
+				}
+				cnt[1] = j ? tree_value(st.T[3], b) : tree_value(st.T[1], b);
+				cnt[0] = j ? tree_value(st.T[2], b) : tree_value(st.T[0], b);
+				prm.lstar[p] = (uint8_t)lstar_from_counts(cnt, prm.t);
+				if (prm.H != nullptr) {
+					store_row(prm.H, p, cnt);
+				}
+			}
+		}
+		__syncwarp();
+	}
+}
+
+int g_stream_ctas_per_sm = 0;
+int g_stream_sms = 0;
+
+} /* namespace */
+
+cudaError_t x3k_stream_init_device(void)
+{
+	cudaError_t e = cudaFuncSetAttribute(x3_lcp_stream_kernel<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                                     (int)SCfg<4, 5>::SMEM);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	e = cudaFuncSetAttribute(x3_lcp_stream_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                         (int)SCfg<8, 8>::SMEM);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	int dev = 0, occ = 0;
+	e = cudaGetDevice(&dev);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	e = cudaDeviceGetAttribute(&g_stream_sms, cudaDevAttrMultiProcessorCount, dev);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, x3_lcp_stream_kernel<4, 5>, 32, SCfg<4, 5>::SMEM);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	g_stream_ctas_per_sm = occ > 0 ? occ : 1;
+	return cudaSuccess;
+}
+
+int x3k_stream_max_grid(void)
+{
+	return g_stream_sms * g_stream_ctas_per_sm;
+}
+
+int x3k_stream_grid(unsigned long long n)
+{
+	const unsigned long long ntiles = (n + X3K_STREAM_TILE - 1) / X3K_STREAM_TILE;
+	const unsigned long long cap = (unsigned long long)x3k_stream_max_grid();
+	return (int)(ntiles < cap ? ntiles : cap);
+}
+
+/* full: u8 counters (any t <= 254, exact H rows); otherwise the t <= 15 fast path */
+cudaError_t x3k_launch_stream(bool full, X3SearchParams prm, cudaStream_t stream)
+{
+	prm.ntiles = (unsigned int)((prm.n + X3K_STREAM_TILE - 1) / X3K_STREAM_TILE);
+	const int grid = x3k_stream_grid(prm.n);
+	cudaError_t e = cudaMemsetAsync(prm.tile_counter, 0, sizeof(unsigned int), stream);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	if (full) {
+		x3_lcp_stream_kernel<8, 8><<<grid, 32, SCfg<8, 8>::SMEM, stream>>>(prm);
+	} else {
+		x3_lcp_stream_kernel<4, 5><<<grid, 32, SCfg<4, 5>::SMEM, stream>>>(prm);
+	}
+	return cudaGetLastError();
+}
