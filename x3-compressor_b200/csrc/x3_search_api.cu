@@ -77,6 +77,7 @@ int ensure_kernel_init(int device)
 		Scratch &sc = g_scratch[device];
 		CU_TRY(cudaMalloc((void **)&sc.counter, 256));
 		CU_TRY(cudaMalloc((void **)&sc.deep, (size_t)x3k_stream_max_grid() * X3K_DEEP_BYTES_PER_CTA));
+		CU_TRY(cudaMemset(sc.deep, 0, (size_t)x3k_stream_max_grid() * X3K_DEEP_BYTES_PER_CTA));
 		CU_TRY(cudaEventCreateWithFlags(&sc.last, cudaEventDisableTiming));
 		g_kernel_inited[device] = true;
 	}

@@ -23,9 +23,10 @@ struct X3SearchParams {
 };
 
 /* Scratch the stream kernel needs: the grid it will be launched with and the
- * bytes of `deep` histogram rows behind it (32 B per position of a resident tile). */
+ * bytes of `deep` histogram rows behind it (64 B per position of a resident tile;
+ * the rows must be ZERO when a launch starts and the kernel hands them back zeroed). */
 #define X3K_STREAM_TILE 1984
-#define X3K_DEEP_BYTES_PER_CTA ((size_t)X3K_STREAM_TILE * 32)
+#define X3K_DEEP_BYTES_PER_CTA ((size_t)X3K_STREAM_TILE * 64)
 int x3k_stream_grid(unsigned long long n);
 int x3k_stream_max_grid(void); /* valid after x3k_init_device() */
 

@@ -29,18 +29,24 @@
  *   - Levels LCP >= 1 and >= 2 are counted for all 32 positions at once in
  *     bit-sliced counters fed by a 16-input carry-save adder tree
  *     (~1.9 LOP3 per input).
- *   - Levels LCP >= 3 are rare (0.35 % of pairs on text): such match words go to
- *     a per-lane queue in shared memory and are drained in batches into exact-LCP
- *     histograms: LCP 3..8 (3..5) packed into one shared-memory word per position,
- *     deeper ones in a lazily initialised per-position row of global scratch that
- *     stays in L2.  A position whose LCP-32 bin reaches the cap is masked out of
- *     the queue filter, so long zero/periodic runs stop generating events.
+ *   - Levels LCP >= 3 are rare (0.35 % of pairs on text) but very unevenly spread
+ *     over positions (frequent trigrams): such match words go to a per-lane queue
+ *     in shared memory, and the warp drains all queues COOPERATIVELY: the entries
+ *     are dealt out evenly over the 32 lanes (prefix sum + owner search by SHFL),
+ *     and each event updates an exact-LCP histogram with an atomic add: LCP 3..7
+ *     (3..4) packed into one shared-memory word per position, deeper ones in a
+ *     per-position row of global scratch that stays in L2.  A position whose
+ *     LCP-32 bin reaches the cap is masked out of the queue filter, so long
+ *     zero/periodic runs stop generating events.
+ *   - Shared-memory plane arrays are split by word parity and plane half, so the
+ *     LDS.128 of 32 lanes that each own words 2*lane, 2*lane+1 are contiguous
+ *     (no bank conflicts).
  *   - Persistent CTAs fetch tiles from an atomic counter (no tail wave).
  *
  * Two instantiations:
- *   <4,5>  FAST: t <= 15, every counter saturates at 16 (lossless for Lstar because
- *          the selection only evaluates count > tc with tc <= t, backend.c:78)
- *   <8,8>  FULL: u8 counters saturating at 255, any t <= 254, exact H rows
+ *   <4,6>   FAST: t <= 15, every counter saturates at 16 (lossless for Lstar because
+ *           the selection only evaluates count > tc with tc <= t, backend.c:78)
+ *   <8,15>  FULL: counters exact up to 255, any t <= 254, exact H rows
  */
 #include "x3_search_device.cuh"
 
@@ -54,21 +60,30 @@ struct SCfg {
 	static constexpr int MCH = 128;                /* 32-distance blocks per window chunk */
 	static constexpr int NPW = NWORD + MCH + 1;    /* plane words staged per chunk */
 	static constexpr int NSR = NWORD + MCH;        /* shifted plane words per r */
-	static constexpr int NSH = HB == 5 ? 6 : 3;    /* LCP levels kept in the shared word: 3 .. 2+NSH */
+	static constexpr int SEG = (NPW + 1) / 2;      /* uint4 per (parity, half) segment of a plane array */
+	static constexpr int NSH = HB == 6 ? 5 : 2;    /* LCP levels kept in the shared word: 3 .. 2+NSH (bits 0..29;
+	                                                * bit 31 flags a touched deep row) */
 	static constexpr int NDEEP = 30 - NSH;         /* LCP levels kept in the global row: 3+NSH .. 32 */
-	static constexpr uint32_t CAP = HB == 5 ? 16u : 255u;
+	static constexpr int DBITS = HB == 6 ? 8 : 16; /* bits per deep bin */
+	static constexpr int ROWB = HB == 6 ? 32 : 64; /* bytes per deep row */
+	static constexpr uint32_t CAP = HB == 6 ? 16u : 255u;
 	static constexpr uint32_t FMASK = (1u << HB) - 1u;
+	static constexpr uint32_t DMASK = (1u << DBITS) - 1u;
 	static constexpr int QCAP = 24;                /* queue slots per lane */
 
 	static constexpr size_t OFF_PW = 0;
-	static constexpr size_t OFF_SR = OFF_PW + (size_t)NPW * 32;   /* also the byte staging buffer */
-	static constexpr size_t OFF_HIST = OFF_SR + (size_t)NPW * 32;
-	static constexpr size_t OFF_Q = OFF_HIST + (size_t)64 * 32 * 4;
+	static constexpr size_t OFF_SR = OFF_PW + (size_t)4 * SEG * 16; /* also the byte staging buffer */
+	static constexpr size_t OFF_HIST = OFF_SR + (size_t)4 * SEG * 16;
+	static constexpr size_t OFF_DONE = OFF_HIST + (size_t)64 * 32 * 4;
+	static constexpr size_t OFF_Q = OFF_DONE + (size_t)64 * 4;
 	static constexpr size_t OFF_BAR = OFF_Q + (size_t)QCAP * 32 * 8;
 	static constexpr size_t SMEM = OFF_BAR + 16;
+	static_assert((size_t)NPW * 32 <= (size_t)4 * SEG * 16, "staging buffer fits the SR array");
+	static_assert(NDEEP * DBITS <= ROWB * 8, "deep row holds every deep bin");
 };
 
-static_assert(SCfg<4, 5>::P == X3K_STREAM_TILE, "tile size");
+static_assert(SCfg<4, 6>::P == X3K_STREAM_TILE, "tile size");
+static_assert((size_t)SCfg<8, 15>::ROWB * SCfg<8, 15>::P <= X3K_DEEP_BYTES_PER_CTA, "deep scratch per CTA");
 
 /* Bit-sliced counter over 32 positions fed by a 16-input carry-save tree. */
 template <int CB>
@@ -163,75 +178,111 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b)
 	asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b));
 }
 
+/* Plane arrays in shared memory: word k, half h (planes 0-3 / 4-7) lives at
+ * uint4 index ((k & 1) * 2 + h) * SEG + (k >> 1). */
+template <int SEG>
+__device__ __forceinline__ int pidx(int k, int h)
+{
+	return ((k & 1) * 2 + h) * SEG + (k >> 1);
+}
+
+template <int SEG>
 __device__ __forceinline__ void load_word(const uint4 *base, int k, uint32_t (&w)[8])
 {
-	const uint4 lo = base[2 * k], hi = base[2 * k + 1];
+	const uint4 lo = base[pidx<SEG>(k, 0)], hi = base[pidx<SEG>(k, 1)];
 	w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w;
 	w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
 }
 
+template <int SEG>
+__device__ __forceinline__ void store_word(uint4 *base, int k, const uint32_t (&w)[8])
+{
+	base[pidx<SEG>(k, 0)] = make_uint4(w[0], w[1], w[2], w[3]);
+	base[pidx<SEG>(k, 1)] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
 /*
- * Drains the lane's queue of (E, E_next) match words into the exact-LCP
- * histograms.  One flattened loop: every iteration either fetches the lane's next
- * entry or retires one set bit of its LCP>=3 word, so lanes stay busy until their
- * own work runs out.  Returns the updated "done" masks (x: word 0, y: word 1).
+ * Cooperative drain.  Lane l holds n0 word-0 entries (slots 0 .. n0-1) and n1 word-1
+ * entries (slots QCAP-1 .. QCAP-n1) of (E, E_next) match words.  Entries are numbered
+ * globally by an exclusive prefix sum over lanes and dealt out 32 at a time, so every
+ * lane gets the same number of entries no matter how skewed the queues are; the owner
+ * of a global index is found by a 5-step search over the prefix sums with SHFL.  Each
+ * set bit of the entry's LCP>=3 word is one event: an atomic add into the exact-LCP
+ * bin of that position (several lanes may hit the same position).  Bins may overshoot
+ * the cap by at most 31 (one add in flight per lane), which the field widths absorb
+ * and the epilogue clamps.
  */
 template <int CB, int HB>
-__device__ __noinline__ uint2 st_drain(const uint2 *q, uint32_t n0, uint32_t n1, uint32_t *hist,
-                                       uint8_t *deep_tile, int lane, uint2 done)
+__device__ __noinline__ void st_drain(const uint2 *q, uint32_t n0, uint32_t n1, uint32_t *hist, uint32_t *done_s,
+                                      uint8_t *deep_tile, int lane)
 {
 	using C = SCfg<CB, HB>;
-	/* word-0 entries sit in slots 0 .. n0-1, word-1 entries in slots QCAP-1 .. QCAP-n1 */
-	uint32_t s = 0, R = 0, e = 0, eh = 0, j = 0;
-	const uint32_t qn = n0 + n1;
-	for (;;) {
-		if (R == 0) {
-			if (s >= qn) {
-				break;
-			}
-			j = s >= n0 ? 1u : 0u;
-			const uint32_t slot = j ? (uint32_t)C::QCAP - 1u - (s - n0) : s;
-			const uint2 en = q[slot * 32 + lane];
-			++s;
-			e = en.x;
-			eh = en.y;
-			R = e & __funnelshift_r(e, eh, 1) & __funnelshift_r(e, eh, 2) & ~(j ? done.y : done.x);
-			continue;
+	const uint32_t n = n0 + n1;
+	uint32_t inc = n;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t t = __shfl_up_sync(FULL_MASK, inc, d);
+		if (lane >= d) {
+			inc += t;
 		}
-		const int b = __ffs(R) - 1;
-		R &= R - 1;
-		const uint32_t v = __funnelshift_r(e, eh, b);
-		const uint32_t run = (v == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~v) - 1);
-		const uint32_t idx = ((j * 32 + b) * 32) + lane;
-		const uint32_t word = hist[idx];
-		if (run < 3u + C::NSH) {
-			const uint32_t sh = HB * (run - 3u);
-			if (((word >> sh) & C::FMASK) < C::CAP) {
-				hist[idx] = word + (1u << sh);
+	}
+	const uint32_t excl = inc - n;
+	const uint32_t E = __shfl_sync(FULL_MASK, inc, 31);
+
+	for (uint32_t base = 0; base < E; base += 32) {
+		const uint32_t idx = base + lane;
+		/* last lane o with excl[o] <= idx (empty lanes tie with their successor and lose) */
+		int o = 0;
+#pragma unroll
+		for (int step = 16; step > 0; step >>= 1) {
+			const int cand = o + step;
+			const uint32_t ex = __shfl_sync(FULL_MASK, excl, cand & 31);
+			if (ex <= idx) {
+				o = cand;
 			}
-		} else {
-			uint8_t *row = deep_tile + ((size_t)(lane * 64 + j * 32 + b)) * 32;
-			if ((word >> 31) == 0) {
-				uint4 *r4 = reinterpret_cast<uint4 *>(row);
-				r4[0] = make_uint4(0, 0, 0, 0);
-				r4[1] = make_uint4(0, 0, 0, 0);
-				hist[idx] = word | 0x80000000u;
-			}
-			const uint32_t k = run - (3u + C::NSH);
-			const uint32_t cv = row[k];
-			if (cv < C::CAP) {
-				row[k] = (uint8_t)(cv + 1);
-				if (run == 32u && cv + 1 == C::CAP) {
-					if (j) {
-						done.y |= 1u << b;
-					} else {
-						done.x |= 1u << b;
+		}
+		const uint32_t exo = __shfl_sync(FULL_MASK, excl, o);
+		const uint32_t n0o = __shfl_sync(FULL_MASK, n0, o);
+		if (idx < E) {
+			const uint32_t s = idx - exo;
+			const uint32_t j = s >= n0o ? 1u : 0u;
+			const uint32_t slot = j ? (uint32_t)C::QCAP - 1u - (s - n0o) : s;
+			const uint2 en = q[slot * 32 + o];
+			const uint32_t e = en.x, eh = en.y;
+			const uint32_t w = 2u * (uint32_t)o + j;
+			uint32_t R = e & __funnelshift_r(e, eh, 1) & __funnelshift_r(e, eh, 2) & ~done_s[w];
+			while (R != 0) {
+				const int b = __ffs(R) - 1;
+				R &= R - 1;
+				const uint32_t v = __funnelshift_r(e, eh, b);
+				const uint32_t run = (v == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~v) - 1);
+				const uint32_t pos = w * 32u + (uint32_t)b;
+				const uint32_t word = hist[pos];
+				if (run < 3u + C::NSH) {
+					const uint32_t sh = HB * (run - 3u);
+					if (((word >> sh) & C::FMASK) < C::CAP) {
+						atomicAdd(&hist[pos], 1u << sh);
+					}
+				} else {
+					if ((word >> 31) == 0) {
+						atomicOr(&hist[pos], 0x80000000u); /* row touched */
+					}
+					const uint32_t k = run - (3u + C::NSH);
+					constexpr uint32_t PER = 32 / C::DBITS; /* bins per 32-bit word of the row */
+					unsigned int *rw = reinterpret_cast<unsigned int *>(deep_tile + (size_t)pos * C::ROWB) + k / PER;
+					const uint32_t sh = C::DBITS * (k % PER);
+					const uint32_t cv = (__ldcg(rw) >> sh) & C::DMASK;
+					if (cv < C::CAP) {
+						atomicAdd(rw, 1u << sh);
+					}
+					if (run == 32u && cv + 1u >= C::CAP) {
+						atomicOr(&done_s[w], 1u << b); /* every level of this position is saturated */
 					}
 				}
 			}
 		}
 	}
-	return done;
+	__syncwarp();
 }
 
 /* State a lane carries through the search loop. */
@@ -245,14 +296,16 @@ struct LaneState {
 };
 
 template <int CB, int HB>
-__device__ __forceinline__ void st_flush(LaneState<CB> &st, uint2 *q, uint32_t *hist, uint8_t *deep_tile, int lane)
+__device__ __forceinline__ void st_flush(LaneState<CB> &st, uint2 *q, uint32_t *hist, uint32_t *done_s,
+                                         uint8_t *deep_tile, int lane)
 {
 	using C = SCfg<CB, HB>;
 	const uint32_t lo = smem_u32(q + lane), hi = smem_u32(q + (C::QCAP - 1) * 32 + lane);
 	const uint32_t n0 = (st.q0 - lo) / 256u;
 	const uint32_t n1 = (hi - st.q1) / 256u;
 	/* the helper lane owns no positions: its entries are dropped */
-	st.done = st_drain<CB, HB>(q, lane == 31 ? 0u : n0, lane == 31 ? 0u : n1, hist, deep_tile, lane, st.done);
+	st_drain<CB, HB>(q, lane == 31 ? 0u : n0, lane == 31 ? 0u : n1, hist, done_s, deep_tile, lane);
+	st.done = make_uint2(done_s[2 * lane], done_s[2 * lane + 1]);
 	st.q0 = lo;
 	st.q1 = hi;
 }
@@ -263,14 +316,28 @@ __device__ __forceinline__ void st_flush(LaneState<CB> &st, uint2 *q, uint32_t *
  */
 template <int CB, int HB, bool MASKED>
 __device__ __forceinline__ void st_group16(LaneState<CB> &st, const uint4 *sr, uint2 *q, uint32_t *hist,
-                                           uint8_t *deep_tile, int lane, int wA, int mm0, int vlo, int vhi)
+                                           uint32_t *done_s, uint8_t *deep_tile, int lane, int wA, int mm0, int vlo,
+                                           int vhi)
 {
 	using C = SCfg<CB, HB>;
 	uint32_t S0[8], S1[8];
-	load_word(sr, wA + mm0, S0);
+	/* mm0 is a multiple of 16 and wA = 2 * lane: the parity of every plane word index below is a
+	 * compile-time constant after unrolling, and the 32 lanes read contiguous uint4 */
+	const uint4 *srl = sr + lane + (mm0 >> 1);
+	{
+		const uint4 lo = srl[0 * C::SEG], hi = srl[1 * C::SEG]; /* word wA + mm0: even */
+		S0[0] = lo.x; S0[1] = lo.y; S0[2] = lo.z; S0[3] = lo.w;
+		S0[4] = hi.x; S0[5] = hi.y; S0[6] = hi.z; S0[7] = hi.w;
+	}
 #pragma unroll
 	for (int i = 0; i < 16; ++i) {
-		load_word(sr, wA + 1 + mm0 + i, S1);
+		{
+			/* word wA + 1 + mm0 + i */
+			const int par = (1 + i) & 1, off = (1 + i) >> 1;
+			const uint4 lo = srl[(par * 2 + 0) * C::SEG + off], hi = srl[(par * 2 + 1) * C::SEG + off];
+			S1[0] = lo.x; S1[1] = lo.y; S1[2] = lo.z; S1[3] = lo.w;
+			S1[4] = hi.x; S1[5] = hi.y; S1[6] = hi.z; S1[7] = hi.w;
+		}
 		uint32_t e0 = eq8(st.A0, S0);
 		uint32_t e1 = eq8(st.A1, S1);
 		if (MASKED) {
@@ -301,11 +368,12 @@ __device__ __forceinline__ void st_group16(LaneState<CB> &st, const uint4 *sr, u
 		}
 		if ((i & 7) == 7) {
 			/* 8 more blocks can push 8 entries at each end */
-			if (__any_sync(FULL_MASK, st.q1 - st.q0 < 256u * 15u)) {
-				st_flush<CB, HB>(st, q, hist, deep_tile, lane);
+			if (__any_sync(FULL_MASK, (int)(st.q1 - st.q0) < 256 * 15)) { /* signed: a full queue gives -256 */
+				st_flush<CB, HB>(st, q, hist, done_s, deep_tile, lane);
 			}
 		}
 	}
+	(void)wA;
 }
 
 template <int CB, int HB>
@@ -317,6 +385,7 @@ __global__ void __launch_bounds__(32, 8) x3_lcp_stream_kernel(X3SearchParams prm
 	uint4 *sr = reinterpret_cast<uint4 *>(smem + C::OFF_SR);
 	uint8_t *stage = smem + C::OFF_SR;
 	uint32_t *hist = reinterpret_cast<uint32_t *>(smem + C::OFF_HIST);
+	uint32_t *done_s = reinterpret_cast<uint32_t *>(smem + C::OFF_DONE);
 	uint2 *q = reinterpret_cast<uint2 *>(smem + C::OFF_Q);
 	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
 
@@ -355,6 +424,8 @@ __global__ void __launch_bounds__(32, 8) x3_lcp_stream_kernel(X3SearchParams prm
 		for (int i = lane; i < 64 * 32; i += 32) {
 			hist[i] = 0;
 		}
+		done_s[lane] = 0;
+		done_s[lane + 32] = 0;
 
 		for (uint32_t c = 0; c < nchunks; ++c) {
 			/* ---- stage the chunk's bytes and transpose them into bit-planes ---- */
@@ -374,16 +445,16 @@ __global__ void __launch_bounds__(32, 8) x3_lcp_stream_kernel(X3SearchParams prm
 					bal[j] = __ballot_sync(FULL_MASK, (byte >> j) & 1u);
 				}
 				if (lane == 0) {
-					pw[2 * k] = make_uint4(bal[0], bal[1], bal[2], bal[3]);
+					pw[pidx<C::SEG>(k, 0)] = make_uint4(bal[0], bal[1], bal[2], bal[3]);
 				}
 				if (lane == 1) {
-					pw[2 * k + 1] = make_uint4(bal[4], bal[5], bal[6], bal[7]);
+					pw[pidx<C::SEG>(k, 1)] = make_uint4(bal[4], bal[5], bal[6], bal[7]);
 				}
 			}
 			__syncwarp();
 			if (c == 0) {
-				load_word(pw, wA, st.A0);
-				load_word(pw, wA + 1, st.A1);
+				load_word<C::SEG>(pw, wA, st.A0);
+				load_word<C::SEG>(pw, wA + 1, st.A1);
 #pragma unroll
 				for (int j = 0; j < 8; ++j) {
 					st.A0[j] = ~st.A0[j];
@@ -404,17 +475,22 @@ __global__ void __launch_bounds__(32, 8) x3_lcp_stream_kernel(X3SearchParams prm
 				}
 				/* ---- window planes shifted by r bits ---- */
 				__syncwarp();
-				for (int k = lane; k < C::NSR; k += 32) {
-					uint32_t a[8], b[8];
-					load_word(pw, k, a);
-					load_word(pw, k + 1, b);
-					uint32_t s[8];
+				for (int k2 = lane; k2 < C::NSR / 2; k2 += 32) {
+					/* words 2*k2 and 2*k2+1: lanes touch contiguous uint4 of every segment */
+					uint32_t a[8], b[8], c2[8], s[8];
+					load_word<C::SEG>(pw, 2 * k2, a);
+					load_word<C::SEG>(pw, 2 * k2 + 1, b);
+					load_word<C::SEG>(pw, 2 * k2 + 2, c2);
 #pragma unroll
 					for (int j = 0; j < 8; ++j) {
 						s[j] = __funnelshift_r(a[j], b[j], r);
 					}
-					sr[2 * k] = make_uint4(s[0], s[1], s[2], s[3]);
-					sr[2 * k + 1] = make_uint4(s[4], s[5], s[6], s[7]);
+					store_word<C::SEG>(sr, 2 * k2, s);
+#pragma unroll
+					for (int j = 0; j < 8; ++j) {
+						s[j] = __funnelshift_r(b[j], c2[j], r);
+					}
+					store_word<C::SEG>(sr, 2 * k2 + 1, s);
 				}
 				__syncwarp();
 
@@ -424,15 +500,15 @@ __global__ void __launch_bounds__(32, 8) x3_lcp_stream_kernel(X3SearchParams prm
 						continue;
 					}
 					if (mm0 >= vlo && mm0 + 15 <= vhi) {
-						st_group16<CB, HB, false>(st, sr, q, hist, deep_tile, lane, wA, mm0, vlo, vhi);
+						st_group16<CB, HB, false>(st, sr, q, hist, done_s, deep_tile, lane, wA, mm0, vlo, vhi);
 					} else {
-						st_group16<CB, HB, true>(st, sr, q, hist, deep_tile, lane, wA, mm0, vlo, vhi);
+						st_group16<CB, HB, true>(st, sr, q, hist, done_s, deep_tile, lane, wA, mm0, vlo, vhi);
 					}
 				}
 			}
 		}
 
-		st_flush<CB, HB>(st, q, hist, deep_tile, lane);
+		st_flush<CB, HB>(st, q, hist, done_s, deep_tile, lane);
 		__syncwarp();
 
 		/* ---- epilogue: counts -> Lstar (and the 32-bin row) ---- */
@@ -442,20 +518,26 @@ __global__ void __launch_bounds__(32, 8) x3_lcp_stream_kernel(X3SearchParams prm
 			for (int jb = 0; jb < 64; ++jb) {
 				const int j = jb >> 5, b = jb & 31;
 				const unsigned long long p = pbase + jb;
-				if (p >= prm.n) {
-					break;
-				}
-				const uint32_t word = hist[jb * 32 + lane];
+				const bool live = p < prm.n; /* rows of padding positions are still handed back zeroed */
+				const uint32_t pos = (uint32_t)lane * 64u + (uint32_t)jb;
+				const uint32_t word = hist[pos];
 				uint32_t cnt[32];
 				uint32_t acc = 0;
 				if (word >> 31) {
-					const uint4 *r4 = reinterpret_cast<const uint4 *>(deep_tile + ((size_t)(lane * 64 + jb)) * 32);
-					const uint4 lo = r4[0], hi = r4[1];
-					const uint32_t rw[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+					/* read the deep row and hand it back zeroed (the scratch invariant) */
+					uint4 *r4 = reinterpret_cast<uint4 *>(deep_tile + (size_t)pos * C::ROWB);
+					uint32_t rw[C::ROWB / 4];
+#pragma unroll
+					for (int v4 = 0; v4 < C::ROWB / 16; ++v4) {
+						const uint4 t4 = __ldcg(r4 + v4);
+						rw[4 * v4] = t4.x; rw[4 * v4 + 1] = t4.y; rw[4 * v4 + 2] = t4.z; rw[4 * v4 + 3] = t4.w;
+						__stcg(r4 + v4, make_uint4(0, 0, 0, 0));
+					}
+					constexpr int PER = 32 / C::DBITS;
 #pragma unroll
 					for (int L = 32; L >= 3 + C::NSH; --L) {
 						const int k = L - 3 - C::NSH;
-						acc = min(acc + ((rw[k >> 2] >> (8 * (k & 3))) & 0xffu), C::CAP);
+						acc = min(acc + ((rw[k / PER] >> (C::DBITS * (k % PER))) & C::DMASK), C::CAP);
 						cnt[L - 1] = acc;
 					}
 				} else {
@@ -471,9 +553,11 @@ __global__ void __launch_bounds__(32, 8) x3_lcp_stream_kernel(X3SearchParams prm
 				}
 				cnt[1] = j ? tree_value(st.T[3], b) : tree_value(st.T[1], b);
 				cnt[0] = j ? tree_value(st.T[2], b) : tree_value(st.T[0], b);
-				prm.lstar[p] = (uint8_t)lstar_from_counts(cnt, prm.t);
-				if (prm.H != nullptr) {
-					store_row(prm.H, p, cnt);
+				if (live) {
+					prm.lstar[p] = (uint8_t)lstar_from_counts(cnt, prm.t);
+					if (prm.H != nullptr) {
+						store_row(prm.H, p, cnt);
+					}
 				}
 			}
 		}
@@ -488,13 +572,13 @@ int g_stream_sms = 0;
 
 cudaError_t x3k_stream_init_device(void)
 {
-	cudaError_t e = cudaFuncSetAttribute(x3_lcp_stream_kernel<4, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                                     (int)SCfg<4, 5>::SMEM);
+	cudaError_t e = cudaFuncSetAttribute(x3_lcp_stream_kernel<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                                     (int)SCfg<4, 6>::SMEM);
 	if (e != cudaSuccess) {
 		return e;
 	}
-	e = cudaFuncSetAttribute(x3_lcp_stream_kernel<8, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                         (int)SCfg<8, 8>::SMEM);
+	e = cudaFuncSetAttribute(x3_lcp_stream_kernel<8, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                         (int)SCfg<8, 15>::SMEM);
 	if (e != cudaSuccess) {
 		return e;
 	}
@@ -507,7 +591,7 @@ cudaError_t x3k_stream_init_device(void)
 	if (e != cudaSuccess) {
 		return e;
 	}
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, x3_lcp_stream_kernel<4, 5>, 32, SCfg<4, 5>::SMEM);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, x3_lcp_stream_kernel<4, 6>, 32, SCfg<4, 6>::SMEM);
 	if (e != cudaSuccess) {
 		return e;
 	}
@@ -537,9 +621,9 @@ cudaError_t x3k_launch_stream(bool full, X3SearchParams prm, cudaStream_t stream
 		return e;
 	}
 	if (full) {
-		x3_lcp_stream_kernel<8, 8><<<grid, 32, SCfg<8, 8>::SMEM, stream>>>(prm);
+		x3_lcp_stream_kernel<8, 15><<<grid, 32, SCfg<8, 15>::SMEM, stream>>>(prm);
 	} else {
-		x3_lcp_stream_kernel<4, 5><<<grid, 32, SCfg<4, 5>::SMEM, stream>>>(prm);
+		x3_lcp_stream_kernel<4, 6><<<grid, 32, SCfg<4, 6>::SMEM, stream>>>(prm);
 	}
 	return cudaGetLastError();
 }
