@@ -13,15 +13,16 @@
  *     (cp.async.bulk + mbarrier) and transposed into 8 bit-planes; one LOP3 then
  *     compares 32 byte pairs of one plane, 8 LOP3 give the match word
  *     E_d[w] = (x[p] == x[p+d]) for the 32 positions p of plane word w.
- *   - One warp = one independent worker (a 32-thread CTA, 8 resident per SM):
- *     no CTA-wide barrier exists in the search loop, so a warp that is busy with
- *     the rare-event path never stalls its neighbours, and the 2 warps that
- *     share an SM sub-partition fill each other's latency.
- *   - Distance d = 32 m + r.  For each r the warp materialises the window planes
- *     shifted by r bits once in shared memory (8 funnel shifts per plane word,
- *     amortised over all 62 position words), so the inner loop over m has no
- *     alignment shifts at all: 2 LDS.128 bring the next shifted word, which
- *     serves both position words of the thread.
+ *   - One warp = one independent worker (a 32-thread CTA with 17 KB of shared
+ *     memory, 12 resident per SM): no CTA-wide barrier exists in the search loop,
+ *     so a warp that is busy with the rare-event path never stalls its
+ *     neighbours, and the 3 warps that share an SM sub-partition fill each
+ *     other's latency.
+ *   - Distance d = 32 m + r.  For each r the warp keeps the window planes shifted
+ *     by r bits in shared memory; going from r to r+1 is one in-place 1-bit funnel
+ *     shift of the array (8 SHF per plane word, amortised over all 62 position
+ *     words), so the inner loop over m has no alignment shifts at all: 2 LDS.128
+ *     bring the next shifted word, which serves both position words of the thread.
  *   - Each lane owns 2 consecutive position words (64 positions): the match word
  *     of word 1 is the run continuation of word 0, the neighbour lane supplies
  *     the continuation of word 1 with one SHFL.  Lane 31 is a helper that owns
@@ -57,10 +58,9 @@ struct SCfg {
 	static constexpr int OWN = 62;                 /* position words per warp: 31 lanes x 2 */
 	static constexpr int NWORD = 64;               /* + the helper lane's two words */
 	static constexpr int P = OWN * 32;             /* positions per tile */
-	static constexpr int MCH = 128;                /* 32-distance blocks per window chunk */
+	static constexpr int MCH = 64;                 /* 32-distance blocks per window chunk */
 	static constexpr int NPW = NWORD + MCH + 1;    /* plane words staged per chunk */
-	static constexpr int NSR = NWORD + MCH;        /* shifted plane words per r */
-	static constexpr int SEG = (NPW + 1) / 2;      /* uint4 per (parity, half) segment of a plane array */
+	static constexpr int SEG = (NPW + 1) / 2;      /* uint4 per (parity, half) segment of the plane array */
 	static constexpr int NSH = HB == 6 ? 5 : 2;    /* LCP levels kept in the shared word: 3 .. 2+NSH (bits 0..29;
 	                                                * bit 31 flags a touched deep row) */
 	static constexpr int NDEEP = 30 - NSH;         /* LCP levels kept in the global row: 3+NSH .. 32 */
@@ -69,16 +69,15 @@ struct SCfg {
 	static constexpr uint32_t CAP = HB == 6 ? 16u : 255u;
 	static constexpr uint32_t FMASK = (1u << HB) - 1u;
 	static constexpr uint32_t DMASK = (1u << DBITS) - 1u;
-	static constexpr int QCAP = 24;                /* queue slots per lane */
+	static constexpr int QCAP = 16;                /* queue slots per lane; checked every 4 blocks */
+	static constexpr size_t QBYTES = (size_t)NPW * 32 > (size_t)QCAP * 256 ? (size_t)NPW * 32 : (size_t)QCAP * 256;
 
 	static constexpr size_t OFF_PW = 0;
-	static constexpr size_t OFF_SR = OFF_PW + (size_t)4 * SEG * 16; /* also the byte staging buffer */
-	static constexpr size_t OFF_HIST = OFF_SR + (size_t)4 * SEG * 16;
+	static constexpr size_t OFF_Q = OFF_PW + (size_t)4 * SEG * 16; /* queue; also the byte staging buffer */
+	static constexpr size_t OFF_HIST = OFF_Q + ((QBYTES + 127) / 128) * 128;
 	static constexpr size_t OFF_DONE = OFF_HIST + (size_t)64 * 32 * 4;
-	static constexpr size_t OFF_Q = OFF_DONE + (size_t)64 * 4;
-	static constexpr size_t OFF_BAR = OFF_Q + (size_t)QCAP * 32 * 8;
+	static constexpr size_t OFF_BAR = OFF_DONE + (size_t)64 * 4;
 	static constexpr size_t SMEM = OFF_BAR + 16;
-	static_assert((size_t)NPW * 32 <= (size_t)4 * SEG * 16, "staging buffer fits the SR array");
 	static_assert(NDEEP * DBITS <= ROWB * 8, "deep row holds every deep bin");
 };
 
@@ -366,9 +365,10 @@ __device__ __forceinline__ void st_group16(LaneState<CB> &st, const uint4 *sr, u
 		for (int j = 0; j < 8; ++j) {
 			S0[j] = S1[j];
 		}
-		if ((i & 7) == 7) {
-			/* 8 more blocks can push 8 entries at each end */
-			if (__any_sync(FULL_MASK, (int)(st.q1 - st.q0) < 256 * 15)) { /* signed: a full queue gives -256 */
+		if ((i & 3) == 3) {
+			/* 4 more blocks can push 4 entries at each end: flush when fewer than 8 slots are free
+			 * (signed compare: a full queue gives -256) */
+			if (__any_sync(FULL_MASK, (int)(st.q1 - st.q0) < 256 * 7)) {
 				st_flush<CB, HB>(st, q, hist, done_s, deep_tile, lane);
 			}
 		}
@@ -377,13 +377,12 @@ __device__ __forceinline__ void st_group16(LaneState<CB> &st, const uint4 *sr, u
 }
 
 template <int CB, int HB>
-__global__ void __launch_bounds__(32, 8) x3_lcp_stream_kernel(X3SearchParams prm)
+__global__ void __launch_bounds__(32, 12) x3_lcp_stream_kernel(X3SearchParams prm)
 {
 	using C = SCfg<CB, HB>;
 	extern __shared__ __align__(128) uint8_t smem[];
 	uint4 *pw = reinterpret_cast<uint4 *>(smem + C::OFF_PW);
-	uint4 *sr = reinterpret_cast<uint4 *>(smem + C::OFF_SR);
-	uint8_t *stage = smem + C::OFF_SR;
+	uint8_t *stage = smem + C::OFF_Q;
 	uint32_t *hist = reinterpret_cast<uint32_t *>(smem + C::OFF_HIST);
 	uint32_t *done_s = reinterpret_cast<uint32_t *>(smem + C::OFF_DONE);
 	uint2 *q = reinterpret_cast<uint2 *>(smem + C::OFF_Q);
@@ -428,7 +427,11 @@ __global__ void __launch_bounds__(32, 8) x3_lcp_stream_kernel(X3SearchParams prm
 		done_s[lane + 32] = 0;
 
 		for (uint32_t c = 0; c < nchunks; ++c) {
-			/* ---- stage the chunk's bytes and transpose them into bit-planes ---- */
+			/* ---- stage the chunk's bytes (into the drained queue's memory) and transpose them
+			 *      into bit-planes ---- */
+			if (c > 0) {
+				st_flush<CB, HB>(st, q, hist, done_s, deep_tile, lane);
+			}
 			__syncwarp();
 			if (lane == 0) {
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -470,29 +473,50 @@ __global__ void __launch_bounds__(32, 8) x3_lcp_stream_kernel(X3SearchParams prm
 				const int vlo = (c == 0 && r == 0) ? 1 : 0;
 				const long long hi = (long long)((D - (uint32_t)r) / 32) - (long long)C::MCH * c;
 				const int vhi = hi >= C::MCH ? C::MCH - 1 : (int)hi;
+				if (r > 0) {
+					/* ---- window planes: shift the whole array by one more bit, in place.  Word k
+					 *      takes its top bit from word k+1; ascending passes read a word before the
+					 *      pass that owns it rewrites it; the last word shifts in zeros. ---- */
+					for (int pass = 0; 64 * pass < C::NPW; ++pass) { /* uniform trip count: __syncwarp inside */
+						const int k2 = lane + 32 * pass;
+						uint32_t a[8], b[8], c2[8], s[8];
+						const bool hasa = 2 * k2 < C::NPW, hasb = 2 * k2 + 1 < C::NPW, hasc = 2 * k2 + 2 < C::NPW;
+#pragma unroll
+						for (int j = 0; j < 8; ++j) {
+							a[j] = 0;
+							b[j] = 0;
+							c2[j] = 0;
+						}
+						if (hasa) {
+							load_word<C::SEG>(pw, 2 * k2, a);
+						}
+						if (hasb) {
+							load_word<C::SEG>(pw, 2 * k2 + 1, b);
+						}
+						if (hasc) {
+							load_word<C::SEG>(pw, 2 * k2 + 2, c2);
+						}
+						__syncwarp();
+#pragma unroll
+						for (int j = 0; j < 8; ++j) {
+							s[j] = __funnelshift_r(a[j], b[j], 1);
+						}
+						if (hasa) {
+							store_word<C::SEG>(pw, 2 * k2, s);
+						}
+						if (hasb) {
+#pragma unroll
+							for (int j = 0; j < 8; ++j) {
+								s[j] = __funnelshift_r(b[j], c2[j], 1);
+							}
+							store_word<C::SEG>(pw, 2 * k2 + 1, s);
+						}
+					}
+					__syncwarp();
+				}
 				if (vhi < vlo) {
 					continue;
 				}
-				/* ---- window planes shifted by r bits ---- */
-				__syncwarp();
-				for (int k2 = lane; k2 < C::NSR / 2; k2 += 32) {
-					/* words 2*k2 and 2*k2+1: lanes touch contiguous uint4 of every segment */
-					uint32_t a[8], b[8], c2[8], s[8];
-					load_word<C::SEG>(pw, 2 * k2, a);
-					load_word<C::SEG>(pw, 2 * k2 + 1, b);
-					load_word<C::SEG>(pw, 2 * k2 + 2, c2);
-#pragma unroll
-					for (int j = 0; j < 8; ++j) {
-						s[j] = __funnelshift_r(a[j], b[j], r);
-					}
-					store_word<C::SEG>(sr, 2 * k2, s);
-#pragma unroll
-					for (int j = 0; j < 8; ++j) {
-						s[j] = __funnelshift_r(b[j], c2[j], r);
-					}
-					store_word<C::SEG>(sr, 2 * k2 + 1, s);
-				}
-				__syncwarp();
 
 				for (int g = 0; g < C::MCH / 16; ++g) {
 					const int mm0 = 16 * g;
@@ -500,9 +524,9 @@ __global__ void __launch_bounds__(32, 8) x3_lcp_stream_kernel(X3SearchParams prm
 						continue;
 					}
 					if (mm0 >= vlo && mm0 + 15 <= vhi) {
-						st_group16<CB, HB, false>(st, sr, q, hist, done_s, deep_tile, lane, wA, mm0, vlo, vhi);
+						st_group16<CB, HB, false>(st, pw, q, hist, done_s, deep_tile, lane, wA, mm0, vlo, vhi);
 					} else {
-						st_group16<CB, HB, true>(st, sr, q, hist, done_s, deep_tile, lane, wA, mm0, vlo, vhi);
+						st_group16<CB, HB, true>(st, pw, q, hist, done_s, deep_tile, lane, wA, mm0, vlo, vhi);
 					}
 				}
 			}
