@@ -347,11 +347,17 @@ def run_b200(args):
     algo_bytes = 2 * n + (W_BYTES - 2)      # 1 B read + 1 B written per position + halo
     achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
     pair_tests = n * D / (ms_per_step * 1e-3)
+    # ALU-pipe bound of the interior loop: 17.4 ALU-pipe warp instructions per
+    # 1024 pair tests, one per 2 cycles per SM sub-partition, at the SM clock seen under load
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    alu_bound = 148 * 4 * 1024 / (17.4 * 2.0) * sm_mhz * 1e6
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "x3_lcp_bitsliced_kernel",
+                "traffic": None, "peak_source": peak_src, "kernel": "x3_lcp_stream_kernel<4,6>",
                 "algorithmic_bytes_per_launch": algo_bytes,
-                "note": "integer-issue bound, not HBM bound (SURVEY.md 8(d)); see pair_tests_per_s",
-                "pair_tests_per_s": pair_tests}
+                "note": "2 B move per 8159 pair tests: the path is bound by the integer ALU pipe, not HBM "
+                        "(SURVEY.md 8(d)); alu_bound_frac = pair_tests_per_s / ALU-pipe bound of the loop",
+                "pair_tests_per_s": pair_tests, "alu_bound_pair_tests_per_s": alu_bound,
+                "alu_bound_frac": pair_tests / alu_bound}
     prof = ROOT / "profiles" / "traffic.json"
     if prof.exists():
         try:

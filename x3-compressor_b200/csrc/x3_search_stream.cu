@@ -64,8 +64,8 @@ struct SCfg {
 	static constexpr int NSH = HB == 6 ? 5 : 2;    /* LCP levels kept in the shared word: 3 .. 2+NSH (bits 0..29;
 	                                                * bit 31 flags a touched deep row) */
 	static constexpr int NDEEP = 30 - NSH;         /* LCP levels kept in the global row: 3+NSH .. 32 */
-	static constexpr int DBITS = HB == 6 ? 8 : 16; /* bits per deep bin */
-	static constexpr int ROWB = HB == 6 ? 32 : 64; /* bytes per deep row */
+	static constexpr int DBITS = 16;               /* bits per deep bin: never overflows while D <= 65535 */
+	static constexpr int ROWB = 64;                /* bytes per deep row */
 	static constexpr uint32_t CAP = HB == 6 ? 16u : 255u;
 	static constexpr uint32_t FMASK = (1u << HB) - 1u;
 	static constexpr uint32_t DMASK = (1u << DBITS) - 1u;
@@ -213,7 +213,7 @@ __device__ __forceinline__ void store_word(uint4 *base, int k, const uint32_t (&
  */
 template <int CB, int HB>
 __device__ __noinline__ void st_drain(const uint2 *q, uint32_t n0, uint32_t n1, uint32_t *hist, uint32_t *done_s,
-                                      uint8_t *deep_tile, int lane)
+                                      uint8_t *deep_tile, int lane, bool uncond)
 {
 	using C = SCfg<CB, HB>;
 	const uint32_t n = n0 + n1;
@@ -270,12 +270,24 @@ __device__ __noinline__ void st_drain(const uint2 *q, uint32_t n0, uint32_t n1, 
 					constexpr uint32_t PER = 32 / C::DBITS; /* bins per 32-bit word of the row */
 					unsigned int *rw = reinterpret_cast<unsigned int *>(deep_tile + (size_t)pos * C::ROWB) + k / PER;
 					const uint32_t sh = C::DBITS * (k % PER);
-					const uint32_t cv = (__ldcg(rw) >> sh) & C::DMASK;
-					if (cv < C::CAP) {
+					if (uncond && run != 32u) {
+						/* a 16-bit bin cannot overflow while D <= 65535: fire-and-forget reduction,
+						 * no L2 round trip on the critical path; the epilogue clamps */
 						atomicAdd(rw, 1u << sh);
-					}
-					if (run == 32u && cv + 1u >= C::CAP) {
-						atomicOr(&done_s[w], 1u << b); /* every level of this position is saturated */
+					} else if (uncond) {
+						/* LCP-32 bin: the returned count tells when every level is saturated */
+						const uint32_t cv = (atomicAdd(rw, 1u << sh) >> sh) & C::DMASK;
+						if (cv + 1u >= C::CAP) {
+							atomicOr(&done_s[w], 1u << b);
+						}
+					} else {
+						const uint32_t cv = (__ldcg(rw) >> sh) & C::DMASK;
+						if (cv < C::CAP) {
+							atomicAdd(rw, 1u << sh);
+						}
+						if (run == 32u && cv + 1u >= C::CAP) {
+							atomicOr(&done_s[w], 1u << b); /* every level of this position is saturated */
+						}
 					}
 				}
 			}
@@ -290,6 +302,7 @@ struct LaneState {
 	uint32_t A0[8], A1[8]; /* COMPLEMENTED planes of the two owned position words */
 	Tree<CB> T[4];         /* [word 0 L>=1, word 0 L>=2, word 1 L>=1, word 1 L>=2] */
 	uint2 done;
+	bool uncond;           /* D <= 65535: deep bins are added to without a bound check */
 	uint32_t q0, q1;       /* shared-space byte address of the next free slot of the word-0 queue (grows
 	                        * up) and of the word-1 queue (grows down) */
 };
@@ -303,7 +316,7 @@ __device__ __forceinline__ void st_flush(LaneState<CB> &st, uint2 *q, uint32_t *
 	const uint32_t n0 = (st.q0 - lo) / 256u;
 	const uint32_t n1 = (hi - st.q1) / 256u;
 	/* the helper lane owns no positions: its entries are dropped */
-	st_drain<CB, HB>(q, lane == 31 ? 0u : n0, lane == 31 ? 0u : n1, hist, done_s, deep_tile, lane);
+	st_drain<CB, HB>(q, lane == 31 ? 0u : n0, lane == 31 ? 0u : n1, hist, done_s, deep_tile, lane, st.uncond);
 	st.done = make_uint2(done_s[2 * lane], done_s[2 * lane + 1]);
 	st.q0 = lo;
 	st.q1 = hi;
@@ -418,6 +431,7 @@ __global__ void __launch_bounds__(32, 12) x3_lcp_stream_kernel(X3SearchParams pr
 			tree_clear(st.T[k]);
 		}
 		st.done = make_uint2(0, 0);
+		st.uncond = D <= 65535u;
 		st.q0 = smem_u32(q + lane);
 		st.q1 = smem_u32(q + (C::QCAP - 1) * 32 + lane);
 		for (int i = lane; i < 64 * 32; i += 32) {
