@@ -1,0 +1,392 @@
+/*
+ * x3_codec.c -- the parse loop and event model of x3 (reference x3.c:19-434) over
+ * the structures of x3_structs.c.  Same events, same probabilities (float32, same
+ * operand order, strict '>' tie order), same coded intervals: the stream is the
+ * reference's, bit for bit.
+ */
+#include "x3_host.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct x3_codec {
+	struct x3_dict *dict;
+	struct x3_ctxset *ctx0; /* previous two tags (via the tag-pair map), x3.c:19 */
+	struct x3_ctxset *ctx1; /* previous tag, x3.c:20 */
+	struct x3_pairmap *pairs;
+	struct x3_model events, match_size, chars, index1; /* x3.c:47-50 */
+	struct x3_ac ac;
+	struct x3_stats st;
+	int nl;
+};
+
+static struct x3_codec *g_codec = NULL; /* for the dictionary callbacks of the search backend */
+
+static float prob_to_bits(float prob)
+{
+	return -log2f(prob); /* x3.c:52-55 */
+}
+
+struct x3_codec *x3_codec_create(void)
+{
+	struct x3_codec *c = calloc(1, sizeof(*c));
+	if (c == NULL) {
+		abort();
+	}
+	c->dict = x3_dict_create();
+	c->ctx0 = x3_ctxset_create();
+	c->ctx1 = x3_ctxset_create();
+	c->pairs = x3_pairmap_create();
+	x3_model_create(&c->events, X3_E_LAST);
+	/* initial frequencies, x3.c:239-244 */
+	x3_model_set(&c->events, X3_E_CTX0, 1024);
+	x3_model_set(&c->events, X3_E_CTX1, 1024);
+	x3_model_set(&c->events, X3_E_IDX1, 1);
+	x3_model_set(&c->events, X3_E_NEW, 1);
+	x3_model_create(&c->match_size, X3_MAX_MATCH_LEN);
+	x3_model_create(&c->chars, 256);
+	x3_model_create(&c->index1, 0);
+	g_codec = c;
+	return c;
+}
+
+void x3_codec_destroy(struct x3_codec *c)
+{
+	if (g_codec == c) {
+		g_codec = NULL;
+	}
+	c->st.ctx0_entries = x3_pairmap_elems(c->pairs);
+	c->st.ctx1_entries = x3_dict_elems(c->dict);
+	x3_dict_destroy(c->dict);
+	x3_ctxset_destroy(c->ctx0);
+	x3_ctxset_destroy(c->ctx1);
+	x3_pairmap_destroy(c->pairs);
+	x3_model_destroy(&c->events);
+	x3_model_destroy(&c->match_size);
+	x3_model_destroy(&c->chars);
+	x3_model_destroy(&c->index1);
+	free(c);
+}
+
+void x3_codec_set_nl(struct x3_codec *c, int nl)
+{
+	c->nl = nl;
+}
+
+const struct x3_stats *x3_codec_stats(struct x3_codec *c)
+{
+	c->st.ctx0_entries = x3_pairmap_elems(c->pairs);
+	c->st.ctx1_entries = x3_dict_elems(c->dict);
+	return &c->st;
+}
+
+size_t x3_codec_dict_find(const char *p)
+{
+	const int64_t tag = x3_dict_find_match(g_codec->dict, (const uint8_t *)p);
+	return tag < 0 ? (size_t)-1 : (size_t)tag;
+}
+
+size_t x3_codec_dict_len(size_t handle)
+{
+	return x3_dict_len(g_codec->dict, (uint32_t)handle);
+}
+
+static size_t nl_len(const struct x3_codec *c, size_t len)
+{
+	if (c->nl != 0) { /* x3.c:357-370 */
+		switch (len - 1) {
+			case 0: return 1;
+			case 1: return 4;
+			case 2: return 6;
+			case 3: return 8;
+			default: return 9999;
+		}
+	}
+	return len;
+}
+
+static void enc_symbol(struct x3_codec *c, struct x3_bitw *w, struct x3_model *m, uint32_t sym)
+{
+	const uint64_t lo = x3_model_cum(m, sym);
+	x3_ac_encode(&c->ac, w, lo, lo + m->freq[sym], m->total);
+}
+
+static uint32_t dec_symbol(struct x3_codec *c, struct x3_bitr *r, struct x3_model *m)
+{
+	uint64_t step;
+	const uint64_t value = x3_ac_decode_target(&c->ac, m->total, &step);
+	const uint32_t sym = x3_model_find(m, value);
+	const uint64_t lo = x3_model_cum(m, sym);
+	x3_ac_decode_update(&c->ac, r, step, lo, lo + m->freq[sym]);
+	return sym;
+}
+
+/* contexts and tag pair update shared by encode_tag / decode_tag (x3.c:95-129,197-222) */
+static void update_contexts(struct x3_codec *c, uint32_t ctx0_id, uint32_t context1, uint32_t tag, int64_t item0,
+                            int64_t item1)
+{
+	if (item0 < 0) {
+		x3_ctx_add(c->ctx0, ctx0_id, tag);
+	} else {
+		x3_ctx_inc(c->ctx0, ctx0_id, (uint32_t)item0);
+	}
+	if (item1 < 0) {
+		x3_ctx_add(c->ctx1, context1, tag);
+	} else {
+		x3_ctx_inc(c->ctx1, context1, (uint32_t)item1);
+	}
+	/* (context1, tag) constitutes a new pair of tags */
+	if (x3_pairmap_query(c->pairs, context1, tag) < 0) {
+		const uint32_t id = x3_pairmap_add(c->pairs, context1, tag);
+		(void)x3_ctxset_get(c->ctx0, id); /* enlarge_ctx0 */
+	}
+}
+
+/* encode_tag, x3.c:132-223.  `tag` is the element, `index` its position in the
+ * cost-sorted dictionary at this moment. */
+static void encode_tag(struct x3_codec *c, struct x3_bitw *w, uint32_t prev_context1, uint32_t context1,
+                       uint32_t tag, uint32_t index)
+{
+	int64_t id = x3_pairmap_query(c->pairs, prev_context1, context1);
+	const uint32_t ctx0_id = id < 0 ? 0u : (uint32_t)id; /* x3.c:141-145 */
+
+	const int64_t item0 = x3_ctx_find(c->ctx0, ctx0_id, tag);
+	const int64_t item1 = x3_ctx_find(c->ctx1, context1, tag);
+	const struct x3_ctx *c0 = x3_ctxset_get(c->ctx0, ctx0_id);
+	const struct x3_ctx *c1 = x3_ctxset_get(c->ctx1, context1);
+
+	/* x3.c:152-160: float products, in this order */
+	float prob_ctx0 = 0;
+	if (item0 >= 0) {
+		prob_ctx0 = x3_model_prob(&c->events, X3_E_CTX0) * ((float)x3_ctx_freqs(c0)[item0] / (float)c0->total);
+	}
+	float prob_ctx1 = 0;
+	if (item1 >= 0) {
+		prob_ctx1 = x3_model_prob(&c->events, X3_E_CTX1) * ((float)x3_ctx_freqs(c1)[item1] / (float)c1->total);
+	}
+	const float prob_idx1 = x3_model_prob(&c->events, X3_E_IDX1) * x3_model_prob(&c->index1, index);
+
+	int mode = X3_E_IDX1;
+	float prob = prob_idx1;
+	if (prob_ctx0 > prob) {
+		mode = X3_E_CTX0;
+		prob = prob_ctx0;
+	}
+	if (prob_ctx1 > prob) {
+		mode = X3_E_CTX1;
+		prob = prob_ctx1;
+	}
+
+	enc_symbol(c, w, &c->events, (uint32_t)mode);
+	x3_model_inc(&c->events, (uint32_t)mode);
+
+	switch (mode) {
+		case X3_E_CTX0: {
+			const uint64_t lo = x3_ctx_cum(c0, (uint32_t)item0);
+			x3_ac_encode(&c->ac, w, lo, lo + x3_ctx_freqs(c0)[item0], c0->total);
+			break;
+		}
+		case X3_E_CTX1: {
+			const uint64_t lo = x3_ctx_cum(c1, (uint32_t)item1);
+			x3_ac_encode(&c->ac, w, lo, lo + x3_ctx_freqs(c1)[item1], c1->total);
+			break;
+		}
+		default:
+			enc_symbol(c, w, &c->index1, index);
+			x3_model_inc(&c->index1, index);
+			break;
+	}
+
+	c->st.events[mode]++;
+	c->st.sizes[mode] += prob_to_bits(prob);
+
+	update_contexts(c, ctx0_id, context1, tag, item0, item1);
+}
+
+/* encode_match, x3.c:251-270 */
+static void encode_match(struct x3_codec *c, struct x3_bitw *w, const uint8_t *p, size_t len)
+{
+	c->st.sizes[X3_E_NEW] += prob_to_bits(x3_model_prob(&c->events, X3_E_NEW));
+	enc_symbol(c, w, &c->events, X3_E_NEW);
+	x3_model_inc(&c->events, X3_E_NEW);
+
+	c->st.sizes[X3_E_NEW] += prob_to_bits(x3_model_prob(&c->match_size, (uint32_t)(len - 1)));
+	enc_symbol(c, w, &c->match_size, (uint32_t)(len - 1));
+	x3_model_inc(&c->match_size, (uint32_t)(len - 1));
+
+	for (size_t k = 0; k < len; ++k) {
+		c->st.sizes[X3_E_NEW] += prob_to_bits(x3_model_prob(&c->chars, p[k]));
+		enc_symbol(c, w, &c->chars, p[k]);
+		x3_model_inc(&c->chars, p[k]);
+	}
+	c->st.events[X3_E_NEW]++;
+}
+
+void *x3_compress(struct x3_codec *c, char *base, size_t isize, x3_fbm_fn fbm, size_t *out_bytes)
+{
+	struct x3_bitw w;
+	x3_bitw_open(&w, isize / 2 + 64);
+	x3_ac_init(&c->ac);
+	g_codec = c;
+
+	uint8_t *ptr = (uint8_t *)base;
+	uint8_t *end = ptr + isize;
+	uint32_t prev_context1 = 0, context1 = 0; /* x3.c:376-377 */
+
+	for (uint8_t *p = ptr; p < end;) {
+		/* (1) look into the dictionary, x3.c:381-383.  find_best_match() is a pure function of
+		 * (p, dictionary state); the reference evaluates it lazily and possibly twice. */
+		const int64_t tag = x3_dict_find_match(c->dict, p);
+		size_t best = 0;
+		int hit = 0;
+		if (tag >= 0) {
+			const size_t dl = x3_dict_len(c->dict, (uint32_t)tag);
+			best = fbm((char *)p);
+			hit = nl_len(c, dl) >= best && p + dl <= end;
+		}
+		if (hit) {
+			const uint32_t len = x3_dict_len(c->dict, (uint32_t)tag);
+			const uint32_t index = x3_dict_index_of(c->dict, (uint32_t)tag);
+			encode_tag(c, &w, prev_context1, context1, (uint32_t)tag, index);
+			prev_context1 = context1;
+			context1 = (uint32_t)tag; /* dict_get_tag_by_index */
+			x3_dict_touch(c->dict, (uint32_t)tag); /* dict_set_last_pos + dict_update_costs */
+			p += len;
+		} else {
+			/* (2) new fragment, x3.c:399-428 */
+			size_t len = tag >= 0 ? best : fbm((char *)p);
+			if (p + len > end) {
+				len = (size_t)(end - p);
+			}
+			encode_match(c, &w, p, len);
+			if (!x3_dict_query(c->dict, p, (uint32_t)len)) {
+				x3_dict_insert(c->dict, p, (uint32_t)len);
+				(void)x3_ctxset_get(c->ctx1, x3_dict_elems(c->dict) - 1); /* enlarge_ctx1 */
+				x3_model_append(&c->index1);
+			}
+			p += len;
+			prev_context1 = 0;
+			context1 = 0;
+		}
+	}
+
+	/* signal end of input, x3.c:431-433 */
+	enc_symbol(c, &w, &c->events, X3_E_EOF);
+	x3_model_inc(&c->events, X3_E_EOF);
+
+	x3_ac_encode_flush(&c->ac, &w); /* x3.c:603 */
+	*out_bytes = x3_bitw_close(&w); /* x3.c:604 */
+	return w.buf;
+}
+
+/* decode_tag, x3.c:58-129: returns the element (tag) */
+static uint32_t decode_tag(struct x3_codec *c, struct x3_bitr *r, uint32_t decision, uint32_t prev_context1,
+                           uint32_t context1)
+{
+	int64_t id = x3_pairmap_query(c->pairs, prev_context1, context1);
+	const uint32_t ctx0_id = id < 0 ? 0u : (uint32_t)id;
+	const struct x3_ctx *c0 = x3_ctxset_get(c->ctx0, ctx0_id);
+	const struct x3_ctx *c1 = x3_ctxset_get(c->ctx1, context1);
+
+	uint32_t tag;
+	float size;
+	switch (decision) {
+		case X3_E_CTX0:
+		case X3_E_CTX1: {
+			const struct x3_ctx *cx = decision == X3_E_CTX0 ? c0 : c1;
+			if (cx->items == 0 || cx->total == 0) {
+				abort();
+			}
+			uint64_t step, lo;
+			const uint64_t value = x3_ac_decode_target(&c->ac, cx->total, &step);
+			const uint32_t item = x3_ctx_find_value(cx, value, &lo);
+			x3_ac_decode_update(&c->ac, r, step, lo, lo + x3_ctx_freqs(cx)[item]);
+			tag = x3_ctx_tags(cx)[item];
+			size = prob_to_bits((float)x3_ctx_freqs(cx)[item] / (float)cx->total);
+			break;
+		}
+		case X3_E_IDX1: {
+			if (c->index1.n == 0) {
+				abort();
+			}
+			const uint32_t index = dec_symbol(c, r, &c->index1);
+			size = prob_to_bits(x3_model_prob(&c->index1, index));
+			x3_model_inc(&c->index1, index);
+			tag = x3_dict_tag_at(c->dict, index);
+			break;
+		}
+		default:
+			abort();
+	}
+	c->st.events[decision]++;
+	c->st.sizes[decision] += size;
+
+	const int64_t item0 = x3_ctx_find(c->ctx0, ctx0_id, tag);
+	const int64_t item1 = x3_ctx_find(c->ctx1, context1, tag);
+	update_contexts(c, ctx0_id, context1, tag, item0, item1);
+	return tag;
+}
+
+void *x3_decompress(struct x3_codec *c, const void *stream, size_t bytes, size_t *out_bytes)
+{
+	struct x3_bitr r;
+	x3_bitr_open(&r, stream, bytes);
+	x3_ac_init(&c->ac);
+	x3_ac_decode_init(&c->ac, &r);
+	g_codec = c;
+
+	size_t cap = bytes * 4 + 4096, n = 0;
+	uint8_t *out = malloc(cap);
+	if (out == NULL) {
+		abort();
+	}
+	uint32_t prev_context1 = 0, context1 = 0;
+
+	for (;;) {
+		const uint32_t decision = dec_symbol(c, &r, &c->events);
+		c->st.sizes[decision] += prob_to_bits(x3_model_prob(&c->events, decision));
+		x3_model_inc(&c->events, decision);
+
+		if (n + X3_MAX_MATCH_LEN > cap) {
+			cap *= 2;
+			out = realloc(out, cap);
+			if (out == NULL) {
+				abort();
+			}
+		}
+		if (decision == X3_E_EOF) {
+			break;
+		} else if (decision == X3_E_NEW) {
+			/* decode_match, x3.c:272-283 */
+			const uint32_t len = dec_symbol(c, &r, &c->match_size) + 1;
+			c->st.sizes[X3_E_NEW] += prob_to_bits(x3_model_prob(&c->match_size, len - 1));
+			x3_model_inc(&c->match_size, len - 1);
+			for (uint32_t k = 0; k < len; ++k) {
+				const uint32_t ch = dec_symbol(c, &r, &c->chars);
+				out[n + k] = (uint8_t)ch;
+				c->st.sizes[X3_E_NEW] += prob_to_bits(x3_model_prob(&c->chars, ch));
+				x3_model_inc(&c->chars, ch);
+			}
+			if (!x3_dict_query(c->dict, out + n, len)) {
+				x3_dict_insert(c->dict, out + n, len);
+				(void)x3_ctxset_get(c->ctx1, x3_dict_elems(c->dict) - 1);
+				x3_model_append(&c->index1);
+			}
+			n += len;
+			prev_context1 = 0;
+			context1 = 0;
+			c->st.events[X3_E_NEW]++;
+		} else {
+			const uint32_t tag = decode_tag(c, &r, decision, prev_context1, context1);
+			const uint32_t len = x3_dict_len(c->dict, tag);
+			prev_context1 = context1;
+			context1 = tag;
+			memcpy(out + n, x3_dict_str(c->dict, tag), len);
+			x3_dict_touch(c->dict, tag);
+			n += len;
+		}
+	}
+	*out_bytes = n;
+	return out;
+}
