@@ -200,7 +200,15 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 	if (x == nullptr || (lstar == nullptr && n > 0)) {
 		return fail(X3S_ERR_ARG, "null host pointer");
 	}
+	const bool trace = getenv("X3_TRACE") != nullptr;
+	auto lap = [&](const char *what) {
+		if (trace) {
+			fprintf(stderr, "x3s_search_host: %-28s +%.3f ms\n", what,
+			        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
+		}
+	};
 	const int nvis = x3s_device_count();
+	lap("device count (cuInit)");
 	if (nvis <= 0) {
 		return fail(X3S_ERR_CUDA, "no CUDA device visible (the search has no CPU fallback)");
 	}
@@ -233,7 +241,9 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 			continue;
 		}
 		CU_TRY(cudaSetDevice(dev));
+		lap("cudaSetDevice");
 		rc = ensure_kernel_init(dev);
+		lap("kernel init + scratch");
 		if (rc != X3S_OK) {
 			return rc;
 		}
@@ -264,6 +274,7 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 		if (a[g] + have > total) {
 			have = total - a[g];
 		}
+		lap("buffers");
 		CU_TRY(cudaEventRecord(ds.ev[0], ds.stream));
 		CU_TRY(cudaMemcpyAsync(ds.d_x, (const uint8_t *)x + a[g], have, cudaMemcpyHostToDevice, ds.stream));
 		if (need > have) {
@@ -310,6 +321,7 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 		CU_TRY(cudaEventElapsedTime(&ms, ds.ev[2], ds.ev[3]));
 		if (ms > tm.d2h_ms) tm.d2h_ms = ms;
 	}
+	lap("done");
 	tm.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
 	if (timing != nullptr) {
 		*timing = tm;
