@@ -51,6 +51,9 @@
  */
 #include "x3_search_device.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace {
 
 template <int CB, int HB>
@@ -58,9 +61,10 @@ struct SCfg {
 	static constexpr int OWN = 62;                 /* position words per warp: 31 lanes x 2 */
 	static constexpr int NWORD = 64;               /* + the helper lane's two words */
 	static constexpr int P = OWN * 32;             /* positions per tile */
-	static constexpr int MCH = 64;                 /* 32-distance blocks per window chunk */
+	static constexpr int MCH = 48;                 /* 32-distance blocks per window chunk (3 groups of 16) */
 	static constexpr int NPW = NWORD + MCH + 1;    /* plane words staged per chunk */
-	static constexpr int SEG = (NPW + 1) / 2;      /* uint4 per (parity, half) segment of the plane array */
+	static constexpr int SEG0 = (NPW + 1) / 2;     /* uint4 per (even word, half) segment of the plane array */
+	static constexpr int SEG1 = NPW / 2;           /* uint4 per (odd word, half) segment */
 	static constexpr int NSH = HB == 6 ? 5 : 2;    /* LCP levels kept in the shared word: 3 .. 2+NSH (bits 0..29;
 	                                                * bit 31 flags a touched deep row) */
 	static constexpr int NDEEP = 30 - NSH;         /* LCP levels kept in the global row: 3+NSH .. 32 */
@@ -70,14 +74,20 @@ struct SCfg {
 	static constexpr uint32_t FMASK = (1u << HB) - 1u;
 	static constexpr uint32_t DMASK = (1u << DBITS) - 1u;
 	static constexpr int QCAP = 16;                /* queue slots per lane; checked every 4 blocks */
-	static constexpr size_t QBYTES = (size_t)NPW * 32 > (size_t)QCAP * 256 ? (size_t)NPW * 32 : (size_t)QCAP * 256;
 
+	/* 16 896 bytes: 13 CTAs (warps) per SM (shared memory is granted in 256-byte units on top
+	 * of 1 KB per CTA) */
 	static constexpr size_t OFF_PW = 0;
-	static constexpr size_t OFF_Q = OFF_PW + (size_t)4 * SEG * 16; /* queue; also the byte staging buffer */
-	static constexpr size_t OFF_HIST = OFF_Q + ((QBYTES + 127) / 128) * 128;
-	static constexpr size_t OFF_DONE = OFF_HIST + (size_t)64 * 32 * 4;
-	static constexpr size_t OFF_BAR = OFF_DONE + (size_t)64 * 4;
-	static constexpr size_t SMEM = OFF_BAR + 16;
+	static constexpr size_t OFF_Q = OFF_PW + (size_t)2 * (SEG0 + SEG1) * 16; /* queue; also the byte staging buffer */
+	static constexpr size_t OFF_HIST = OFF_Q + (size_t)QCAP * 256;
+	static constexpr size_t OFF_TAB = OFF_HIST + (size_t)62 * 32 * 4;  /* drain index table, 31 * QCAP entries */
+	static constexpr size_t OFF_DONE = OFF_TAB + (size_t)31 * QCAP * 2;
+	static constexpr size_t OFF_BAR = OFF_DONE + (size_t)62 * 4;
+	static constexpr size_t SMEM = OFF_BAR + 8;
+	static_assert((size_t)NPW * 32 <= (size_t)QCAP * 256, "staging buffer fits the drained queue");
+	static_assert(MCH % 16 == 0, "whole groups of 16 blocks");
+	static_assert(SMEM <= 16896, "13 CTAs per SM");
+	static_assert(OFF_Q % 16 == 0 && OFF_BAR % 8 == 0, "alignment");
 	static_assert(NDEEP * DBITS <= ROWB * 8, "deep row holds every deep bin");
 };
 
@@ -177,43 +187,77 @@ __device__ __forceinline__ void sts64(uint32_t addr, uint32_t a, uint32_t b)
 	asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b));
 }
 
-/* Plane arrays in shared memory: word k, half h (planes 0-3 / 4-7) lives at
- * uint4 index ((k & 1) * 2 + h) * SEG + (k >> 1). */
-template <int SEG>
-__device__ __forceinline__ int pidx(int k, int h)
+/* 8 bytes (a: bytes 0..3, b: bytes 4..7) -> plo: byte j = bit j of the 8 bytes (byte i -> bit i),
+ * j = 0..3, phi: the same for j = 4..7. */
+__device__ __forceinline__ void transpose8x8(uint32_t a, uint32_t b, uint32_t &plo, uint32_t &phi)
 {
-	return ((k & 1) * 2 + h) * SEG + (k >> 1);
+	uint32_t x = b, y = a, t;
+	t = (x ^ (x >> 7)) & 0x00AA00AAu;  x = x ^ t ^ (t << 7);
+	t = (y ^ (y >> 7)) & 0x00AA00AAu;  y = y ^ t ^ (t << 7);
+	t = (x ^ (x >> 14)) & 0x0000CCCCu; x = x ^ t ^ (t << 14);
+	t = (y ^ (y >> 14)) & 0x0000CCCCu; y = y ^ t ^ (t << 14);
+	t = (x & 0xF0F0F0F0u) | ((y >> 4) & 0x0F0F0F0Fu);
+	y = ((x << 4) & 0xF0F0F0F0u) | (y & 0x0F0F0F0Fu);
+	plo = y;
+	phi = t;
 }
 
-template <int SEG>
+/* p[g] byte j -> out_j byte g */
+__device__ __forceinline__ void bytes4x4(const uint32_t (&p)[4], uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3)
+{
+	const uint32_t u0 = __byte_perm(p[0], p[1], 0x5140), u1 = __byte_perm(p[2], p[3], 0x5140);
+	const uint32_t u2 = __byte_perm(p[0], p[1], 0x7362), u3 = __byte_perm(p[2], p[3], 0x7362);
+	o0 = __byte_perm(u0, u1, 0x5410);
+	o1 = __byte_perm(u0, u1, 0x7632);
+	o2 = __byte_perm(u2, u3, 0x5410);
+	o3 = __byte_perm(u2, u3, 0x7632);
+}
+
+/* Plane array in shared memory, split by word parity and plane half so that lanes owning
+ * words 2*lane, 2*lane+1 read contiguous uint4: word k, half h (planes 0-3 / 4-7) lives at
+ * uint4 index segbase(k & 1, h) + (k >> 1). */
+template <class C>
+__device__ __forceinline__ constexpr int segbase(int par, int h)
+{
+	return par == 0 ? h * C::SEG0 : 2 * C::SEG0 + h * C::SEG1;
+}
+
+template <class C>
+__device__ __forceinline__ int pidx(int k, int h)
+{
+	return segbase<C>(k & 1, h) + (k >> 1);
+}
+
+template <class C>
 __device__ __forceinline__ void load_word(const uint4 *base, int k, uint32_t (&w)[8])
 {
-	const uint4 lo = base[pidx<SEG>(k, 0)], hi = base[pidx<SEG>(k, 1)];
+	const uint4 lo = base[pidx<C>(k, 0)], hi = base[pidx<C>(k, 1)];
 	w[0] = lo.x; w[1] = lo.y; w[2] = lo.z; w[3] = lo.w;
 	w[4] = hi.x; w[5] = hi.y; w[6] = hi.z; w[7] = hi.w;
 }
 
-template <int SEG>
+template <class C>
 __device__ __forceinline__ void store_word(uint4 *base, int k, const uint32_t (&w)[8])
 {
-	base[pidx<SEG>(k, 0)] = make_uint4(w[0], w[1], w[2], w[3]);
-	base[pidx<SEG>(k, 1)] = make_uint4(w[4], w[5], w[6], w[7]);
+	base[pidx<C>(k, 0)] = make_uint4(w[0], w[1], w[2], w[3]);
+	base[pidx<C>(k, 1)] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
 /*
  * Cooperative drain.  Lane l holds n0 word-0 entries (slots 0 .. n0-1) and n1 word-1
- * entries (slots QCAP-1 .. QCAP-n1) of (E, E_next) match words.  Entries are numbered
- * globally by an exclusive prefix sum over lanes and dealt out 32 at a time, so every
- * lane gets the same number of entries no matter how skewed the queues are; the owner
- * of a global index is found by a 5-step search over the prefix sums with SHFL.  Each
- * set bit of the entry's LCP>=3 word is one event: an atomic add into the exact-LCP
- * bin of that position (several lanes may hit the same position).  Bins may overshoot
- * the cap by at most 31 (one add in flight per lane), which the field widths absorb
- * and the epilogue clamps.
+ * entries (slots QCAP-1 .. QCAP-n1) of (E, E_next) match words.  The queues are very
+ * uneven (frequent trigrams) and so are the numbers of events per entry, so the work
+ * is dealt out dynamically: entries are numbered by an exclusive prefix sum over lanes
+ * and listed in a small index table; in every iteration of the loop each idle lane
+ * takes the next unclaimed entry (ballot + popc on a warp-uniform cursor) and every
+ * lane retires ONE event of the entry it holds.  An event is one set bit of the
+ * entry's LCP>=3 word: an atomic add into the exact-LCP bin of that position (several
+ * lanes may hit the same position).  Bins may overshoot the cap by at most 31 (one add
+ * in flight per lane), which the field widths absorb and the epilogue clamps.
  */
 template <int CB, int HB>
 __device__ __noinline__ void st_drain(const uint2 *q, uint32_t n0, uint32_t n1, uint32_t *hist, uint32_t *done_s,
-                                      uint8_t *deep_tile, int lane, bool uncond)
+                                      uint16_t *tab, uint8_t *deep_tile, int lane, bool uncond)
 {
 	using C = SCfg<CB, HB>;
 	const uint32_t n = n0 + n1;
@@ -227,67 +271,92 @@ __device__ __noinline__ void st_drain(const uint2 *q, uint32_t n0, uint32_t n1, 
 	}
 	const uint32_t excl = inc - n;
 	const uint32_t E = __shfl_sync(FULL_MASK, inc, 31);
+	if (E == 0) {
+		return;
+	}
+	/* index table: entry number -> (word j, queue address slot * 32 + owner lane) */
+	for (uint32_t s = 0; s < n; ++s) {
+		const uint32_t j = s >= n0 ? 1u : 0u;
+		const uint32_t slot = j ? (uint32_t)C::QCAP - 1u - (s - n0) : s;
+		tab[excl + s] = (uint16_t)((j << 9) | (slot * 32u + (uint32_t)lane));
+	}
+	__syncwarp();
 
-	for (uint32_t base = 0; base < E; base += 32) {
-		const uint32_t idx = base + lane;
-		/* last lane o with excl[o] <= idx (empty lanes tie with their successor and lose) */
-		int o = 0;
-#pragma unroll
-		for (int step = 16; step > 0; step >>= 1) {
-			const int cand = o + step;
-			const uint32_t ex = __shfl_sync(FULL_MASK, excl, cand & 31);
-			if (ex <= idx) {
-				o = cand;
+	const uint32_t lt = (1u << lane) - 1u;
+	uint32_t cursor = 0; /* warp-uniform: entries claimed so far */
+	uint32_t R = 0, e = 0, eh = 0, w = 0;
+	for (;;) {
+		const bool need = R == 0;
+		const uint32_t nmask = __ballot_sync(FULL_MASK, need);
+		if (nmask == FULL_MASK && cursor >= E) {
+			break;
+		}
+		if (need) {
+			const uint32_t idx = cursor + __popc(nmask & lt);
+			if (idx < E) {
+				const uint32_t t = tab[idx];
+				const uint2 en = q[t & 511u];
+				w = 2u * (t & 31u) + (t >> 9);
+				e = en.x;
+				eh = en.y;
+				R = e & __funnelshift_r(e, eh, 1) & __funnelshift_r(e, eh, 2) & ~done_s[w];
 			}
 		}
-		const uint32_t exo = __shfl_sync(FULL_MASK, excl, o);
-		const uint32_t n0o = __shfl_sync(FULL_MASK, n0, o);
-		if (idx < E) {
-			const uint32_t s = idx - exo;
-			const uint32_t j = s >= n0o ? 1u : 0u;
-			const uint32_t slot = j ? (uint32_t)C::QCAP - 1u - (s - n0o) : s;
-			const uint2 en = q[slot * 32 + o];
-			const uint32_t e = en.x, eh = en.y;
-			const uint32_t w = 2u * (uint32_t)o + j;
-			uint32_t R = e & __funnelshift_r(e, eh, 1) & __funnelshift_r(e, eh, 2) & ~done_s[w];
-			while (R != 0) {
-				const int b = __ffs(R) - 1;
-				R &= R - 1;
-				const uint32_t v = __funnelshift_r(e, eh, b);
+		cursor += __popc(nmask);
+		if (R != 0) {
+			/* one event: highest set bit b; v = the pair's bits from b upwards (bits 0..2 are set) */
+			const int cz = __clz(R);
+			const int b = 31 - cz;
+			R &= ~(0x80000000u >> cz);
+			const uint32_t v = __funnelshift_r(e, eh, b);
+			const uint32_t pos = w * 32u + (uint32_t)b;
+			const uint32_t word = hist[pos];
+			/* zeros among bits 3 .. 2+NSH of v: the lowest one marks the run length */
+			const uint32_t y = ~(v >> 3) & ((1u << C::NSH) - 1u);
+			if (y != 0) {
+				uint32_t inc;
+				bool full;
+				if (HB == 6) {
+					/* run - 3 = log2(z) for the one-hot z; the field increment 1 << 6 (run - 3) is z^6,
+					 * computed by 3 multiplies on the FMA pipe (FLO/POPC share the slow XU pipe) */
+					const uint32_t z = y & (0u - y);
+					const uint32_t z3 = z * z * z;
+					inc = z3 * z3;
+					full = (word & (inc * 48u)) != 0; /* bits 4 and 5 of the field: value >= 16 */
+				} else {
+					const uint32_t sh = HB * (uint32_t)(__ffs(y) - 1);
+					inc = 1u << sh;
+					full = ((word >> sh) & C::FMASK) >= C::CAP;
+				}
+				if (!full) {
+					atomicAdd(&hist[pos], inc);
+				}
+			} else {
 				const uint32_t run = (v == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~v) - 1);
-				const uint32_t pos = w * 32u + (uint32_t)b;
-				const uint32_t word = hist[pos];
-				if (run < 3u + C::NSH) {
-					const uint32_t sh = HB * (run - 3u);
-					if (((word >> sh) & C::FMASK) < C::CAP) {
-						atomicAdd(&hist[pos], 1u << sh);
+				if ((word >> 31) == 0) {
+					atomicOr(&hist[pos], 0x80000000u); /* row touched */
+				}
+				const uint32_t k = run - (3u + C::NSH);
+				constexpr uint32_t PER = 32 / C::DBITS; /* bins per 32-bit word of the row */
+				unsigned int *rw = reinterpret_cast<unsigned int *>(deep_tile + (size_t)pos * C::ROWB) + k / PER;
+				const uint32_t sh = C::DBITS * (k % PER);
+				if (uncond && run != 32u) {
+					/* a 16-bit bin cannot overflow while D <= 65535: fire-and-forget reduction, no
+					 * L2 round trip on the critical path; the epilogue clamps */
+					atomicAdd(rw, 1u << sh);
+				} else if (uncond) {
+					/* LCP-32 bin: the returned count tells when every level is saturated */
+					const uint32_t cv = (atomicAdd(rw, 1u << sh) >> sh) & C::DMASK;
+					if (cv + 1u >= C::CAP) {
+						atomicOr(&done_s[w], 1u << b);
 					}
 				} else {
-					if ((word >> 31) == 0) {
-						atomicOr(&hist[pos], 0x80000000u); /* row touched */
-					}
-					const uint32_t k = run - (3u + C::NSH);
-					constexpr uint32_t PER = 32 / C::DBITS; /* bins per 32-bit word of the row */
-					unsigned int *rw = reinterpret_cast<unsigned int *>(deep_tile + (size_t)pos * C::ROWB) + k / PER;
-					const uint32_t sh = C::DBITS * (k % PER);
-					if (uncond && run != 32u) {
-						/* a 16-bit bin cannot overflow while D <= 65535: fire-and-forget reduction,
-						 * no L2 round trip on the critical path; the epilogue clamps */
+					const uint32_t cv = (__ldcg(rw) >> sh) & C::DMASK;
+					if (cv < C::CAP) {
 						atomicAdd(rw, 1u << sh);
-					} else if (uncond) {
-						/* LCP-32 bin: the returned count tells when every level is saturated */
-						const uint32_t cv = (atomicAdd(rw, 1u << sh) >> sh) & C::DMASK;
-						if (cv + 1u >= C::CAP) {
-							atomicOr(&done_s[w], 1u << b);
-						}
-					} else {
-						const uint32_t cv = (__ldcg(rw) >> sh) & C::DMASK;
-						if (cv < C::CAP) {
-							atomicAdd(rw, 1u << sh);
-						}
-						if (run == 32u && cv + 1u >= C::CAP) {
-							atomicOr(&done_s[w], 1u << b); /* every level of this position is saturated */
-						}
+					}
+					if (run == 32u && cv + 1u >= C::CAP) {
+						atomicOr(&done_s[w], 1u << b); /* every level of this position is saturated */
 					}
 				}
 			}
@@ -311,13 +380,16 @@ template <int CB, int HB>
 __device__ __forceinline__ void st_flush(LaneState<CB> &st, uint2 *q, uint32_t *hist, uint32_t *done_s,
                                          uint8_t *deep_tile, int lane)
 {
+	uint16_t *tab = reinterpret_cast<uint16_t *>(hist + 62 * 32); /* OFF_TAB follows the histograms */
 	using C = SCfg<CB, HB>;
 	const uint32_t lo = smem_u32(q + lane), hi = smem_u32(q + (C::QCAP - 1) * 32 + lane);
 	const uint32_t n0 = (st.q0 - lo) / 256u;
 	const uint32_t n1 = (hi - st.q1) / 256u;
 	/* the helper lane owns no positions: its entries are dropped */
-	st_drain<CB, HB>(q, lane == 31 ? 0u : n0, lane == 31 ? 0u : n1, hist, done_s, deep_tile, lane, st.uncond);
-	st.done = make_uint2(done_s[2 * lane], done_s[2 * lane + 1]);
+	st_drain<CB, HB>(q, lane == 31 ? 0u : n0, lane == 31 ? 0u : n1, hist, done_s, tab, deep_tile, lane, st.uncond);
+	if (lane != 31) {
+		st.done = make_uint2(done_s[2 * lane], done_s[2 * lane + 1]);
+	}
 	st.q0 = lo;
 	st.q1 = hi;
 }
@@ -337,7 +409,7 @@ __device__ __forceinline__ void st_group16(LaneState<CB> &st, const uint4 *sr, u
 	 * compile-time constant after unrolling, and the 32 lanes read contiguous uint4 */
 	const uint4 *srl = sr + lane + (mm0 >> 1);
 	{
-		const uint4 lo = srl[0 * C::SEG], hi = srl[1 * C::SEG]; /* word wA + mm0: even */
+		const uint4 lo = srl[segbase<C>(0, 0)], hi = srl[segbase<C>(0, 1)]; /* word wA + mm0: even */
 		S0[0] = lo.x; S0[1] = lo.y; S0[2] = lo.z; S0[3] = lo.w;
 		S0[4] = hi.x; S0[5] = hi.y; S0[6] = hi.z; S0[7] = hi.w;
 	}
@@ -346,7 +418,7 @@ __device__ __forceinline__ void st_group16(LaneState<CB> &st, const uint4 *sr, u
 		{
 			/* word wA + 1 + mm0 + i */
 			const int par = (1 + i) & 1, off = (1 + i) >> 1;
-			const uint4 lo = srl[(par * 2 + 0) * C::SEG + off], hi = srl[(par * 2 + 1) * C::SEG + off];
+			const uint4 lo = srl[segbase<C>(par, 0) + off], hi = srl[segbase<C>(par, 1) + off];
 			S1[0] = lo.x; S1[1] = lo.y; S1[2] = lo.z; S1[3] = lo.w;
 			S1[4] = hi.x; S1[5] = hi.y; S1[6] = hi.z; S1[7] = hi.w;
 		}
@@ -390,7 +462,7 @@ __device__ __forceinline__ void st_group16(LaneState<CB> &st, const uint4 *sr, u
 }
 
 template <int CB, int HB>
-__global__ void __launch_bounds__(32, 12) x3_lcp_stream_kernel(X3SearchParams prm)
+__global__ void __launch_bounds__(32, 13) x3_lcp_stream_kernel(X3SearchParams prm)
 {
 	using C = SCfg<CB, HB>;
 	extern __shared__ __align__(128) uint8_t smem[];
@@ -434,11 +506,13 @@ __global__ void __launch_bounds__(32, 12) x3_lcp_stream_kernel(X3SearchParams pr
 		st.uncond = D <= 65535u;
 		st.q0 = smem_u32(q + lane);
 		st.q1 = smem_u32(q + (C::QCAP - 1) * 32 + lane);
-		for (int i = lane; i < 64 * 32; i += 32) {
+		for (int i = lane; i < 62 * 32; i += 32) {
 			hist[i] = 0;
 		}
 		done_s[lane] = 0;
-		done_s[lane + 32] = 0;
+		if (lane + 32 < 62) {
+			done_s[lane + 32] = 0;
+		}
 
 		for (uint32_t c = 0; c < nchunks; ++c) {
 			/* ---- stage the chunk's bytes (into the drained queue's memory) and transpose them
@@ -454,24 +528,26 @@ __global__ void __launch_bounds__(32, 12) x3_lcp_stream_kernel(X3SearchParams pr
 			}
 			mbar_wait(bar, phase);
 			phase ^= 1;
-			for (int k = 0; k < C::NPW; ++k) {
-				const uint32_t byte = stage[32 * k + lane];
-				uint32_t bal[8];
+			/* every lane transposes whole 32-byte words: four 8x8 bit-matrix transposes
+			 * (SWAR, Hacker's Delight 7-3) and a 4x4 byte transpose with PRMT */
+			for (int k = lane; k < C::NPW; k += 32) {
+				const uint4 *src = reinterpret_cast<const uint4 *>(stage + 32 * k);
+				const uint4 lo = src[0], hi = src[1];
+				const uint32_t in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+				uint32_t pl[4], ph[4];
 #pragma unroll
-				for (int j = 0; j < 8; ++j) {
-					bal[j] = __ballot_sync(FULL_MASK, (byte >> j) & 1u);
+				for (int g = 0; g < 4; ++g) {
+					transpose8x8(in[2 * g], in[2 * g + 1], pl[g], ph[g]);
 				}
-				if (lane == 0) {
-					pw[pidx<C::SEG>(k, 0)] = make_uint4(bal[0], bal[1], bal[2], bal[3]);
-				}
-				if (lane == 1) {
-					pw[pidx<C::SEG>(k, 1)] = make_uint4(bal[4], bal[5], bal[6], bal[7]);
-				}
+				uint32_t w[8];
+				bytes4x4(pl, w[0], w[1], w[2], w[3]);
+				bytes4x4(ph, w[4], w[5], w[6], w[7]);
+				store_word<C>(pw, k, w);
 			}
 			__syncwarp();
 			if (c == 0) {
-				load_word<C::SEG>(pw, wA, st.A0);
-				load_word<C::SEG>(pw, wA + 1, st.A1);
+				load_word<C>(pw, wA, st.A0);
+				load_word<C>(pw, wA + 1, st.A1);
 #pragma unroll
 				for (int j = 0; j < 8; ++j) {
 					st.A0[j] = ~st.A0[j];
@@ -502,13 +578,13 @@ __global__ void __launch_bounds__(32, 12) x3_lcp_stream_kernel(X3SearchParams pr
 							c2[j] = 0;
 						}
 						if (hasa) {
-							load_word<C::SEG>(pw, 2 * k2, a);
+							load_word<C>(pw, 2 * k2, a);
 						}
 						if (hasb) {
-							load_word<C::SEG>(pw, 2 * k2 + 1, b);
+							load_word<C>(pw, 2 * k2 + 1, b);
 						}
 						if (hasc) {
-							load_word<C::SEG>(pw, 2 * k2 + 2, c2);
+							load_word<C>(pw, 2 * k2 + 2, c2);
 						}
 						__syncwarp();
 #pragma unroll
@@ -516,14 +592,14 @@ __global__ void __launch_bounds__(32, 12) x3_lcp_stream_kernel(X3SearchParams pr
 							s[j] = __funnelshift_r(a[j], b[j], 1);
 						}
 						if (hasa) {
-							store_word<C::SEG>(pw, 2 * k2, s);
+							store_word<C>(pw, 2 * k2, s);
 						}
 						if (hasb) {
 #pragma unroll
 							for (int j = 0; j < 8; ++j) {
 								s[j] = __funnelshift_r(b[j], c2[j], 1);
 							}
-							store_word<C::SEG>(pw, 2 * k2 + 1, s);
+							store_word<C>(pw, 2 * k2 + 1, s);
 						}
 					}
 					__syncwarp();
@@ -654,6 +730,11 @@ cudaError_t x3k_launch_stream(bool full, X3SearchParams prm, cudaStream_t stream
 {
 	prm.ntiles = (unsigned int)((prm.n + X3K_STREAM_TILE - 1) / X3K_STREAM_TILE);
 	const int grid = x3k_stream_grid(prm.n);
+	if (getenv("X3_TRACE") != nullptr) {
+		fprintf(stderr, "x3k_launch_stream: %s path, %u tiles, grid %d (%d CTAs/SM x %d SMs), %zu B shared memory per CTA\n",
+		        full ? "full" : "fast", prm.ntiles, grid, g_stream_ctas_per_sm, g_stream_sms,
+		        full ? SCfg<8, 15>::SMEM : SCfg<4, 6>::SMEM);
+	}
 	cudaError_t e = cudaMemsetAsync(prm.tile_counter, 0, sizeof(unsigned int), stream);
 	if (e != cudaSuccess) {
 		return e;
