@@ -286,7 +286,6 @@ def run_b200(args):
         e0.record(stream)
         step_device()
         e1.record(stream)
-        launches += 1
     barrier()
     dev_ms = sum(e0.elapsed_time(e1) for (e0, e1) in ev)
     lstar_dev = d_l.cpu().numpy()
@@ -397,7 +396,8 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(len(x_host)) * world,
                 "d2h_bytes_per_step": int(n) * world, "ms_per_step": e2e_s / args.steps * 1e3,
                 "api": "x3s_search_host (include/x3_search.h), pinned host buffers"},
-        "gpu_launches": launches + e2e_launches,
+        # per search: probe kernel + the two stream-kernel instantiations (one of them exits at once)
+        "gpu_launches": e2e_launches + args.steps * (e2e_launches // max(1, args.steps)),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "compress": compress,

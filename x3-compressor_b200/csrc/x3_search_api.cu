@@ -91,6 +91,10 @@ int launch_on(int device, int variant, X3SearchParams &prm, cudaStream_t stream,
 	prm.tile_counter = sc.counter;
 	prm.deep = sc.deep;
 	prm.ntiles = 0;
+	{
+		const char *kd = getenv("X3_STREAM_KD"); /* tuning/testing knob; never changes results */
+		prm.kd = kd != nullptr ? atoi(kd) : 0;
+	}
 	CU_TRY(cudaStreamWaitEvent(stream, sc.last, 0));
 	CU_TRY(x3k_launch(variant, prm, stream, launches));
 	CU_TRY(cudaEventRecord(sc.last, stream));

@@ -457,7 +457,7 @@ size_t x3k_required_bytes(size_t n, size_t W)
 }
 
 cudaError_t x3k_stream_init_device(void);
-cudaError_t x3k_launch_stream(bool full, X3SearchParams prm, cudaStream_t stream);
+cudaError_t x3k_launch_stream(bool full, X3SearchParams prm, cudaStream_t stream, int *launches);
 
 cudaError_t x3k_init_device(void)
 {
@@ -475,7 +475,7 @@ cudaError_t x3k_launch(int variant, const X3SearchParams &prm, cudaStream_t stre
 	if (prm.n == 0) {
 		return cudaSuccess;
 	}
-	if (launches != nullptr) {
+	if (launches != nullptr && (variant == 1 || variant == 2)) {
 		*launches += 1;
 	}
 	if (variant == 1) {
@@ -487,7 +487,7 @@ cudaError_t x3k_launch(int variant, const X3SearchParams &prm, cudaStream_t stre
 	} else {
 		/* t <= 0: the selection never runs (backend.c:76) -- the fast path handles it, Lstar = 0 */
 		const bool full = prm.H != nullptr || prm.t > 15 || variant == 4;
-		return x3k_launch_stream(full, prm, stream);
+		return x3k_launch_stream(full, prm, stream, launches);
 	}
 	return cudaGetLastError();
 }

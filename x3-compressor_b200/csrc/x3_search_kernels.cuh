@@ -20,6 +20,7 @@ struct X3SearchParams {
 	unsigned int *tile_counter; /* dynamic tile scheduler, zeroed before each launch */
 	uint8_t *deep;              /* X3K_DEEP_BYTES_PER_CTA bytes per resident CTA */
 	unsigned int ntiles;
+	int kd;                     /* dense levels: 2, 3, or 0 = choose per tile from a probe */
 };
 
 /* Scratch the stream kernel needs: the grid it will be launched with and the

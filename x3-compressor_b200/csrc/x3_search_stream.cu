@@ -56,7 +56,7 @@
 
 namespace {
 
-template <int CB, int HB>
+template <int CB, int HB, int KD_>
 struct SCfg {
 	static constexpr int OWN = 62;                 /* position words per warp: 31 lanes x 2 */
 	static constexpr int NWORD = 64;               /* + the helper lane's two words */
@@ -65,9 +65,11 @@ struct SCfg {
 	static constexpr int NPW = NWORD + MCH + 1;    /* plane words staged per chunk */
 	static constexpr int SEG0 = (NPW + 1) / 2;     /* uint4 per (even word, half) segment of the plane array */
 	static constexpr int SEG1 = NPW / 2;           /* uint4 per (odd word, half) segment */
-	static constexpr int NSH = HB == 6 ? 5 : 2;    /* LCP levels kept in the shared word: 3 .. 2+NSH (bits 0..29;
-	                                                * bit 31 flags a touched deep row) */
-	static constexpr int NDEEP = 30 - NSH;         /* LCP levels kept in the global row: 3+NSH .. 32 */
+	static constexpr int KD = KD_;                 /* LCP levels 1..KD are counted densely (bit-sliced): 2 or 3 */
+	static constexpr int L0 = KD + 1;              /* first LCP level that goes through the event queue */
+	static constexpr int NSH = HB == 6 ? 5 : 2;    /* LCP levels kept in the shared word: L0 .. L0+NSH-1 (bits
+	                                                * 0..29; bit 31 flags a touched deep row) */
+	static constexpr int NDEEP = 32 - KD - NSH;    /* LCP levels kept in the global row: L0+NSH .. 32 */
 	static constexpr int DBITS = 16;               /* bits per deep bin: never overflows while D <= 65535 */
 	static constexpr int ROWB = 64;                /* bytes per deep row */
 	static constexpr uint32_t CAP = HB == 6 ? 16u : 255u;
@@ -91,8 +93,8 @@ struct SCfg {
 	static_assert(NDEEP * DBITS <= ROWB * 8, "deep row holds every deep bin");
 };
 
-static_assert(SCfg<4, 6>::P == X3K_STREAM_TILE, "tile size");
-static_assert((size_t)SCfg<8, 15>::ROWB * SCfg<8, 15>::P <= X3K_DEEP_BYTES_PER_CTA, "deep scratch per CTA");
+static_assert(SCfg<4, 6, 2>::P == X3K_STREAM_TILE, "tile size");
+static_assert((size_t)SCfg<8, 15, 3>::ROWB * SCfg<8, 15, 3>::P <= X3K_DEEP_BYTES_PER_CTA, "deep scratch per CTA");
 
 /* Bit-sliced counter over 32 positions fed by a 16-input carry-save tree. */
 template <int CB>
@@ -255,11 +257,11 @@ __device__ __forceinline__ void store_word(uint4 *base, int k, const uint32_t (&
  * lanes may hit the same position).  Bins may overshoot the cap by at most 31 (one add
  * in flight per lane), which the field widths absorb and the epilogue clamps.
  */
-template <int CB, int HB>
+template <int CB, int HB, int KD>
 __device__ __noinline__ void st_drain(const uint2 *q, uint32_t n0, uint32_t n1, uint32_t *hist, uint32_t *done_s,
                                       uint16_t *tab, uint8_t *deep_tile, int lane, bool uncond)
 {
-	using C = SCfg<CB, HB>;
+	using C = SCfg<CB, HB, KD>;
 	const uint32_t n = n0 + n1;
 	uint32_t inc = n;
 #pragma unroll
@@ -300,19 +302,22 @@ __device__ __noinline__ void st_drain(const uint2 *q, uint32_t n0, uint32_t n1, 
 				e = en.x;
 				eh = en.y;
 				R = e & __funnelshift_r(e, eh, 1) & __funnelshift_r(e, eh, 2) & ~done_s[w];
+				if (C::KD >= 3) {
+					R &= __funnelshift_r(e, eh, 3);
+				}
 			}
 		}
 		cursor += __popc(nmask);
 		if (R != 0) {
-			/* one event: highest set bit b; v = the pair's bits from b upwards (bits 0..2 are set) */
+			/* one event: highest set bit b; v = the pair's bits from b upwards (bits 0..KD are set) */
 			const int cz = __clz(R);
 			const int b = 31 - cz;
 			R &= ~(0x80000000u >> cz);
 			const uint32_t v = __funnelshift_r(e, eh, b);
 			const uint32_t pos = w * 32u + (uint32_t)b;
 			const uint32_t word = hist[pos];
-			/* zeros among bits 3 .. 2+NSH of v: the lowest one marks the run length */
-			const uint32_t y = ~(v >> 3) & ((1u << C::NSH) - 1u);
+			/* zeros among bits L0 .. L0+NSH-1 of v: the lowest one marks the run length */
+			const uint32_t y = ~(v >> C::L0) & ((1u << C::NSH) - 1u);
 			if (y != 0) {
 				uint32_t inc;
 				bool full;
@@ -336,7 +341,7 @@ __device__ __noinline__ void st_drain(const uint2 *q, uint32_t n0, uint32_t n1, 
 				if ((word >> 31) == 0) {
 					atomicOr(&hist[pos], 0x80000000u); /* row touched */
 				}
-				const uint32_t k = run - (3u + C::NSH);
+				const uint32_t k = run - (uint32_t)(C::L0 + C::NSH);
 				constexpr uint32_t PER = 32 / C::DBITS; /* bins per 32-bit word of the row */
 				unsigned int *rw = reinterpret_cast<unsigned int *>(deep_tile + (size_t)pos * C::ROWB) + k / PER;
 				const uint32_t sh = C::DBITS * (k % PER);
@@ -366,27 +371,27 @@ __device__ __noinline__ void st_drain(const uint2 *q, uint32_t n0, uint32_t n1, 
 }
 
 /* State a lane carries through the search loop. */
-template <int CB>
+template <int CB, int KD>
 struct LaneState {
 	uint32_t A0[8], A1[8]; /* COMPLEMENTED planes of the two owned position words */
-	Tree<CB> T[4];         /* [word 0 L>=1, word 0 L>=2, word 1 L>=1, word 1 L>=2] */
+	Tree<CB> T[2 * KD]; /* [word j][level k] at index j * KD + k: counts of LCP >= k + 1 */
 	uint2 done;
 	bool uncond;           /* D <= 65535: deep bins are added to without a bound check */
 	uint32_t q0, q1;       /* shared-space byte address of the next free slot of the word-0 queue (grows
 	                        * up) and of the word-1 queue (grows down) */
 };
 
-template <int CB, int HB>
-__device__ __forceinline__ void st_flush(LaneState<CB> &st, uint2 *q, uint32_t *hist, uint32_t *done_s,
+template <int CB, int HB, int KD>
+__device__ __forceinline__ void st_flush(LaneState<CB, KD> &st, uint2 *q, uint32_t *hist, uint32_t *done_s,
                                          uint8_t *deep_tile, int lane)
 {
 	uint16_t *tab = reinterpret_cast<uint16_t *>(hist + 62 * 32); /* OFF_TAB follows the histograms */
-	using C = SCfg<CB, HB>;
+	using C = SCfg<CB, HB, KD>;
 	const uint32_t lo = smem_u32(q + lane), hi = smem_u32(q + (C::QCAP - 1) * 32 + lane);
 	const uint32_t n0 = (st.q0 - lo) / 256u;
 	const uint32_t n1 = (hi - st.q1) / 256u;
 	/* the helper lane owns no positions: its entries are dropped */
-	st_drain<CB, HB>(q, lane == 31 ? 0u : n0, lane == 31 ? 0u : n1, hist, done_s, tab, deep_tile, lane, st.uncond);
+	st_drain<CB, HB, KD>(q, lane == 31 ? 0u : n0, lane == 31 ? 0u : n1, hist, done_s, tab, deep_tile, lane, st.uncond);
 	if (lane != 31) {
 		st.done = make_uint2(done_s[2 * lane], done_s[2 * lane + 1]);
 	}
@@ -398,12 +403,12 @@ __device__ __forceinline__ void st_flush(LaneState<CB> &st, uint2 *q, uint32_t *
  * 16 consecutive distance blocks mm0 .. mm0+15 (chunk relative) at a fixed r.
  * MASKED: blocks outside [vlo, vhi] contribute nothing (d = 0 or d > D).
  */
-template <int CB, int HB, bool MASKED>
-__device__ __forceinline__ void st_group16(LaneState<CB> &st, const uint4 *sr, uint2 *q, uint32_t *hist,
+template <int CB, int HB, int KD, bool MASKED>
+__device__ __forceinline__ void st_group16(LaneState<CB, KD> &st, const uint4 *sr, uint2 *q, uint32_t *hist,
                                            uint32_t *done_s, uint8_t *deep_tile, int lane, int wA, int mm0, int vlo,
                                            int vhi)
 {
-	using C = SCfg<CB, HB>;
+	using C = SCfg<CB, HB, KD>;
 	uint32_t S0[8], S1[8];
 	/* mm0 is a multiple of 16 and wA = 2 * lane: the parity of every plane word index below is a
 	 * compile-time constant after unrolling, and the 32 lanes read contiguous uint4 */
@@ -432,12 +437,22 @@ __device__ __forceinline__ void st_group16(LaneState<CB> &st, const uint4 *sr, u
 		const uint32_t en = __shfl_down_sync(FULL_MASK, e0, 1);
 		const uint32_t r20 = e0 & __funnelshift_r(e0, e1, 1);
 		const uint32_t r21 = e1 & __funnelshift_r(e1, en, 1);
-		const uint32_t r30 = r20 & __funnelshift_r(e0, e1, 2) & ~st.done.x;
-		const uint32_t r31 = r21 & __funnelshift_r(e1, en, 2) & ~st.done.y;
-		tree_add(st.T[0], e0, i);
-		tree_add(st.T[1], r20, i);
-		tree_add(st.T[2], e1, i);
-		tree_add(st.T[3], r21, i);
+		tree_add(st.T[0 * C::KD + 0], e0, i);
+		tree_add(st.T[0 * C::KD + 1], r20, i);
+		tree_add(st.T[1 * C::KD + 0], e1, i);
+		tree_add(st.T[1 * C::KD + 1], r21, i);
+		uint32_t r30, r31; /* the queue filter: LCP >= KD + 1 at a position that is not done */
+		if (C::KD == 2) {
+			r30 = r20 & __funnelshift_r(e0, e1, 2) & ~st.done.x;
+			r31 = r21 & __funnelshift_r(e1, en, 2) & ~st.done.y;
+		} else {
+			const uint32_t t30 = r20 & __funnelshift_r(e0, e1, 2);
+			const uint32_t t31 = r21 & __funnelshift_r(e1, en, 2);
+			tree_add(st.T[0 * C::KD + 2], t30, i);
+			tree_add(st.T[1 * C::KD + 2], t31, i);
+			r30 = t30 & __funnelshift_r(e0, e1, 3) & ~st.done.x;
+			r31 = t31 & __funnelshift_r(e1, en, 3) & ~st.done.y;
+		}
 		if (r30 != 0) {
 			sts64(st.q0, e0, e1);
 			st.q0 += 256;
@@ -454,32 +469,321 @@ __device__ __forceinline__ void st_group16(LaneState<CB> &st, const uint4 *sr, u
 			/* 4 more blocks can push 4 entries at each end: flush when fewer than 8 slots are free
 			 * (signed compare: a full queue gives -256) */
 			if (__any_sync(FULL_MASK, (int)(st.q1 - st.q0) < 256 * 7)) {
-				st_flush<CB, HB>(st, q, hist, done_s, deep_tile, lane);
+				st_flush<CB, HB, KD>(st, q, hist, done_s, deep_tile, lane);
 			}
 		}
 	}
 	(void)wA;
 }
 
-template <int CB, int HB>
-__global__ void __launch_bounds__(32, 13) x3_lcp_stream_kernel(X3SearchParams prm)
+/* Stages plane words [32 MCH c, +NPW) of the tile: one TMA bulk copy into the (drained)
+ * queue memory, then every lane transposes whole 32-byte words into bit-planes: four 8x8
+ * bit-matrix transposes (SWAR, Hacker's Delight 7-3) and a 4x4 byte transpose with PRMT. */
+template <class C>
+__device__ __forceinline__ void st_stage(const X3SearchParams &prm, uint8_t *smem, unsigned long long p0, uint32_t c,
+                                         uint32_t &phase, int lane)
 {
-	using C = SCfg<CB, HB>;
-	extern __shared__ __align__(128) uint8_t smem[];
 	uint4 *pw = reinterpret_cast<uint4 *>(smem + C::OFF_PW);
 	uint8_t *stage = smem + C::OFF_Q;
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+	__syncwarp();
+	if (lane == 0) {
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+		mbar_expect_tx(bar, C::NPW * 32);
+		tma_load_1d(stage, prm.x + p0 + 32ull * C::MCH * c, C::NPW * 32, bar);
+	}
+	mbar_wait(bar, phase);
+	phase ^= 1;
+	for (int k = lane; k < C::NPW; k += 32) {
+		const uint4 *src = reinterpret_cast<const uint4 *>(stage + 32 * k);
+		const uint4 lo = src[0], hi = src[1];
+		const uint32_t in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+		uint32_t pl[4], ph[4];
+#pragma unroll
+		for (int g = 0; g < 4; ++g) {
+			transpose8x8(in[2 * g], in[2 * g + 1], pl[g], ph[g]);
+		}
+		uint32_t w[8];
+		bytes4x4(pl, w[0], w[1], w[2], w[3]);
+		bytes4x4(ph, w[4], w[5], w[6], w[7]);
+		store_word<C>(pw, k, w);
+	}
+	__syncwarp();
+}
+
+/* Window planes: shifts the whole array by one more bit, in place.  Word k takes its top bit
+ * from word k+1; ascending passes read a word before the pass that owns it rewrites it; the last
+ * word shifts in zeros. */
+template <class C>
+__device__ __forceinline__ void st_shift1(uint4 *pw, int lane)
+{
+	for (int pass = 0; 64 * pass < C::NPW; ++pass) { /* uniform trip count: __syncwarp inside */
+		const int k2 = lane + 32 * pass;
+		uint32_t a[8], b[8], c2[8], s[8];
+		const bool hasa = 2 * k2 < C::NPW, hasb = 2 * k2 + 1 < C::NPW, hasc = 2 * k2 + 2 < C::NPW;
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			a[j] = 0;
+			b[j] = 0;
+			c2[j] = 0;
+		}
+		if (hasa) {
+			load_word<C>(pw, 2 * k2, a);
+		}
+		if (hasb) {
+			load_word<C>(pw, 2 * k2 + 1, b);
+		}
+		if (hasc) {
+			load_word<C>(pw, 2 * k2 + 2, c2);
+		}
+		__syncwarp();
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			s[j] = __funnelshift_r(a[j], b[j], 1);
+		}
+		if (hasa) {
+			store_word<C>(pw, 2 * k2, s);
+		}
+		if (hasb) {
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				s[j] = __funnelshift_r(b[j], c2[j], 1);
+			}
+			store_word<C>(pw, 2 * k2 + 1, s);
+		}
+	}
+}
+
+/*
+ * Probe: how many (lane, word) units of distance blocks 1..15 at r = 0..7 would push a queue
+ * entry with 2 dense levels.  Chunk 0 must be staged; the plane array is left shifted by 7.
+ */
+#define X3_PROBE_R 8
+template <class C>
+__device__ __forceinline__ uint32_t st_probe(uint4 *pw, int lane)
+{
+	uint32_t A0[8], A1[8], S0[8], S1[8];
+	load_word<C>(pw, 2 * lane, A0);
+	load_word<C>(pw, 2 * lane + 1, A1);
+#pragma unroll
+	for (int j = 0; j < 8; ++j) {
+		A0[j] = ~A0[j];
+		A1[j] = ~A1[j];
+	}
+	uint32_t pushes = 0;
+	for (int r = 0; r < X3_PROBE_R; ++r) {
+		if (r > 0) {
+			__syncwarp();
+			st_shift1<C>(pw, lane);
+			__syncwarp();
+		}
+		load_word<C>(pw, 2 * lane + 1, S0); /* block 1 of word 0 */
+#pragma unroll 3
+		for (int i = 1; i < 16; ++i) {
+			load_word<C>(pw, 2 * lane + 1 + i, S1);
+			const uint32_t e0 = eq8(A0, S0), e1 = eq8(A1, S1);
+			const uint32_t en = __shfl_down_sync(FULL_MASK, e0, 1);
+			const uint32_t r30 = e0 & __funnelshift_r(e0, e1, 1) & __funnelshift_r(e0, e1, 2);
+			const uint32_t r31 = e1 & __funnelshift_r(e1, en, 1) & __funnelshift_r(e1, en, 2);
+			pushes += (r30 != 0) + (r31 != 0);
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				S0[j] = S1[j];
+			}
+		}
+	}
+	if (lane == 31) {
+		pushes = 0;
+	}
+	return __reduce_add_sync(FULL_MASK, pushes);
+}
+
+/* One tile (1984 positions) with KD dense levels; chunk 0 is already staged. */
+template <int CB, int HB, int KD>
+__device__ __forceinline__ void st_tile(const X3SearchParams &prm, uint8_t *smem, unsigned long long p0, uint32_t &phase,
+                                     uint8_t *deep_tile)
+{
+	using C = SCfg<CB, HB, KD>;
+	uint4 *pw = reinterpret_cast<uint4 *>(smem + C::OFF_PW);
 	uint32_t *hist = reinterpret_cast<uint32_t *>(smem + C::OFF_HIST);
 	uint32_t *done_s = reinterpret_cast<uint32_t *>(smem + C::OFF_DONE);
 	uint2 *q = reinterpret_cast<uint2 *>(smem + C::OFF_Q);
-	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
-
 	const int lane = threadIdx.x;
 	const int wA = 2 * lane;
 	const uint32_t D = prm.D;
 	const uint32_t MB = D / 32 + 1; /* distance blocks m = 0 .. D/32 */
 	const uint32_t nchunks = (MB + C::MCH - 1) / C::MCH;
+
+	LaneState<CB, KD> st;
+#pragma unroll
+	for (int k = 0; k < 2 * C::KD; ++k) {
+		tree_clear(st.T[k]);
+	}
+	st.done = make_uint2(0, 0);
+	st.uncond = D <= 65535u;
+	st.q0 = smem_u32(q + lane);
+	st.q1 = smem_u32(q + (C::QCAP - 1) * 32 + lane);
+	for (int i = lane; i < 62 * 32; i += 32) {
+		hist[i] = 0;
+	}
+	done_s[lane] = 0;
+	if (lane + 32 < 62) {
+		done_s[lane + 32] = 0;
+	}
+	__syncwarp();
+
+	for (uint32_t c = 0; c < nchunks; ++c) {
+		if (c > 0) {
+			st_flush<CB, HB, KD>(st, q, hist, done_s, deep_tile, lane);
+			st_stage<C>(prm, smem, p0, c, phase, lane);
+		}
+		if (c == 0) {
+			load_word<C>(pw, wA, st.A0);
+			load_word<C>(pw, wA + 1, st.A1);
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				st.A0[j] = ~st.A0[j];
+				st.A1[j] = ~st.A1[j];
+			}
+		}
+
+		for (int r = 0; r < 32; ++r) {
+			/* valid chunk-relative blocks: d = 32 (MCH c + mm) + r in [1, D] */
+			if (D < (uint32_t)r) {
+				break;
+			}
+			const int vlo = (c == 0 && r == 0) ? 1 : 0;
+			const long long hi = (long long)((D - (uint32_t)r) / 32) - (long long)C::MCH * c;
+			const int vhi = hi >= C::MCH ? C::MCH - 1 : (int)hi;
+			if (r > 0) {
+				st_shift1<C>(pw, lane);
+				__syncwarp();
+			}
+			if (vhi < vlo) {
+				continue;
+			}
+
+			for (int g = 0; g < C::MCH / 16; ++g) {
+				const int mm0 = 16 * g;
+				if (mm0 > vhi || mm0 + 15 < vlo) {
+					continue;
+				}
+				if (mm0 >= vlo && mm0 + 15 <= vhi) {
+					st_group16<CB, HB, KD, false>(st, pw, q, hist, done_s, deep_tile, lane, wA, mm0, vlo, vhi);
+				} else {
+					st_group16<CB, HB, KD, true>(st, pw, q, hist, done_s, deep_tile, lane, wA, mm0, vlo, vhi);
+				}
+			}
+		}
+	}
+
+	st_flush<CB, HB, KD>(st, q, hist, done_s, deep_tile, lane);
+	__syncwarp();
+
+	/* ---- epilogue: counts -> Lstar (and the 32-bin row) ---- */
+	if (lane != 31) {
+		const unsigned long long pbase = p0 + 64ull * lane;
+#pragma unroll 1
+		for (int jb = 0; jb < 64; ++jb) {
+			const int j = jb >> 5, b = jb & 31;
+			const unsigned long long p = pbase + jb;
+			const bool live = p < prm.n; /* rows of padding positions are still handed back zeroed */
+			const uint32_t pos = (uint32_t)lane * 64u + (uint32_t)jb;
+			const uint32_t word = hist[pos];
+			uint32_t cnt[32];
+			uint32_t acc = 0;
+			if (word >> 31) {
+				/* read the deep row and hand it back zeroed (the scratch invariant) */
+				uint4 *r4 = reinterpret_cast<uint4 *>(deep_tile + (size_t)pos * C::ROWB);
+				uint32_t rw[C::ROWB / 4];
+#pragma unroll
+				for (int v4 = 0; v4 < C::ROWB / 16; ++v4) {
+					const uint4 t4 = __ldcg(r4 + v4);
+					rw[4 * v4] = t4.x; rw[4 * v4 + 1] = t4.y; rw[4 * v4 + 2] = t4.z; rw[4 * v4 + 3] = t4.w;
+					__stcg(r4 + v4, make_uint4(0, 0, 0, 0));
+				}
+				constexpr int PER = 32 / C::DBITS;
+#pragma unroll
+				for (int L = 32; L >= C::L0 + C::NSH; --L) {
+					const int k = L - C::L0 - C::NSH;
+					acc = min(acc + ((rw[k / PER] >> (C::DBITS * (k % PER))) & C::DMASK), C::CAP);
+					cnt[L - 1] = acc;
+				}
+			} else {
+#pragma unroll
+				for (int L = 32; L >= C::L0 + C::NSH; --L) {
+					cnt[L - 1] = 0;
+				}
+			}
+#pragma unroll
+			for (int L = C::L0 + C::NSH - 1; L >= C::L0; --L) {
+				acc = min(acc + ((word >> (HB * (L - C::L0))) & C::FMASK), C::CAP);
+				cnt[L - 1] = acc;
+			}
+#pragma unroll
+			for (int k = 0; k < C::KD; ++k) {
+				cnt[k] = j ? tree_value(st.T[C::KD + k], b) : tree_value(st.T[k], b);
+			}
+			if (live) {
+				prm.lstar[p] = (uint8_t)lstar_from_counts(cnt, prm.t);
+				if (prm.H != nullptr) {
+					store_row(prm.H, p, cnt);
+				}
+			}
+		}
+	}
+}
+
+/*
+ * Probe kernel: samples the queue push rate of up to gridDim.x tiles spread over the input
+ * (first 15 distance blocks at r = 0 each) into prm.tile_counter[1] (pushes) and [2] (units).
+ * The two search kernels (KD = 2 and KD = 3) are launched back to back behind it; each reads the
+ * sums and only the one that the rate selects does the work -- no host round trip.
+ * A third dense level costs 4 ALU instructions per unit and removes the LCP == 3 events (40 % of
+ * them on text): worth it when more than ~3 % of the units push an entry (measured break-even: C2-shaped text 3.9 %, C4-shaped binary 2 %).
+ */
+template <int CB, int HB>
+__global__ void __launch_bounds__(32) x3_lcp_probe_kernel(X3SearchParams prm)
+{
+	using C = SCfg<CB, HB, 2>;
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+	const int lane = threadIdx.x;
+	if (lane == 0) {
+		mbar_init(bar, 1);
+	}
+	__syncwarp();
+	uint32_t phase = 0;
+	const unsigned int tile = (unsigned int)(((unsigned long long)blockIdx.x * prm.ntiles) / gridDim.x);
+	st_stage<C>(prm, smem, (unsigned long long)tile * C::P, 0, phase, lane);
+	const uint32_t pushes = st_probe<C>(reinterpret_cast<uint4 *>(smem + C::OFF_PW), lane);
+	if (lane == 0) {
+		atomicAdd(prm.tile_counter + 1, pushes);
+		atomicAdd(prm.tile_counter + 2, 15u * 62u * X3_PROBE_R);
+	}
+}
+
+__device__ __forceinline__ int st_choice(const X3SearchParams &prm)
+{
+	if (prm.kd == 2 || prm.kd == 3) {
+		return prm.kd;
+	}
+	const unsigned int pushes = __ldcg(prm.tile_counter + 1), units = __ldcg(prm.tile_counter + 2);
+	return pushes * 32u > units ? 3 : 2; /* more than 1 in 32 sampled units push an entry */
+}
+
+template <int CB, int HB, int KD>
+__global__ void __launch_bounds__(32, 13) x3_lcp_stream_kernel(X3SearchParams prm)
+{
+	using C = SCfg<CB, HB, KD>;
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_BAR);
+	const int lane = threadIdx.x;
 	uint8_t *deep_tile = prm.deep + (size_t)blockIdx.x * X3K_DEEP_BYTES_PER_CTA;
 
+	if (st_choice(prm) != KD) {
+		return; /* the other instantiation does this launch */
+	}
 	if (lane == 0) {
 		mbar_init(bar, 1);
 	}
@@ -496,185 +800,8 @@ __global__ void __launch_bounds__(32, 13) x3_lcp_stream_kernel(X3SearchParams pr
 			break;
 		}
 		const unsigned long long p0 = (unsigned long long)tile * C::P;
-
-		LaneState<CB> st;
-#pragma unroll
-		for (int k = 0; k < 4; ++k) {
-			tree_clear(st.T[k]);
-		}
-		st.done = make_uint2(0, 0);
-		st.uncond = D <= 65535u;
-		st.q0 = smem_u32(q + lane);
-		st.q1 = smem_u32(q + (C::QCAP - 1) * 32 + lane);
-		for (int i = lane; i < 62 * 32; i += 32) {
-			hist[i] = 0;
-		}
-		done_s[lane] = 0;
-		if (lane + 32 < 62) {
-			done_s[lane + 32] = 0;
-		}
-
-		for (uint32_t c = 0; c < nchunks; ++c) {
-			/* ---- stage the chunk's bytes (into the drained queue's memory) and transpose them
-			 *      into bit-planes ---- */
-			if (c > 0) {
-				st_flush<CB, HB>(st, q, hist, done_s, deep_tile, lane);
-			}
-			__syncwarp();
-			if (lane == 0) {
-				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-				mbar_expect_tx(bar, C::NPW * 32);
-				tma_load_1d(stage, prm.x + p0 + 32ull * C::MCH * c, C::NPW * 32, bar);
-			}
-			mbar_wait(bar, phase);
-			phase ^= 1;
-			/* every lane transposes whole 32-byte words: four 8x8 bit-matrix transposes
-			 * (SWAR, Hacker's Delight 7-3) and a 4x4 byte transpose with PRMT */
-			for (int k = lane; k < C::NPW; k += 32) {
-				const uint4 *src = reinterpret_cast<const uint4 *>(stage + 32 * k);
-				const uint4 lo = src[0], hi = src[1];
-				const uint32_t in[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-				uint32_t pl[4], ph[4];
-#pragma unroll
-				for (int g = 0; g < 4; ++g) {
-					transpose8x8(in[2 * g], in[2 * g + 1], pl[g], ph[g]);
-				}
-				uint32_t w[8];
-				bytes4x4(pl, w[0], w[1], w[2], w[3]);
-				bytes4x4(ph, w[4], w[5], w[6], w[7]);
-				store_word<C>(pw, k, w);
-			}
-			__syncwarp();
-			if (c == 0) {
-				load_word<C>(pw, wA, st.A0);
-				load_word<C>(pw, wA + 1, st.A1);
-#pragma unroll
-				for (int j = 0; j < 8; ++j) {
-					st.A0[j] = ~st.A0[j];
-					st.A1[j] = ~st.A1[j];
-				}
-			}
-
-			for (int r = 0; r < 32; ++r) {
-				/* valid chunk-relative blocks: d = 32 (MCH c + mm) + r in [1, D] */
-				if (D < (uint32_t)r) {
-					break;
-				}
-				const int vlo = (c == 0 && r == 0) ? 1 : 0;
-				const long long hi = (long long)((D - (uint32_t)r) / 32) - (long long)C::MCH * c;
-				const int vhi = hi >= C::MCH ? C::MCH - 1 : (int)hi;
-				if (r > 0) {
-					/* ---- window planes: shift the whole array by one more bit, in place.  Word k
-					 *      takes its top bit from word k+1; ascending passes read a word before the
-					 *      pass that owns it rewrites it; the last word shifts in zeros. ---- */
-					for (int pass = 0; 64 * pass < C::NPW; ++pass) { /* uniform trip count: __syncwarp inside */
-						const int k2 = lane + 32 * pass;
-						uint32_t a[8], b[8], c2[8], s[8];
-						const bool hasa = 2 * k2 < C::NPW, hasb = 2 * k2 + 1 < C::NPW, hasc = 2 * k2 + 2 < C::NPW;
-#pragma unroll
-						for (int j = 0; j < 8; ++j) {
-							a[j] = 0;
-							b[j] = 0;
-							c2[j] = 0;
-						}
-						if (hasa) {
-							load_word<C>(pw, 2 * k2, a);
-						}
-						if (hasb) {
-							load_word<C>(pw, 2 * k2 + 1, b);
-						}
-						if (hasc) {
-							load_word<C>(pw, 2 * k2 + 2, c2);
-						}
-						__syncwarp();
-#pragma unroll
-						for (int j = 0; j < 8; ++j) {
-							s[j] = __funnelshift_r(a[j], b[j], 1);
-						}
-						if (hasa) {
-							store_word<C>(pw, 2 * k2, s);
-						}
-						if (hasb) {
-#pragma unroll
-							for (int j = 0; j < 8; ++j) {
-								s[j] = __funnelshift_r(b[j], c2[j], 1);
-							}
-							store_word<C>(pw, 2 * k2 + 1, s);
-						}
-					}
-					__syncwarp();
-				}
-				if (vhi < vlo) {
-					continue;
-				}
-
-				for (int g = 0; g < C::MCH / 16; ++g) {
-					const int mm0 = 16 * g;
-					if (mm0 > vhi || mm0 + 15 < vlo) {
-						continue;
-					}
-					if (mm0 >= vlo && mm0 + 15 <= vhi) {
-						st_group16<CB, HB, false>(st, pw, q, hist, done_s, deep_tile, lane, wA, mm0, vlo, vhi);
-					} else {
-						st_group16<CB, HB, true>(st, pw, q, hist, done_s, deep_tile, lane, wA, mm0, vlo, vhi);
-					}
-				}
-			}
-		}
-
-		st_flush<CB, HB>(st, q, hist, done_s, deep_tile, lane);
-		__syncwarp();
-
-		/* ---- epilogue: counts -> Lstar (and the 32-bin row) ---- */
-		if (lane != 31) {
-			const unsigned long long pbase = p0 + 64ull * lane;
-#pragma unroll 1
-			for (int jb = 0; jb < 64; ++jb) {
-				const int j = jb >> 5, b = jb & 31;
-				const unsigned long long p = pbase + jb;
-				const bool live = p < prm.n; /* rows of padding positions are still handed back zeroed */
-				const uint32_t pos = (uint32_t)lane * 64u + (uint32_t)jb;
-				const uint32_t word = hist[pos];
-				uint32_t cnt[32];
-				uint32_t acc = 0;
-				if (word >> 31) {
-					/* read the deep row and hand it back zeroed (the scratch invariant) */
-					uint4 *r4 = reinterpret_cast<uint4 *>(deep_tile + (size_t)pos * C::ROWB);
-					uint32_t rw[C::ROWB / 4];
-#pragma unroll
-					for (int v4 = 0; v4 < C::ROWB / 16; ++v4) {
-						const uint4 t4 = __ldcg(r4 + v4);
-						rw[4 * v4] = t4.x; rw[4 * v4 + 1] = t4.y; rw[4 * v4 + 2] = t4.z; rw[4 * v4 + 3] = t4.w;
-						__stcg(r4 + v4, make_uint4(0, 0, 0, 0));
-					}
-					constexpr int PER = 32 / C::DBITS;
-#pragma unroll
-					for (int L = 32; L >= 3 + C::NSH; --L) {
-						const int k = L - 3 - C::NSH;
-						acc = min(acc + ((rw[k / PER] >> (C::DBITS * (k % PER))) & C::DMASK), C::CAP);
-						cnt[L - 1] = acc;
-					}
-				} else {
-#pragma unroll
-					for (int L = 32; L >= 3 + C::NSH; --L) {
-						cnt[L - 1] = 0;
-					}
-				}
-#pragma unroll
-				for (int L = 2 + C::NSH; L >= 3; --L) {
-					acc = min(acc + ((word >> (HB * (L - 3))) & C::FMASK), C::CAP);
-					cnt[L - 1] = acc;
-				}
-				cnt[1] = j ? tree_value(st.T[3], b) : tree_value(st.T[1], b);
-				cnt[0] = j ? tree_value(st.T[2], b) : tree_value(st.T[0], b);
-				if (live) {
-					prm.lstar[p] = (uint8_t)lstar_from_counts(cnt, prm.t);
-					if (prm.H != nullptr) {
-						store_row(prm.H, p, cnt);
-					}
-				}
-			}
-		}
+		st_stage<C>(prm, smem, p0, 0, phase, lane);
+		st_tile<CB, HB, KD>(prm, smem, p0, phase, deep_tile);
 		__syncwarp();
 	}
 }
@@ -684,19 +811,34 @@ int g_stream_sms = 0;
 
 } /* namespace */
 
+template <int CB, int HB>
+static cudaError_t stream_set_attr(void)
+{
+	cudaError_t e = cudaFuncSetAttribute(x3_lcp_stream_kernel<CB, HB, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                                     (int)SCfg<CB, HB, 2>::SMEM);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	e = cudaFuncSetAttribute(x3_lcp_stream_kernel<CB, HB, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                         (int)SCfg<CB, HB, 3>::SMEM);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	return cudaFuncSetAttribute(x3_lcp_probe_kernel<CB, HB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	                            (int)SCfg<CB, HB, 2>::SMEM);
+}
+
 cudaError_t x3k_stream_init_device(void)
 {
-	cudaError_t e = cudaFuncSetAttribute(x3_lcp_stream_kernel<4, 6>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                                     (int)SCfg<4, 6>::SMEM);
+	cudaError_t e = stream_set_attr<4, 6>();
 	if (e != cudaSuccess) {
 		return e;
 	}
-	e = cudaFuncSetAttribute(x3_lcp_stream_kernel<8, 15>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	                         (int)SCfg<8, 15>::SMEM);
+	e = stream_set_attr<8, 15>();
 	if (e != cudaSuccess) {
 		return e;
 	}
-	int dev = 0, occ = 0;
+	int dev = 0, occ = 0, occ3 = 0;
 	e = cudaGetDevice(&dev);
 	if (e != cudaSuccess) {
 		return e;
@@ -705,10 +847,15 @@ cudaError_t x3k_stream_init_device(void)
 	if (e != cudaSuccess) {
 		return e;
 	}
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, x3_lcp_stream_kernel<4, 6>, 32, SCfg<4, 6>::SMEM);
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, x3_lcp_stream_kernel<4, 6, 2>, 32, SCfg<4, 6, 2>::SMEM);
 	if (e != cudaSuccess) {
 		return e;
 	}
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, x3_lcp_stream_kernel<4, 6, 3>, 32, SCfg<4, 6, 3>::SMEM);
+	if (e != cudaSuccess) {
+		return e;
+	}
+	occ = occ > occ3 ? occ : occ3;
 	g_stream_ctas_per_sm = occ > 0 ? occ : 1;
 	return cudaSuccess;
 }
@@ -725,24 +872,44 @@ int x3k_stream_grid(unsigned long long n)
 	return (int)(ntiles < cap ? ntiles : cap);
 }
 
-/* full: u8 counters (any t <= 254, exact H rows); otherwise the t <= 15 fast path */
-cudaError_t x3k_launch_stream(bool full, X3SearchParams prm, cudaStream_t stream)
+template <int CB, int HB>
+static cudaError_t stream_launch(const X3SearchParams &prm, int grid, cudaStream_t stream, int *launches)
+{
+	constexpr size_t SM = SCfg<CB, HB, 2>::SMEM;
+	int n = 0;
+	if (prm.kd != 2 && prm.kd != 3) {
+		const int pgrid = prm.ntiles < 128u ? (int)prm.ntiles : 128;
+		x3_lcp_probe_kernel<CB, HB><<<pgrid, 32, SM, stream>>>(prm);
+		++n;
+	}
+	if (prm.kd != 3) {
+		x3_lcp_stream_kernel<CB, HB, 2><<<grid, 32, SM, stream>>>(prm);
+		++n;
+	}
+	if (prm.kd != 2) {
+		x3_lcp_stream_kernel<CB, HB, 3><<<grid, 32, SM, stream>>>(prm);
+		++n;
+	}
+	if (launches != nullptr) {
+		*launches += n;
+	}
+	return cudaGetLastError();
+}
+
+/* full: u8-exact counters (any t <= 254, exact H rows); otherwise the t <= 15 fast path */
+cudaError_t x3k_launch_stream(bool full, X3SearchParams prm, cudaStream_t stream, int *launches)
 {
 	prm.ntiles = (unsigned int)((prm.n + X3K_STREAM_TILE - 1) / X3K_STREAM_TILE);
 	const int grid = x3k_stream_grid(prm.n);
 	if (getenv("X3_TRACE") != nullptr) {
-		fprintf(stderr, "x3k_launch_stream: %s path, %u tiles, grid %d (%d CTAs/SM x %d SMs), %zu B shared memory per CTA\n",
-		        full ? "full" : "fast", prm.ntiles, grid, g_stream_ctas_per_sm, g_stream_sms,
-		        full ? SCfg<8, 15>::SMEM : SCfg<4, 6>::SMEM);
+		fprintf(stderr, "x3k_launch_stream: %s path, kd %d, %u tiles, grid %d (%d CTAs/SM x %d SMs), %zu B shared memory per CTA\n",
+		        full ? "full" : "fast", prm.kd, prm.ntiles, grid, g_stream_ctas_per_sm, g_stream_sms,
+		        SCfg<4, 6, 2>::SMEM);
 	}
-	cudaError_t e = cudaMemsetAsync(prm.tile_counter, 0, sizeof(unsigned int), stream);
+	/* [0] tile scheduler, [1] probe pushes, [2] probe units */
+	cudaError_t e = cudaMemsetAsync(prm.tile_counter, 0, 4 * sizeof(unsigned int), stream);
 	if (e != cudaSuccess) {
 		return e;
 	}
-	if (full) {
-		x3_lcp_stream_kernel<8, 15><<<grid, 32, SCfg<8, 15>::SMEM, stream>>>(prm);
-	} else {
-		x3_lcp_stream_kernel<4, 6><<<grid, 32, SCfg<4, 6>::SMEM, stream>>>(prm);
-	}
-	return cudaGetLastError();
+	return full ? stream_launch<8, 15>(prm, grid, stream, launches) : stream_launch<4, 6>(prm, grid, stream, launches);
 }
