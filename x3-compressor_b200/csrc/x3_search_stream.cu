@@ -683,6 +683,9 @@ __device__ __forceinline__ void st_tile(const X3SearchParams &prm, uint8_t *smem
 	/* ---- epilogue: counts -> Lstar (and the 32-bin row) ---- */
 	if (lane != 31) {
 		const unsigned long long pbase = p0 + 64ull * lane;
+		const bool want_rows = prm.H != nullptr;
+		const bool aligned4 = (reinterpret_cast<uintptr_t>(prm.lstar) & 3u) == 0;
+		uint32_t pack = 0;
 #pragma unroll 1
 		for (int jb = 0; jb < 64; ++jb) {
 			const int j = jb >> 5, b = jb & 31;
@@ -690,45 +693,92 @@ __device__ __forceinline__ void st_tile(const X3SearchParams &prm, uint8_t *smem
 			const bool live = p < prm.n; /* rows of padding positions are still handed back zeroed */
 			const uint32_t pos = (uint32_t)lane * 64u + (uint32_t)jb;
 			const uint32_t word = hist[pos];
-			uint32_t cnt[32];
-			uint32_t acc = 0;
-			if (word >> 31) {
+			uint32_t dense[C::KD];
+#pragma unroll
+			for (int k = 0; k < C::KD; ++k) {
+				dense[k] = j ? tree_value(st.T[C::KD + k], b) : tree_value(st.T[k], b);
+			}
+			uint32_t rw[C::ROWB / 4];
+			const bool deep = (word >> 31) != 0;
+			if (deep) {
 				/* read the deep row and hand it back zeroed (the scratch invariant) */
 				uint4 *r4 = reinterpret_cast<uint4 *>(deep_tile + (size_t)pos * C::ROWB);
-				uint32_t rw[C::ROWB / 4];
 #pragma unroll
 				for (int v4 = 0; v4 < C::ROWB / 16; ++v4) {
 					const uint4 t4 = __ldcg(r4 + v4);
 					rw[4 * v4] = t4.x; rw[4 * v4 + 1] = t4.y; rw[4 * v4 + 2] = t4.z; rw[4 * v4 + 3] = t4.w;
 					__stcg(r4 + v4, make_uint4(0, 0, 0, 0));
 				}
-				constexpr int PER = 32 / C::DBITS;
+			}
+			constexpr int PER = 32 / C::DBITS;
+			uint32_t ls;
+			if (!want_rows) {
+				/* Lstar only: count the levels whose (suffix-summed) count exceeds tc* without
+				 * materialising the row (reference backend.c:76-78 collapsed) */
+				const uint32_t c0 = dense[0];
+				if (prm.t <= 0 || c0 < 2) {
+					ls = 0;
+				} else {
+					const uint32_t tcs = min((uint32_t)prm.t, c0 - 1);
+					uint32_t acc = 0;
+					ls = 0;
+					if (deep) {
+#pragma unroll
+						for (int L = 32; L >= C::L0 + C::NSH; --L) {
+							const int k = L - C::L0 - C::NSH;
+							acc += (rw[k / PER] >> (C::DBITS * (k % PER))) & C::DMASK;
+							ls += acc > tcs;
+						}
+					}
+#pragma unroll
+					for (int L = C::L0 + C::NSH - 1; L >= C::L0; --L) {
+						acc += (word >> (HB * (L - C::L0))) & C::FMASK;
+						ls += acc > tcs;
+					}
+#pragma unroll
+					for (int k = 0; k < C::KD; ++k) {
+						ls += dense[k] > tcs;
+					}
+				}
+			} else {
+				uint32_t cnt[32];
+				uint32_t acc = 0;
 #pragma unroll
 				for (int L = 32; L >= C::L0 + C::NSH; --L) {
 					const int k = L - C::L0 - C::NSH;
-					acc = min(acc + ((rw[k / PER] >> (C::DBITS * (k % PER))) & C::DMASK), C::CAP);
+					if (deep) {
+						acc = min(acc + ((rw[k / PER] >> (C::DBITS * (k % PER))) & C::DMASK), C::CAP);
+					}
 					cnt[L - 1] = acc;
 				}
-			} else {
 #pragma unroll
-				for (int L = 32; L >= C::L0 + C::NSH; --L) {
-					cnt[L - 1] = 0;
+				for (int L = C::L0 + C::NSH - 1; L >= C::L0; --L) {
+					acc = min(acc + ((word >> (HB * (L - C::L0))) & C::FMASK), C::CAP);
+					cnt[L - 1] = acc;
 				}
-			}
 #pragma unroll
-			for (int L = C::L0 + C::NSH - 1; L >= C::L0; --L) {
-				acc = min(acc + ((word >> (HB * (L - C::L0))) & C::FMASK), C::CAP);
-				cnt[L - 1] = acc;
-			}
-#pragma unroll
-			for (int k = 0; k < C::KD; ++k) {
-				cnt[k] = j ? tree_value(st.T[C::KD + k], b) : tree_value(st.T[k], b);
-			}
-			if (live) {
-				prm.lstar[p] = (uint8_t)lstar_from_counts(cnt, prm.t);
-				if (prm.H != nullptr) {
+				for (int k = 0; k < C::KD; ++k) {
+					cnt[k] = dense[k];
+				}
+				ls = lstar_from_counts(cnt, prm.t);
+				if (live) {
 					store_row(prm.H, p, cnt);
 				}
+			}
+			/* 4 positions per store where the whole group is live and the output is aligned */
+			pack |= ls << (8 * (jb & 3));
+			if ((jb & 3) == 3) {
+				if (aligned4 && live) {
+					*reinterpret_cast<uint32_t *>(prm.lstar + (p - 3)) = pack;
+				} else {
+#pragma unroll
+					for (int k = 0; k < 4; ++k) {
+						if (p - 3 + k < prm.n) {
+							prm.lstar[p - 3 + k] = (uint8_t)(pack >> (8 * k));
+						}
+					}
+				}
+				pack = 0;
 			}
 		}
 	}
@@ -911,5 +961,13 @@ cudaError_t x3k_launch_stream(bool full, X3SearchParams prm, cudaStream_t stream
 	if (e != cudaSuccess) {
 		return e;
 	}
-	return full ? stream_launch<8, 15>(prm, grid, stream, launches) : stream_launch<4, 6>(prm, grid, stream, launches);
+	e = full ? stream_launch<8, 15>(prm, grid, stream, launches) : stream_launch<4, 6>(prm, grid, stream, launches);
+	if (e == cudaSuccess && getenv("X3_TRACE") != nullptr) {
+		unsigned int c[4] = {0, 0, 0, 0};
+		cudaStreamSynchronize(stream);
+		cudaMemcpy(c, prm.tile_counter, sizeof(c), cudaMemcpyDeviceToHost);
+		fprintf(stderr, "x3k_launch_stream: probe %u pushes / %u units = %.2f %% -> %d dense levels\n", c[1], c[2],
+		        c[2] ? 100.0 * c[1] / c[2] : 0.0, prm.kd == 2 || prm.kd == 3 ? prm.kd : (c[1] * 32u > c[2] ? 3 : 2));
+	}
+	return e;
 }
