@@ -4,11 +4,16 @@
  * operand order, strict '>' tie order), same coded intervals: the stream is the
  * reference's, bit for bit.
  */
+#define _POSIX_C_SOURCE 200809L
 #include "x3_host.h"
 
 #include <math.h>
+#include <pthread.h>
+#include <sched.h>
+#include <stdatomic.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 struct x3_codec {
 	struct x3_dict *dict;
@@ -19,6 +24,10 @@ struct x3_codec {
 	struct x3_ac ac;
 	struct x3_stats st;
 	int nl;
+	/* id of the pair (carry_t0, carry_t1) registered by the previous tag event: it is exactly the
+	 * (prev_context1, context1) the next tag event asks for (x3.c:138-145 after x3.c:213-222) */
+	int carry_valid;
+	uint32_t carry_t0, carry_t1, carry_id;
 };
 
 static struct x3_codec *g_codec = NULL; /* for the dictionary callbacks of the search backend */
@@ -122,7 +131,34 @@ static uint32_t dec_symbol(struct x3_codec *c, struct x3_bitr *r, struct x3_mode
 	return sym;
 }
 
-/* contexts and tag pair update shared by encode_tag / decode_tag (x3.c:95-129,197-222) */
+/* (prev_context1, context1) -> linear context id, 0 when the pair is unknown (x3.c:138-145) */
+static uint32_t ctx0_lookup(struct x3_codec *c, uint32_t prev_context1, uint32_t context1)
+{
+	if (c->carry_valid && c->carry_t0 == prev_context1 && c->carry_t1 == context1) {
+		return c->carry_id;
+	}
+	const int64_t id = x3_pairmap_query(c->pairs, prev_context1, context1);
+	return id < 0 ? 0u : (uint32_t)id;
+}
+
+/* (context1, tag) constitutes a new pair of tags (x3.c:211-222).  The pair map is independent of
+ * the contexts, so the encoder registers the pair before it touches them: the id is the next tag
+ * event's ctx0 id, whose cache line can be fetched while this event is being coded. */
+static void register_pair(struct x3_codec *c, uint32_t context1, uint32_t tag)
+{
+	int64_t id = x3_pairmap_query(c->pairs, context1, tag);
+	if (id < 0) {
+		id = x3_pairmap_add(c->pairs, context1, tag);
+	}
+	const struct x3_ctx *nx = x3_ctxset_get(c->ctx0, (uint32_t)id); /* enlarge_ctx0 */
+	__builtin_prefetch(nx, 1, 1);
+	c->carry_valid = 1;
+	c->carry_t0 = context1;
+	c->carry_t1 = tag;
+	c->carry_id = (uint32_t)id;
+}
+
+/* context update shared by encode_tag / decode_tag (x3.c:95-110,197-209) */
 static void update_contexts(struct x3_codec *c, uint32_t ctx0_id, uint32_t context1, uint32_t tag, int64_t item0,
                             int64_t item1)
 {
@@ -136,11 +172,6 @@ static void update_contexts(struct x3_codec *c, uint32_t ctx0_id, uint32_t conte
 	} else {
 		x3_ctx_inc(c->ctx1, context1, (uint32_t)item1);
 	}
-	/* (context1, tag) constitutes a new pair of tags */
-	if (x3_pairmap_query(c->pairs, context1, tag) < 0) {
-		const uint32_t id = x3_pairmap_add(c->pairs, context1, tag);
-		(void)x3_ctxset_get(c->ctx0, id); /* enlarge_ctx0 */
-	}
 }
 
 /* encode_tag, x3.c:132-223.  `tag` is the element, `index` its position in the
@@ -148,8 +179,8 @@ static void update_contexts(struct x3_codec *c, uint32_t ctx0_id, uint32_t conte
 static void encode_tag(struct x3_codec *c, struct x3_bitw *w, uint32_t prev_context1, uint32_t context1,
                        uint32_t tag, uint32_t index)
 {
-	int64_t id = x3_pairmap_query(c->pairs, prev_context1, context1);
-	const uint32_t ctx0_id = id < 0 ? 0u : (uint32_t)id; /* x3.c:141-145 */
+	const uint32_t ctx0_id = ctx0_lookup(c, prev_context1, context1);
+	register_pair(c, context1, tag);
 
 	const int64_t item0 = x3_ctx_find(c->ctx0, ctx0_id, tag);
 	const int64_t item1 = x3_ctx_find(c->ctx1, context1, tag);
@@ -223,6 +254,124 @@ static void encode_match(struct x3_codec *c, struct x3_bitw *w, const uint8_t *p
 	c->st.events[X3_E_NEW]++;
 }
 
+/*
+ * compress() is split into two stages that only communicate forwards:
+ *
+ *   parse  (x3.c:379-383,392-427 minus the coding): dictionary lookup, find_best_match(),
+ *          hit/miss decision, move-to-front bookkeeping.  Depends on the dictionary only.
+ *   code   (encode_tag / encode_match, x3.c:132-270): contexts, tag pairs, adaptive models,
+ *          arithmetic coder, statistics.  Never feeds back into the parse.
+ *
+ * So the stages run as a two-thread pipeline over a single-producer/single-consumer ring of
+ * step records; with X3_THREADS=1 the same two functions run in one thread.  The stream does not
+ * depend on the mode (tests compare both with the reference).
+ */
+struct step_rec {
+	uint32_t a;   /* hit: the element's tag;            miss: fragment length */
+	uint32_t b;   /* hit: REC_HIT | MTF index;          miss: 1 if the fragment entered the dictionary */
+	uint64_t off; /* miss: offset of the fragment in the input */
+};
+#define REC_HIT 0x80000000u
+#define RING_LOG 15
+#define RING_SIZE (1u << RING_LOG)
+#define RING_BATCH 256u
+
+struct coder_state {
+	struct x3_codec *c;
+	struct x3_bitw *w;
+	const uint8_t *base;
+	uint32_t prev_context1, context1; /* x3.c:376-377 */
+	uint32_t dict_elems;
+};
+
+static void code_step(struct coder_state *cs, const struct step_rec *r)
+{
+	struct x3_codec *c = cs->c;
+	if (r->b & REC_HIT) {
+		encode_tag(c, cs->w, cs->prev_context1, cs->context1, r->a, r->b & ~REC_HIT);
+		cs->prev_context1 = cs->context1;
+		cs->context1 = r->a; /* dict_get_tag_by_index, x3.c:389-390 */
+	} else {
+		encode_match(c, cs->w, cs->base + r->off, r->a);
+		if (r->b) {
+			(void)x3_ctxset_get(c->ctx1, cs->dict_elems); /* enlarge_ctx1, x3.c:414-415 */
+			cs->dict_elems++;
+			x3_model_append(&c->index1); /* x3.c:419 */
+		}
+		cs->prev_context1 = 0; /* x3.c:423-424 */
+		cs->context1 = 0;
+	}
+}
+
+/* one parse step at p: fills r, returns the number of bytes consumed */
+static size_t parse_step(struct x3_codec *c, uint8_t *p, uint8_t *ptr, uint8_t *end, x3_fbm_fn fbm, struct step_rec *r)
+{
+	/* (1) look into the dictionary, x3.c:381-383.  find_best_match() is a pure function of
+	 * (p, dictionary state); the reference evaluates it lazily and possibly twice. */
+	const int64_t tag = x3_dict_find_match(c->dict, p);
+	size_t best = 0;
+	int hit = 0;
+	if (tag >= 0) {
+		const size_t dl = x3_dict_len(c->dict, (uint32_t)tag);
+		best = fbm((char *)p);
+		hit = nl_len(c, dl) >= best && p + dl <= end;
+	}
+	if (hit) {
+		const uint32_t len = x3_dict_len(c->dict, (uint32_t)tag);
+		r->a = (uint32_t)tag;
+		r->b = REC_HIT | x3_dict_index_of(c->dict, (uint32_t)tag);
+		r->off = 0;
+		x3_dict_touch(c->dict, (uint32_t)tag); /* dict_set_last_pos + dict_update_costs */
+		return len;
+	}
+	/* (2) new fragment, x3.c:399-428 */
+	size_t len = tag >= 0 ? best : fbm((char *)p);
+	if (p + len > end) {
+		len = (size_t)(end - p);
+	}
+	r->a = (uint32_t)len;
+	r->b = 0;
+	r->off = (uint64_t)(p - ptr);
+	if (!x3_dict_query(c->dict, p, (uint32_t)len)) {
+		x3_dict_insert(c->dict, p, (uint32_t)len);
+		r->b = 1;
+	}
+	return len;
+}
+
+struct ring {
+	struct step_rec *rec;
+	_Atomic uint64_t head; /* records published by the parser */
+	_Atomic uint64_t tail; /* records consumed by the coder */
+	_Atomic int done;
+	struct coder_state *cs;
+};
+
+static void *coder_thread(void *arg)
+{
+	struct ring *rg = arg;
+	uint64_t tail = 0;
+	for (;;) {
+		uint64_t head = atomic_load_explicit(&rg->head, memory_order_acquire);
+		if (head == tail) {
+			if (atomic_load_explicit(&rg->done, memory_order_acquire)) {
+				head = atomic_load_explicit(&rg->head, memory_order_acquire);
+				if (head == tail) {
+					break;
+				}
+			} else {
+				sched_yield();
+				continue;
+			}
+		}
+		for (; tail < head; ++tail) {
+			code_step(rg->cs, &rg->rec[tail & (RING_SIZE - 1)]);
+		}
+		atomic_store_explicit(&rg->tail, tail, memory_order_release);
+	}
+	return NULL;
+}
+
 void *x3_compress(struct x3_codec *c, char *base, size_t isize, x3_fbm_fn fbm, size_t *out_bytes)
 {
 	struct x3_bitw w;
@@ -232,43 +381,67 @@ void *x3_compress(struct x3_codec *c, char *base, size_t isize, x3_fbm_fn fbm, s
 
 	uint8_t *ptr = (uint8_t *)base;
 	uint8_t *end = ptr + isize;
-	uint32_t prev_context1 = 0, context1 = 0; /* x3.c:376-377 */
+	struct coder_state cs = {c, &w, ptr, 0, 0, x3_dict_elems(c->dict)};
 
-	for (uint8_t *p = ptr; p < end;) {
-		/* (1) look into the dictionary, x3.c:381-383.  find_best_match() is a pure function of
-		 * (p, dictionary state); the reference evaluates it lazily and possibly twice. */
-		const int64_t tag = x3_dict_find_match(c->dict, p);
-		size_t best = 0;
-		int hit = 0;
-		if (tag >= 0) {
-			const size_t dl = x3_dict_len(c->dict, (uint32_t)tag);
-			best = fbm((char *)p);
-			hit = nl_len(c, dl) >= best && p + dl <= end;
+	const char *env = getenv("X3_THREADS");
+	const int threads = env != NULL ? atoi(env) : 2;
+	if (threads == -1) {
+		/* stage timing aid: parse everything, then code everything */
+		struct step_rec *all = malloc(sizeof(struct step_rec) * (isize + 1));
+		size_t nrec = 0;
+		struct timespec t0, t1, t2;
+		clock_gettime(CLOCK_MONOTONIC, &t0);
+		for (uint8_t *p = ptr; p < end;) {
+			p += parse_step(c, p, ptr, end, fbm, &all[nrec++]);
 		}
-		if (hit) {
-			const uint32_t len = x3_dict_len(c->dict, (uint32_t)tag);
-			const uint32_t index = x3_dict_index_of(c->dict, (uint32_t)tag);
-			encode_tag(c, &w, prev_context1, context1, (uint32_t)tag, index);
-			prev_context1 = context1;
-			context1 = (uint32_t)tag; /* dict_get_tag_by_index */
-			x3_dict_touch(c->dict, (uint32_t)tag); /* dict_set_last_pos + dict_update_costs */
-			p += len;
-		} else {
-			/* (2) new fragment, x3.c:399-428 */
-			size_t len = tag >= 0 ? best : fbm((char *)p);
-			if (p + len > end) {
-				len = (size_t)(end - p);
-			}
-			encode_match(c, &w, p, len);
-			if (!x3_dict_query(c->dict, p, (uint32_t)len)) {
-				x3_dict_insert(c->dict, p, (uint32_t)len);
-				(void)x3_ctxset_get(c->ctx1, x3_dict_elems(c->dict) - 1); /* enlarge_ctx1 */
-				x3_model_append(&c->index1);
-			}
-			p += len;
-			prev_context1 = 0;
-			context1 = 0;
+		clock_gettime(CLOCK_MONOTONIC, &t1);
+		for (size_t i = 0; i < nrec; ++i) {
+			code_step(&cs, &all[i]);
 		}
+		clock_gettime(CLOCK_MONOTONIC, &t2);
+		fprintf(stderr, "x3_compress stages: parse %.3f s, code %.3f s, %zu steps\n",
+		        (t1.tv_sec - t0.tv_sec) + (t1.tv_nsec - t0.tv_nsec) * 1e-9,
+		        (t2.tv_sec - t1.tv_sec) + (t2.tv_nsec - t1.tv_nsec) * 1e-9, nrec);
+		free(all);
+	} else if (threads <= 1 || isize < 65536) {
+		struct step_rec r;
+		for (uint8_t *p = ptr; p < end;) {
+			p += parse_step(c, p, ptr, end, fbm, &r);
+			code_step(&cs, &r);
+		}
+	} else {
+		struct ring rg;
+		rg.rec = malloc(sizeof(struct step_rec) * RING_SIZE);
+		if (rg.rec == NULL) {
+			abort();
+		}
+		atomic_init(&rg.head, 0);
+		atomic_init(&rg.tail, 0);
+		atomic_init(&rg.done, 0);
+		rg.cs = &cs;
+		pthread_t th;
+		if (pthread_create(&th, NULL, coder_thread, &rg) != 0) {
+			abort();
+		}
+		uint64_t head = 0, published = 0, tail_seen = 0;
+		for (uint8_t *p = ptr; p < end;) {
+			while (head - tail_seen >= RING_SIZE) { /* ring full: wait for the coder */
+				tail_seen = atomic_load_explicit(&rg.tail, memory_order_acquire);
+				if (head - tail_seen >= RING_SIZE) {
+					sched_yield();
+				}
+			}
+			p += parse_step(c, p, ptr, end, fbm, &rg.rec[head & (RING_SIZE - 1)]);
+			++head;
+			if (head - published >= RING_BATCH) {
+				atomic_store_explicit(&rg.head, head, memory_order_release);
+				published = head;
+			}
+		}
+		atomic_store_explicit(&rg.head, head, memory_order_release);
+		atomic_store_explicit(&rg.done, 1, memory_order_release);
+		pthread_join(th, NULL);
+		free(rg.rec);
 	}
 
 	/* signal end of input, x3.c:431-433 */
@@ -284,8 +457,7 @@ void *x3_compress(struct x3_codec *c, char *base, size_t isize, x3_fbm_fn fbm, s
 static uint32_t decode_tag(struct x3_codec *c, struct x3_bitr *r, uint32_t decision, uint32_t prev_context1,
                            uint32_t context1)
 {
-	int64_t id = x3_pairmap_query(c->pairs, prev_context1, context1);
-	const uint32_t ctx0_id = id < 0 ? 0u : (uint32_t)id;
+	const uint32_t ctx0_id = ctx0_lookup(c, prev_context1, context1);
 	const struct x3_ctx *c0 = x3_ctxset_get(c->ctx0, ctx0_id);
 	const struct x3_ctx *c1 = x3_ctxset_get(c->ctx1, context1);
 
@@ -325,6 +497,7 @@ static uint32_t decode_tag(struct x3_codec *c, struct x3_bitr *r, uint32_t decis
 	const int64_t item0 = x3_ctx_find(c->ctx0, ctx0_id, tag);
 	const int64_t item1 = x3_ctx_find(c->ctx1, context1, tag);
 	update_contexts(c, ctx0_id, context1, tag, item0, item1);
+	register_pair(c, context1, tag);
 	return tag;
 }
 
