@@ -1,37 +1,73 @@
 """Prints the handful of ncu metrics the profiles/ summaries quote.
 
     ncu -i X.ncu-rep --page raw --csv > raw.csv ; python tests/ncu_summary.py raw.csv
+    python tests/ncu_summary.py --launches launches.csv      # per-kernel totals of a launch list
 """
 import csv
 import sys
+from collections import defaultdict
 
-WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "launch__registers_per_thread",
-        "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit",
-        "launch__waves_per_multiprocessor", "sm__warps_active.avg.pct_of_peak_sustained_active",
-        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.sum.pct",
-        "sm__inst_executed_pipe_alu.sum ", "sm__inst_executed_pipe_fma.sum.pct", "sm__inst_executed_pipe_lsu.sum.pct",
-        "sm__inst_executed_pipe_lsu.sum ", "sm__pipe_alu_cycles_active.avg.pct", "smsp__inst_executed.sum ",
-        "sm__inst_executed.sum ", "sm__inst_executed_pipe_fmaheavy", "sm__inst_executed_pipe_fmalite",
-        "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "smsp__average_warp_latency_per_inst_issued", "smsp__average_warps_issue_stalled",
-        "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum ",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct", "sm__cycles_elapsed.max", "sm__cycles_active.avg ",
-        "smsp__warps_eligible.avg.per_cycle_active", "lts__t_sectors_op_read.sum ", "lts__t_sectors_op_write.sum ",
-        "lts__t_bytes.sum ", "sm__inst_executed_pipe_xu", "sm__inst_executed_pipe_adu", "sm__inst_executed_pipe_cbu",
-        "sm__inst_executed_pipe_uniform", "smsp__cycles_active.avg ", "sm__pipe_shared_cycles_active",
-        "l1tex__lsu_writeback_active", "smsp__inst_executed_op_shared", "smsp__inst_issued.avg.per_cycle_active"]
+WANT = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "launch__grid_size", "launch__block_size", "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic",
+    "launch__occupancy_limit_shared_mem", "launch__occupancy_limit_registers", "launch__waves_per_multiprocessor",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "smsp__thread_inst_executed_per_inst_executed.ratio",
+    "sm__inst_executed_pipe_alu.sum.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_adu.sum.pct_of_peak_sustained_active", "sm__inst_executed_pipe_cbu.sum.pct_of_peak_sustained_active",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+    "smsp__average_warp_latency_per_inst_issued.ratio", "smsp__warps_eligible.avg.per_cycle_active",
+    "sm__cycles_elapsed.max", "sm__cycles_active.avg",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+]
 
 
-def main(path):
+def raw(path):
     rows = list(csv.reader(open(path)))
     hdr = rows[0]
     for row in rows[2:]:
-        print("==", row[hdr.index("Kernel Name")][:90])
+        print("==", row[hdr.index("Kernel Name")][:110])
         for h, u, v in zip(hdr, rows[1], row):
-            name = h.split(".", 2)[-1] if h.count(".") >= 3 and h.split(".")[1].startswith("Triage") else h
-            if any((name + " ").startswith(w) or name.startswith(w) for w in WANT):
-                print(f"{name} [{u}] = {v}")
+            if h in WANT:
+                print(f"{h} [{u}] = {v}")
+
+
+def launches(path):
+    lines = open(path).read().splitlines()
+    start = next(i for i, ln in enumerate(lines) if ln.startswith('"ID"'))
+    rows = list(csv.DictReader(lines[start:]))
+    agg = defaultdict(lambda: [0, 0.0])
+    for r in rows:
+        if r["Metric Name"] != "gpu__time_duration.sum":
+            continue
+        v = float(r["Metric Value"].replace(",", ""))
+        v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(r["Metric Unit"], 1e-6)
+        k = (r["Kernel Name"][:100], r["Grid Size"], r["Block Size"])
+        agg[k][0] += 1
+        agg[k][1] += v
+    tot = sum(v[1] for v in agg.values())
+    print(f"{len(rows)} launches, {tot:.3f} ms of device time")
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"{v[0]:5d} x  {v[1]:10.3f} ms  {100 * v[1] / tot:5.1f} %  grid {k[1]} block {k[2]}  {k[0]}")
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if sys.argv[1] == "--launches":
+        launches(sys.argv[2])
+    else:
+        raw(sys.argv[1])
