@@ -41,6 +41,8 @@ extern "C" {
 #define X3S_KERNEL_BITSLICED 2 /* first bit-sliced version (thread-private u8 histograms); kept for comparison */
 #define X3S_KERNEL_STREAM    3 /* same as DEFAULT */
 #define X3S_KERNEL_STREAM_FULL 4 /* stream kernel, u8 counters forced (what H != NULL or t > 15 selects) */
+#define X3S_KERNEL_RANK      5 /* occurrence-rank search: sorts positions by L-gram level by level; Lstar only
+                                * (d_H must be NULL), cost independent of W and t */
 
 typedef struct x3s_timing {
 	double h2d_ms;    /* host -> device copies (max over GPUs) */

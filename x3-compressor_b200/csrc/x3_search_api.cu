@@ -393,6 +393,7 @@ void x3s_release(void)
 			cudaFree(g_scratch[g].counter);
 			cudaFree(g_scratch[g].deep);
 			cudaEventDestroy(g_scratch[g].last);
+			x3k_rank_release((int)g);
 			g_scratch[g] = Scratch();
 			g_kernel_inited[g] = false;
 		}

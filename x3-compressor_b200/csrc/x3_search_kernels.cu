@@ -469,7 +469,7 @@ cudaError_t x3k_init_device(void)
 	return x3k_stream_init_device();
 }
 
-/* variant: 0/3 stream (production), 1 naive, 2 bitsliced (first version) */
+/* variant: 0/3 stream (production), 1 naive, 2 bitsliced (first version), 4 stream with u8 counters, 5 rank */
 cudaError_t x3k_launch(int variant, const X3SearchParams &prm, cudaStream_t stream, int *launches)
 {
 	if (prm.n == 0) {
@@ -477,6 +477,9 @@ cudaError_t x3k_launch(int variant, const X3SearchParams &prm, cudaStream_t stre
 	}
 	if (launches != nullptr && (variant == 1 || variant == 2)) {
 		*launches += 1;
+	}
+	if (variant == 5) {
+		return x3k_launch_rank(prm, stream, launches);
 	}
 	if (variant == 1) {
 		const unsigned long long grid = (prm.n + NAIVE_T - 1) / NAIVE_T;

@@ -37,6 +37,13 @@ size_t x3k_required_bytes(size_t n, size_t W);
 /* Launches the chosen variant on `stream`.  Returns the CUDA error of the launch. */
 cudaError_t x3k_launch(int variant, const X3SearchParams &prm, cudaStream_t stream, int *launches);
 
+/* Rank search (x3_search_rank.cu): Lstar only, any t <= 254, D <= x3k_rank_max_distances().
+ * Issues its launches on `stream` but returns only after the last level has reported its
+ * size (one small read-back per level).  cudaErrorNotSupported when H is requested. */
+cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int *launches);
+uint32_t x3k_rank_max_distances(void);
+void x3k_rank_release(int device);
+
 /* One-time per-device setup (opt-in shared memory size). */
 cudaError_t x3k_init_device(void);
 

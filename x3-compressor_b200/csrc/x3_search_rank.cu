@@ -1,0 +1,720 @@
+/*
+ * x3_search_rank.cu -- "rank" search: the forward-window search of reference
+ * backend.c:58-78 as an occurrence-rank problem, sm_100a.
+ *
+ * The brute-force kernels test every (position, distance) pair: N * (W - 33) byte
+ * compares.  The selection of backend.c:76-78 never needs the counts themselves, only
+ * whether count_L(p) exceeds tc*(p) = min(t, count_1(p) - 1):
+ *
+ *     count_L(p) > k   <=>   the (k+1)-th next occurrence of the L-gram x[p..p+L)
+ *                            starts at most D = W - 33 bytes behind p.
+ *
+ * So level L keeps an array of positions sorted by (L-gram, position); in that order the
+ * test is ONE lookup: the element k+1 places further on has the same L-gram and lies
+ * within D.  Lstar(p) is the deepest level at which p passes (counts are monotone in L).
+ *
+ *   level 1   all M = n + D positions (the D positions behind the searched range are
+ *             followers only), stable counting sort by the byte.  Positions whose byte
+ *             occurs at most t times in their window (tc* < t) are settled here by
+ *             walking their <= t followers: Lstar = min LCP32 (0 when fewer than 2).
+ *   level L   x3_rank_level_kernel, one pass over the sorted array:
+ *               passed(i) = key[i+t+1] == key[i] and pos[i+t+1] - pos[i] <= D  -> Lstar[pos] = L
+ *               kept(i)   = i lies within D behind a passed element of its group
+ *                           (anything else can never be a follower that matters; any
+ *                           superset is exact because every kept element is a real
+ *                           position with its real L-gram)
+ *               new key   = (group rank << 8) | x[pos + L]; compacted with a single-pass
+ *                           chained scan (decoupled look-back over tile aggregates)
+ *             then a stable LSD radix sort of the survivors by the new key
+ *             (x3_rank_radix_kernel: one pass per 8 bits, per-digit decoupled look-back,
+ *             warp-level match ranking), which restores (gram, position) order.
+ *
+ * The work is sum_L m_L element visits instead of N * D pair tests: 3.5 N on text at the
+ * default window, and it does not grow with the window or with t.  Everything is plain
+ * coalesced streaming over 4-byte keys and positions plus one byte gather per element, i.e.
+ * bound by HBM/L2 bandwidth, not by the ALU pipe.
+ *
+ * Inputs larger than 2^24 - D positions are searched chunk by chunk (ranks and chunk-relative
+ * positions then fit 24 bits, so a key is 32 bits).  Lstar only: the 32-bin table H is the
+ * brute-force kernels' job.
+ */
+#include "x3_search_device.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+
+namespace {
+
+constexpr int LV_THREADS = 256;
+constexpr int LV_ITEMS = 8;
+constexpr int LV_TILE = LV_THREADS * LV_ITEMS;
+constexpr int RS_THREADS = 256;
+constexpr int RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = 16;
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr uint32_t RANK_MAX_M = (1u << 24) - 1u;
+
+constexpr unsigned long long ST_AGG = 1ull, ST_INC = 2ull;
+
+struct RankCtrl {
+	uint32_t m[36];             /* m[L]: length of the level-L array (m[1] = M) */
+	uint32_t groups[36];        /* groups[L]: rank range of the level-L keys (groups[1] = 1) */
+	uint32_t tickets[256];      /* one tile dispenser per launch */
+	uint32_t hist[34][4][256];  /* digit histograms of the level-L keys */
+};
+
+struct RankArgs {
+	const uint8_t *x;   /* chunk base */
+	uint8_t *lstar;     /* chunk base */
+	uint32_t n_out;     /* positions searched: [0, n_out) */
+	uint32_t M;         /* elements: n_out + D */
+	uint32_t D;
+	int t;
+	RankCtrl *ctrl;
+	unsigned long long *st_level; /* [tiles of the level kernel] */
+	unsigned long long *st_radix; /* [tiles of the radix kernel][256] */
+};
+
+/* ---- block-wide scans over 256 threads ------------------------------------------------ */
+
+__device__ __forceinline__ unsigned long long block_excl_sum(unsigned long long v, unsigned long long *ws,
+                                                             unsigned long long *total)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned long long inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const unsigned long long o = __shfl_up_sync(FULL_MASK, inc, d);
+		if (lane >= d) {
+			inc += o;
+		}
+	}
+	if (lane == 31) {
+		ws[warp] = inc;
+	}
+	__syncthreads();
+	if (warp == 0) {
+		const unsigned long long w = lane < LV_THREADS / 32 ? ws[lane] : 0ull;
+		unsigned long long wi = w;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const unsigned long long o = __shfl_up_sync(FULL_MASK, wi, d);
+			if (lane >= d) {
+				wi += o;
+			}
+		}
+		if (lane < LV_THREADS / 32) {
+			ws[lane] = wi - w;
+		}
+		if (lane == LV_THREADS / 32 - 1) {
+			ws[LV_THREADS / 32] = wi;
+		}
+	}
+	__syncthreads();
+	const unsigned long long res = ws[warp] + inc - v;
+	*total = ws[LV_THREADS / 32];
+	__syncthreads();
+	return res;
+}
+
+/* exclusive running maximum; `ident` is what the first thread sees */
+__device__ __forceinline__ int block_excl_max(int v, int ident, int *ws)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const int o = __shfl_up_sync(FULL_MASK, inc, d);
+		if (lane >= d) {
+			inc = max(inc, o);
+		}
+	}
+	if (lane == 31) {
+		ws[warp] = inc;
+	}
+	__syncthreads();
+	int before = ident; /* maximum over the warps in front of mine */
+	for (int w = 0; w < warp; ++w) {
+		before = max(before, ws[w]);
+	}
+	int ex = __shfl_up_sync(FULL_MASK, inc, 1);
+	if (lane == 0) {
+		ex = ident;
+	}
+	__syncthreads();
+	return max(before, ex);
+}
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p)
+{
+	unsigned long long v;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v)
+{
+	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+/* ---- level 1 set-up: byte histogram of the M elements ---------------------------------- */
+
+__global__ void __launch_bounds__(256) x3_rank_bytehist_kernel(RankArgs a)
+{
+	__shared__ uint32_t h[256];
+	h[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t nvec = a.M / 16;
+	const uint4 *xv = reinterpret_cast<const uint4 *>(a.x);
+	for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += gridDim.x * blockDim.x) {
+		const uint4 q = __ldg(xv + v);
+		const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+		for (int k = 0; k < 4; ++k) {
+			atomicAdd(&h[w[k] & 255u], 1u);
+			atomicAdd(&h[(w[k] >> 8) & 255u], 1u);
+			atomicAdd(&h[(w[k] >> 16) & 255u], 1u);
+			atomicAdd(&h[w[k] >> 24], 1u);
+		}
+	}
+	if (blockIdx.x == 0) {
+		for (uint32_t i = nvec * 16 + threadIdx.x; i < a.M; i += blockDim.x) {
+			atomicAdd(&h[a.x[i]], 1u);
+		}
+		if (threadIdx.x == 0) {
+			a.ctrl->m[1] = a.M;
+			a.ctrl->groups[1] = 1;
+		}
+	}
+	__syncthreads();
+	if (h[threadIdx.x] != 0) {
+		atomicAdd(&a.ctrl->hist[1][0][threadIdx.x], h[threadIdx.x]);
+	}
+}
+
+/* ---- one stable 8-bit radix pass -------------------------------------------------------
+ * INIT: the elements are the positions 0 .. M-1 themselves, key = x[pos] (level 1). */
+template <bool INIT>
+__global__ void __launch_bounds__(RS_THREADS) x3_rank_radix_kernel(RankArgs a, const uint32_t *__restrict__ keyIn,
+                                                                    const uint32_t *__restrict__ posIn,
+                                                                    uint32_t *__restrict__ keyOut,
+                                                                    uint32_t *__restrict__ posOut, int level, int pass,
+                                                                    int ticket, uint32_t epoch)
+{
+	__shared__ uint32_t gbase[256];
+	__shared__ uint32_t wcnt[RS_WARPS][256];
+	__shared__ uint32_t tbase[256];
+	__shared__ uint32_t s_tile;
+	__shared__ uint32_t wsum[RS_WARPS + 1];
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t m = a.ctrl->m[level];
+	const uint32_t ntiles = (m + RS_TILE - 1) / RS_TILE;
+	const int shift = 8 * pass;
+	const uint32_t lt = (1u << lane) - 1u;
+
+	/* exclusive scan of this pass's global digit histogram */
+	{
+		const uint32_t h = a.ctrl->hist[level][pass][tid];
+		uint32_t inc = h;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t o = __shfl_up_sync(FULL_MASK, inc, d);
+			if (lane >= d) {
+				inc += o;
+			}
+		}
+		if (lane == 31) {
+			wsum[warp] = inc;
+		}
+		__syncthreads();
+		uint32_t before = 0;
+		for (int w = 0; w < warp; ++w) {
+			before += wsum[w];
+		}
+		gbase[tid] = before + inc - h;
+		__syncthreads();
+	}
+
+	for (;;) {
+		if (tid == 0) {
+			s_tile = atomicAdd(&a.ctrl->tickets[ticket], 1u);
+		}
+#pragma unroll
+		for (int w = 0; w < RS_WARPS; ++w) {
+			wcnt[w][tid] = 0;
+		}
+		__syncthreads();
+		const uint32_t tile = s_tile;
+		if (tile >= ntiles) {
+			break;
+		}
+		const uint32_t base = tile * RS_TILE + warp * (32 * RS_ITEMS);
+		uint32_t key[RS_ITEMS], pos[RS_ITEMS], off[RS_ITEMS];
+#pragma unroll
+		for (int k = 0; k < RS_ITEMS; ++k) {
+			const uint32_t i = base + 32 * k + lane;
+			const bool valid = i < m;
+			if (INIT) {
+				key[k] = valid ? (uint32_t)__ldg(a.x + i) : 0u;
+				pos[k] = i;
+			} else {
+				key[k] = valid ? keyIn[i] : 0u;
+				pos[k] = valid ? posIn[i] : 0u;
+			}
+			const uint32_t d = valid ? ((key[k] >> shift) & 255u) : 256u;
+			const uint32_t peers = __match_any_sync(FULL_MASK, d);
+			const int leader = __ffs(peers) - 1;
+			uint32_t old = 0;
+			if (lane == leader && valid) {
+				old = wcnt[warp][d];
+				wcnt[warp][d] = old + __popc(peers);
+			}
+			old = __shfl_sync(FULL_MASK, old, leader);
+			off[k] = valid ? (old + __popc(peers & lt)) | (d << 16) : 0xffffffffu;
+			__syncwarp();
+		}
+		__syncthreads();
+		/* digit tid: offsets of the warps inside the tile, tile total, look-back */
+		{
+			uint32_t run = 0;
+#pragma unroll
+			for (int w = 0; w < RS_WARPS; ++w) {
+				const uint32_t c = wcnt[w][tid];
+				wcnt[w][tid] = run;
+				run += c;
+			}
+			unsigned long long *mine = a.st_radix + (size_t)tile * 256 + tid;
+			const unsigned long long ep = (unsigned long long)epoch << 32;
+			uint32_t excl = 0;
+			if (tile == 0) {
+				st_status(mine, ep | (ST_INC << 30) | run);
+			} else {
+				st_status(mine, ep | (ST_AGG << 30) | run);
+				const unsigned long long *look = mine - 256;
+				for (;;) {
+					const unsigned long long s = ld_status(look);
+					if ((s >> 32) != epoch || ((s >> 30) & 3ull) == 0ull) {
+						continue; /* not published yet */
+					}
+					excl += (uint32_t)(s & 0x3fffffffull);
+					if (((s >> 30) & 3ull) == ST_INC) {
+						break;
+					}
+					look -= 256;
+				}
+				st_status(mine, ep | (ST_INC << 30) | (excl + run));
+			}
+			tbase[tid] = gbase[tid] + excl;
+		}
+		__syncthreads();
+#pragma unroll
+		for (int k = 0; k < RS_ITEMS; ++k) {
+			if (off[k] != 0xffffffffu) {
+				const uint32_t d = off[k] >> 16;
+				const uint32_t dst = tbase[d] + wcnt[warp][d] + (off[k] & 0xffffu);
+				keyOut[dst] = key[k];
+				posOut[dst] = pos[k];
+			}
+		}
+		__syncthreads();
+	}
+}
+
+/* ---- level 1: positions whose first byte is rare in their window ------------------------
+ * The element did not pass at level 1, so its byte has c1 <= t followers within D:
+ * tc* = c1 - 1 and Lstar = #{L : count_L >= c1} = the smallest LCP32 over those followers
+ * (0 when c1 < 2, backend.c:76-78 collapsed). */
+__device__ __noinline__ uint32_t rank_rare(const uint8_t *__restrict__ x, const uint32_t *__restrict__ key,
+                                          const uint32_t *__restrict__ pos, uint32_t i, uint32_t m, uint32_t kk,
+                                          uint32_t p, uint32_t D, int t)
+{
+	uint32_t best = 32, c1 = 0;
+	for (uint32_t k = i + 1; k < m && c1 <= (uint32_t)t; ++k) {
+		if (key[k] != kk) {
+			break;
+		}
+		const uint32_t q = pos[k];
+		if (q - p > D) {
+			break;
+		}
+		++c1;
+		uint32_t l = 1;
+		while (l < best && x[p + l] == x[q + l]) {
+			++l;
+		}
+		best = l;
+	}
+	return c1 >= 2 ? best : 0u;
+}
+
+/* ---- one level: test, prune, re-key, compact -------------------------------------------- */
+__global__ void __launch_bounds__(LV_THREADS) x3_rank_level_kernel(RankArgs a, const uint32_t *__restrict__ keyIn,
+                                                                    const uint32_t *__restrict__ posIn,
+                                                                    uint32_t *__restrict__ keyOut,
+                                                                    uint32_t *__restrict__ posOut, int L, int ticket)
+{
+	__shared__ uint32_t hist[4][256];
+	__shared__ unsigned long long ws[LV_THREADS / 32 + 1];
+	__shared__ int wsi[LV_THREADS / 32];
+	__shared__ uint32_t s_tile;
+	__shared__ unsigned long long s_excl;
+
+	const int tid = threadIdx.x, lane = tid & 31;
+	const uint32_t m = a.ctrl->m[L];
+	const uint32_t ntiles = (m + LV_TILE - 1) / LV_TILE;
+	const uint32_t D = a.D, n_out = a.n_out;
+	const uint32_t la = (uint32_t)a.t + 1u; /* look-ahead of the test */
+	const bool emit = L < 32;
+	/* digits of the new keys that can be non-zero: ranks are below m */
+	int ndig = 1;
+	while (ndig < 4 && ((m - 1u) >> (8 * (ndig - 1))) != 0u) {
+		++ndig;
+	}
+	if (m == 0) {
+		if (blockIdx.x == 0 && tid == 0) {
+			a.ctrl->m[L + 1] = 0;
+			a.ctrl->groups[L + 1] = 0;
+		}
+		return;
+	}
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		hist[j][tid] = 0;
+	}
+	__syncthreads();
+
+	for (;;) {
+		if (tid == 0) {
+			s_tile = atomicAdd(&a.ctrl->tickets[ticket], 1u);
+		}
+		__syncthreads();
+		const uint32_t tile = s_tile;
+		if (tile >= ntiles) {
+			break;
+		}
+		const uint32_t i0 = tile * LV_TILE + tid * LV_ITEMS;
+		uint32_t k[LV_ITEMS], p[LV_ITEMS];
+		if (i0 + LV_ITEMS <= m) {
+			const uint4 k0 = *reinterpret_cast<const uint4 *>(keyIn + i0), k1 = *reinterpret_cast<const uint4 *>(keyIn + i0 + 4);
+			const uint4 p0 = *reinterpret_cast<const uint4 *>(posIn + i0), p1 = *reinterpret_cast<const uint4 *>(posIn + i0 + 4);
+			k[0] = k0.x; k[1] = k0.y; k[2] = k0.z; k[3] = k0.w; k[4] = k1.x; k[5] = k1.y; k[6] = k1.z; k[7] = k1.w;
+			p[0] = p0.x; p[1] = p0.y; p[2] = p0.z; p[3] = p0.w; p[4] = p1.x; p[5] = p1.y; p[6] = p1.z; p[7] = p1.w;
+		} else {
+#pragma unroll
+			for (int e = 0; e < LV_ITEMS; ++e) {
+				const bool v = i0 + e < m;
+				k[e] = v ? keyIn[i0 + e] : 0u;
+				p[e] = v ? posIn[i0 + e] : 0u;
+			}
+		}
+		/* the test: does the (t+1)-th next element of the array share the gram within D? */
+		uint32_t actm = 0;
+		int mylast = -1;
+#pragma unroll
+		for (int e = 0; e < LV_ITEMS; ++e) {
+			const uint32_t i = i0 + e;
+			if (i >= m) {
+				break;
+			}
+			const uint32_t j = i + la;
+			bool pass = false;
+			if (j < m && __ldg(keyIn + j) == k[e]) {
+				pass = __ldg(posIn + j) - p[e] <= D;
+			}
+			const bool out = p[e] < n_out;
+			if (L == 1 && !pass && out) {
+				a.lstar[p[e]] = (uint8_t)rank_rare(a.x, keyIn, posIn, i, m, k[e], p[e], D, a.t);
+			}
+			if (pass && out) {
+				a.lstar[p[e]] = (uint8_t)L;
+				actm |= 1u << e;
+				mylast = (int)i;
+			}
+		}
+		if (!emit) {
+			__syncthreads();
+			continue;
+		}
+		/* last passed element in front of mine; in front of the tile: pretend its neighbour passed
+		 * (a superset of the exact rule, at most t+1 extra elements per tile) */
+		const int prevlast = block_excl_max(mylast, (int)(tile * LV_TILE) - 1, wsi);
+		bool have = prevlast >= 0;
+		uint32_t rk = 0, rp = 0;
+		if (have) {
+			rk = __ldg(keyIn + prevlast);
+			rp = __ldg(posIn + prevlast);
+		}
+		uint32_t partm = 0, headm = 0;
+		uint32_t kprev = i0 > 0 && i0 <= m ? __ldg(keyIn + i0 - 1) : ~k[0];
+#pragma unroll
+		for (int e = 0; e < LV_ITEMS; ++e) {
+			if (i0 + e < m) {
+				if ((actm >> e) & 1u) {
+					have = true;
+					rk = k[e];
+					rp = p[e];
+				}
+				if (have && rk == k[e] && p[e] - rp <= D) {
+					partm |= 1u << e;
+				}
+				if (k[e] != kprev || i0 + e == 0) {
+					headm |= 1u << e;
+				}
+				kprev = k[e];
+			}
+		}
+		/* chained scan of (kept, heads) over the tiles */
+		const unsigned long long mine = (unsigned long long)__popc(partm) | ((unsigned long long)__popc(headm) << 32);
+		unsigned long long total;
+		const unsigned long long ex = block_excl_sum(mine, ws, &total);
+		if (tid < 32) {
+			const unsigned long long pk = (total & 0xffffffull) | ((total >> 32) << 24);
+			const unsigned long long ep = (unsigned long long)L << 50;
+			unsigned long long excl = 0;
+			if (tile == 0) {
+				if (lane == 0) {
+					st_status(a.st_level + tile, ep | (ST_INC << 48) | pk);
+				}
+			} else {
+				if (lane == 0) {
+					st_status(a.st_level + tile, ep | (ST_AGG << 48) | pk);
+				}
+				int look = (int)tile - 1;
+				for (;;) {
+					const int idx = look - lane;
+					unsigned long long s = 0;
+					bool ready;
+					do {
+						if (idx >= 0) {
+							s = ld_status(a.st_level + idx);
+							ready = (s >> 50) == (unsigned long long)L && ((s >> 48) & 3ull) != 0ull;
+						} else {
+							s = ST_INC << 48; /* in front of tile 0: an empty inclusive prefix */
+							ready = true;
+						}
+					} while (__any_sync(FULL_MASK, !ready));
+					const uint32_t incm = __ballot_sync(FULL_MASK, ((s >> 48) & 3ull) == ST_INC);
+					const int first = incm != 0 ? __ffs(incm) - 1 : 31;
+					unsigned long long v = lane <= first ? (s & 0xffffffffffffull) : 0ull;
+#pragma unroll
+					for (int d = 16; d >= 1; d >>= 1) {
+						v += __shfl_xor_sync(FULL_MASK, v, d);
+					}
+					excl += v; /* both 24-bit fields stay below 2^24: no carry between them */
+					if (incm != 0) {
+						break;
+					}
+					look -= 32;
+				}
+				if (lane == 0) {
+					st_status(a.st_level + tile, ep | (ST_INC << 48) | (excl + pk));
+				}
+			}
+			if (lane == 0) {
+				s_excl = excl;
+				if (tile == ntiles - 1) {
+					const unsigned long long tot = excl + pk;
+					a.ctrl->m[L + 1] = (uint32_t)(tot & 0xffffffull);
+					a.ctrl->groups[L + 1] = (uint32_t)((tot >> 24) & 0xffffffull);
+				}
+			}
+		}
+		__syncthreads();
+		const unsigned long long tex = s_excl;
+		uint32_t dst = (uint32_t)(tex & 0xffffffull) + (uint32_t)(ex & 0xffffffffull);
+		uint32_t hcount = (uint32_t)((tex >> 24) & 0xffffffull) + (uint32_t)(ex >> 32);
+#pragma unroll
+		for (int e = 0; e < LV_ITEMS; ++e) {
+			hcount += (headm >> e) & 1u;
+			if ((partm >> e) & 1u) {
+				const uint32_t nk = ((hcount - 1u) << 8) | (uint32_t)__ldg(a.x + p[e] + L);
+				keyOut[dst] = nk;
+				posOut[dst] = p[e];
+				++dst;
+				atomicAdd(&hist[0][nk & 255u], 1u);
+				for (int j = 1; j < ndig; ++j) {
+					atomicAdd(&hist[j][(nk >> (8 * j)) & 255u], 1u);
+				}
+			}
+		}
+		__syncthreads();
+	}
+	if (emit) {
+		__syncthreads();
+		for (int j = 0; j < ndig; ++j) {
+			if (hist[j][tid] != 0) {
+				atomicAdd(&a.ctrl->hist[L + 1][j][tid], hist[j][tid]);
+			}
+		}
+	}
+}
+
+/* ---- per-device scratch ------------------------------------------------------------------ */
+struct RankScratch {
+	uint32_t cap = 0; /* elements */
+	uint32_t *key[2] = {nullptr, nullptr};
+	uint32_t *pos[2] = {nullptr, nullptr};
+	RankCtrl *ctrl = nullptr;
+	unsigned long long *st_level = nullptr;
+	unsigned long long *st_radix = nullptr;
+	uint32_t *h_back = nullptr; /* pinned: m and groups of the next level */
+	int sms = 0;
+};
+RankScratch g_rank[64];
+
+cudaError_t rank_ensure(int dev, uint32_t M)
+{
+	RankScratch &s = g_rank[dev];
+	cudaError_t e;
+	if (s.ctrl == nullptr) {
+		if ((e = cudaMalloc((void **)&s.ctrl, sizeof(RankCtrl))) != cudaSuccess) return e;
+		if ((e = cudaMallocHost((void **)&s.h_back, 64)) != cudaSuccess) return e;
+		if ((e = cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+	}
+	if (M <= s.cap) {
+		return cudaSuccess;
+	}
+	for (int j = 0; j < 2; ++j) {
+		cudaFree(s.key[j]);
+		cudaFree(s.pos[j]);
+		s.key[j] = s.pos[j] = nullptr;
+	}
+	cudaFree(s.st_level);
+	cudaFree(s.st_radix);
+	s.st_level = s.st_radix = nullptr;
+	s.cap = 0;
+	const size_t cap = ((size_t)M + 4095) & ~(size_t)4095;
+	for (int j = 0; j < 2; ++j) {
+		if ((e = cudaMalloc((void **)&s.key[j], cap * 4 + 64)) != cudaSuccess) return e;
+		if ((e = cudaMalloc((void **)&s.pos[j], cap * 4 + 64)) != cudaSuccess) return e;
+	}
+	if ((e = cudaMalloc((void **)&s.st_level, (cap / LV_TILE + 1) * 8)) != cudaSuccess) return e;
+	if ((e = cudaMalloc((void **)&s.st_radix, (cap / RS_TILE + 1) * 256 * 8)) != cudaSuccess) return e;
+	s.cap = (uint32_t)cap;
+	return cudaSuccess;
+}
+
+int radix_passes(uint32_t groups)
+{
+	int bits = 8;
+	while (groups > 1 && ((groups - 1) >> (bits - 8)) != 0) {
+		++bits;
+	}
+	return (bits + 7) / 8;
+}
+
+} /* namespace */
+
+/* largest number of distances the rank search takes (chunks must keep room for positions) */
+uint32_t x3k_rank_max_distances(void)
+{
+	return 1u << 23;
+}
+
+void x3k_rank_release(int dev)
+{
+	RankScratch &s = g_rank[dev];
+	for (int j = 0; j < 2; ++j) {
+		cudaFree(s.key[j]);
+		cudaFree(s.pos[j]);
+	}
+	cudaFree(s.st_level);
+	cudaFree(s.st_radix);
+	cudaFree(s.ctrl);
+	cudaFreeHost(s.h_back);
+	s = RankScratch();
+}
+
+/*
+ * Lstar for positions [0, prm.n) by the rank method.  The launches are issued on `stream`,
+ * but the call returns only after the last level of the last chunk has reported its size
+ * (one 8-byte read-back per level decides how many radix passes follow).
+ */
+cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int *launches)
+{
+	cudaError_t e;
+	if (prm.H != nullptr || prm.D > x3k_rank_max_distances() || prm.t > 254) {
+		return cudaErrorNotSupported;
+	}
+	if (prm.n == 0) {
+		return cudaSuccess;
+	}
+	if (prm.t <= 0 || prm.D == 0) {
+		/* backend.c:76 never enters the selection / the window holds no distance: return 1 everywhere */
+		return cudaMemsetAsync(prm.lstar, 0, prm.n, stream);
+	}
+	int dev = 0;
+	if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+	const bool trace = getenv("X3_TRACE") != nullptr;
+	const uint32_t D = prm.D;
+	const unsigned long long CH = (unsigned long long)((RANK_MAX_M - D) & ~4095u);
+	const unsigned long long first = prm.n < CH ? prm.n : CH;
+	if ((e = rank_ensure(dev, (uint32_t)(first + D))) != cudaSuccess) return e;
+	RankScratch &s = g_rank[dev];
+	int nl = 0;
+
+	for (unsigned long long a0 = 0; a0 < prm.n; a0 += CH) {
+		RankArgs a;
+		a.x = prm.x + a0;
+		a.lstar = prm.lstar + a0;
+		a.n_out = (uint32_t)(prm.n - a0 < CH ? prm.n - a0 : CH);
+		a.M = a.n_out + D;
+		a.D = D;
+		a.t = prm.t;
+		a.ctrl = s.ctrl;
+		a.st_level = s.st_level;
+		a.st_radix = s.st_radix;
+		const uint32_t lv_tiles = (a.M + LV_TILE - 1) / LV_TILE, rs_tiles = (a.M + RS_TILE - 1) / RS_TILE;
+		if ((e = cudaMemsetAsync(s.ctrl, 0, sizeof(RankCtrl), stream)) != cudaSuccess) return e;
+		if ((e = cudaMemsetAsync(s.st_level, 0, (size_t)lv_tiles * 8, stream)) != cudaSuccess) return e;
+		if ((e = cudaMemsetAsync(s.st_radix, 0, (size_t)rs_tiles * 256 * 8, stream)) != cudaSuccess) return e;
+		int ticket = 0;
+		const int maxgrid = s.sms * 8;
+		auto grid_for = [&](uint32_t tiles) { return (int)(tiles < (uint32_t)maxgrid ? (tiles > 0 ? tiles : 1) : maxgrid); };
+
+		x3_rank_bytehist_kernel<<<grid_for((a.M + 65535) / 65536), 256, 0, stream>>>(a);
+		x3_rank_radix_kernel<true><<<grid_for(rs_tiles), RS_THREADS, 0, stream>>>(a, nullptr, nullptr, s.key[0], s.pos[0], 1, 0,
+		                                                                        ticket, (uint32_t)ticket + 1u);
+		++ticket;
+		nl += 2;
+		int cur = 0;
+		uint32_t m = a.M;
+		for (int L = 1; L <= 32; ++L) {
+			x3_rank_level_kernel<<<grid_for((m + LV_TILE - 1) / LV_TILE), LV_THREADS, 0, stream>>>(
+			    a, s.key[cur], s.pos[cur], s.key[cur ^ 1], s.pos[cur ^ 1], L, ticket);
+			++ticket;
+			++nl;
+			if (L == 32) {
+				break;
+			}
+			if ((e = cudaMemcpyAsync(s.h_back, &s.ctrl->m[L + 1], 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+			if ((e = cudaMemcpyAsync(s.h_back + 1, &s.ctrl->groups[L + 1], 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+			if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+			const uint32_t mn = s.h_back[0], groups = s.h_back[1];
+			const int np = radix_passes(groups);
+			if (trace) {
+				fprintf(stderr, "x3k_launch_rank: chunk %llu level %d: %u elements -> %u kept, %u groups, %d radix passes\n",
+				        a0 / CH, L, m, mn, groups, np);
+			}
+			if (mn < (uint32_t)prm.t + 2u) {
+				break; /* nobody can pass the next level */
+			}
+			int src = cur ^ 1;
+			for (int pass = 0; pass < np; ++pass) {
+				x3_rank_radix_kernel<false><<<grid_for((mn + RS_TILE - 1) / RS_TILE), RS_THREADS, 0, stream>>>(
+				    a, s.key[src], s.pos[src], s.key[src ^ 1], s.pos[src ^ 1], L + 1, pass, ticket, (uint32_t)ticket + 1u);
+				++ticket;
+				++nl;
+				src ^= 1;
+			}
+			cur = src;
+			m = mn;
+		}
+		if ((e = cudaGetLastError()) != cudaSuccess) return e;
+	}
+	if (launches != nullptr) {
+		*launches += nl;
+	}
+	return cudaGetLastError();
+}
