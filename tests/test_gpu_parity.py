@@ -78,6 +78,73 @@ def test_table_equals_oracle_threshold_sweep(pkg, corpus, t):
         _assert_same(pkg, _inputs(corpus, "zeros", 3000), 1024, t, variant)
 
 
+def _assert_rank_same(pkg, data, W, t):
+    """The rank search (variant 5, Lstar only) against the oracle."""
+    lstar, _, _ = pkg.search_host(data, W=W, t=t, ngpus=1, variant=pkg.KERNEL_RANK)
+    _, ls_ref = ol.table(data, W, t)
+    assert np.array_equal(lstar, ls_ref), (f"rank search: Lstar differs first at p={int(np.argmax(lstar != ls_ref))} "
+                                           f"(n={len(data)} W={W} t={t})")
+
+
+@pytest.mark.parametrize("kind,n", [("text", 20000), ("binary", 9001), ("mix", 12345), ("zeros", 5000),
+                                    ("period", 4097), ("rand2", 3968), ("rand256", 3969), ("text", 1),
+                                    ("text", 31), ("text", 33), ("text", 70000), ("binary", 70000)])
+def test_rank_search_equals_oracle_default_flags(pkg, corpus, kind, n):
+    _assert_rank_same(pkg, _inputs(corpus, kind, n), 8192, 15)
+
+
+@pytest.mark.parametrize("W", [0, 1, 33, 34, 35, 64, 65, 100, 1024, 4096, 8191, 8193, 10000, 17000, 65536, 1 << 20])
+def test_rank_search_equals_oracle_window_sweep(pkg, corpus, W):
+    n = 6000 if W <= 65536 else 1500
+    _assert_rank_same(pkg, _inputs(corpus, "text", n), W, 15)
+    _assert_rank_same(pkg, _inputs(corpus, "rand2", min(n, 4500)), W, 3)
+
+
+@pytest.mark.parametrize("t", [0, 1, 2, 3, 15, 16, 64, 200, 254])
+def test_rank_search_equals_oracle_threshold_sweep(pkg, corpus, t):
+    _assert_rank_same(pkg, _inputs(corpus, "mix", 9000), 2048, t)
+    _assert_rank_same(pkg, _inputs(corpus, "zeros", 3000), 1024, t)
+    _assert_rank_same(pkg, _inputs(corpus, "binary", 20000), 8192, t)
+
+
+def test_rank_search_rejects_table_request(pkg):
+    with pytest.raises(pkg.X3SearchError):
+        pkg.search_host(np.zeros(100, dtype=np.uint8), W=8192, t=15, variant=pkg.KERNEL_RANK, want_table=True)
+
+
+@pytest.mark.parametrize("name,n,W,t", [("C2", 10_192_446, 8192, 15), ("C4", 8_474_240, 8192, 15),
+                                        ("C3", 6_000_000, 65536, 64), ("C5", 20_000_000, 8192, 15)])
+def test_rank_search_equals_brute_force_at_full_size(pkg, corpus, name, n, W, t):
+    """Two independent algorithms (pair-test histogram vs occurrence rank) agree bit for bit
+    on BASELINE.json-sized inputs; sampled bands also equal the oracle."""
+    data = np.frombuffer(corpus.generate(name, n), dtype=np.uint8)
+    ls_rank, _, _ = pkg.search_host(data, W=W, t=t, variant=pkg.KERNEL_RANK)
+    ls_bf, _, _ = pkg.search_host(data, W=W, t=t, variant=pkg.KERNEL_STREAM)
+    assert np.array_equal(ls_rank, ls_bf), f"first difference at p={int(np.argmax(ls_rank != ls_bf))}"
+    for a in (0, len(data) - 4000):
+        _, ls_ref = ol.table(data, W, t, p0=a, p1=a + 4000)
+        assert np.array_equal(ls_rank[a:a + 4000], ls_ref)
+
+
+def test_rank_search_chunked_input_equals_brute_force(pkg, corpus):
+    """An input larger than one rank chunk (2^24 - D positions): chunk seams are invisible."""
+    data = np.frombuffer(corpus.generate("C5", 36_000_000), dtype=np.uint8)
+    ls_rank, _, _ = pkg.search_host(data, W=8192, t=15, variant=pkg.KERNEL_RANK)
+    ls_bf, _, _ = pkg.search_host(data, W=8192, t=15, variant=pkg.KERNEL_STREAM)
+    assert np.array_equal(ls_rank, ls_bf), f"first difference at p={int(np.argmax(ls_rank != ls_bf))}"
+
+
+def test_rank_search_max_window_sample(pkg, corpus):
+    """-w 1024 -t 64 (C3's flags): brute force needs 10^12 pair tests here, so sampled bands
+    are checked against the oracle."""
+    data = np.frombuffer(corpus.generate("C3", 3_000_000), dtype=np.uint8)
+    W, t = 1 << 20, 64
+    ls_rank, _, _ = pkg.search_host(data, W=W, t=t, variant=pkg.KERNEL_RANK)
+    for a in (0, 1_500_000, len(data) - 3000):
+        _, ls_ref = ol.table(data, W, t, p0=a, p1=a + 3000)
+        assert np.array_equal(ls_rank[a:a + 3000], ls_ref)
+
+
 def test_empty_and_rejected_inputs(pkg):
     ls, H, _ = pkg.search_host(np.zeros(0, dtype=np.uint8), W=8192, t=15, want_table=True)
     assert len(ls) == 0 and H.shape == (0, 32)

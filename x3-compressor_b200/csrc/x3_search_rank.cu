@@ -53,12 +53,17 @@ constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 16;
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
 constexpr uint32_t RANK_MAX_M = (1u << 24) - 1u;
+constexpr uint32_t PMASK = 0x00ffffffu; /* position bits of a position word */
+constexpr uint32_t PFLAG = 0x80000000u; /* "passed the previous level" */
+constexpr uint32_t KEY_NONE = 0xffffffffu; /* no real key: ranks stay below 2^24 - 1 */
 
 constexpr unsigned long long ST_AGG = 1ull, ST_INC = 2ull;
 
 struct RankCtrl {
-	uint32_t m[36];             /* m[L]: length of the level-L array (m[1] = M) */
-	uint32_t groups[36];        /* groups[L]: rank range of the level-L keys (groups[1] = 1) */
+	struct {
+		uint32_t m;             /* length of the level-L array (lv[1].m = M) */
+		uint32_t groups;        /* rank range of the level-L keys (lv[1].groups = 1) */
+	} lv[36];
 	uint32_t tickets[256];      /* one tile dispenser per launch */
 	uint32_t hist[34][4][256];  /* digit histograms of the level-L keys */
 };
@@ -182,8 +187,8 @@ __global__ void __launch_bounds__(256) x3_rank_bytehist_kernel(RankArgs a)
 			atomicAdd(&h[a.x[i]], 1u);
 		}
 		if (threadIdx.x == 0) {
-			a.ctrl->m[1] = a.M;
-			a.ctrl->groups[1] = 1;
+			a.ctrl->lv[1].m = a.M;
+			a.ctrl->lv[1].groups = 1;
 		}
 	}
 	__syncthreads();
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(RS_THREADS) x3_rank_radix_kernel(RankArgs a, c
 	__shared__ uint32_t wsum[RS_WARPS + 1];
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t m = a.ctrl->m[level];
+	const uint32_t m = a.ctrl->lv[level].m;
 	const uint32_t ntiles = (m + RS_TILE - 1) / RS_TILE;
 	const int shift = 8 * pass;
 	const uint32_t lt = (1u << lane) - 1u;
@@ -256,7 +261,10 @@ __global__ void __launch_bounds__(RS_THREADS) x3_rank_radix_kernel(RankArgs a, c
 			const uint32_t i = base + 32 * k + lane;
 			const bool valid = i < m;
 			if (INIT) {
-				key[k] = valid ? (uint32_t)__ldg(a.x + i) : 0u;
+				/* level-1 key: the byte (the sort digit) with its three successors on top, so that the
+				 * level-1 kernel needs no gathers (4 <= W - 33 - ... bytes behind any element are readable) */
+				const uint32_t *xw = reinterpret_cast<const uint32_t *>(a.x) + (i >> 2);
+				key[k] = valid ? __funnelshift_r(__ldg(xw), __ldg(xw + 1), 8 * (i & 3)) : 0u;
 				pos[k] = i;
 			} else {
 				key[k] = valid ? keyIn[i] : 0u;
@@ -321,50 +329,43 @@ __global__ void __launch_bounds__(RS_THREADS) x3_rank_radix_kernel(RankArgs a, c
 	}
 }
 
-/* ---- level 1: positions whose first byte is rare in their window ------------------------
- * The element did not pass at level 1, so its byte has c1 <= t followers within D:
- * tc* = c1 - 1 and Lstar = #{L : count_L >= c1} = the smallest LCP32 over those followers
- * (0 when c1 < 2, backend.c:76-78 collapsed). */
-__device__ __noinline__ uint32_t rank_rare(const uint8_t *__restrict__ x, const uint32_t *__restrict__ key,
-                                          const uint32_t *__restrict__ pos, uint32_t i, uint32_t m, uint32_t kk,
-                                          uint32_t p, uint32_t D, int t)
+/* After the last level that ran: every element that passed it keeps that level. */
+__global__ void __launch_bounds__(256) x3_rank_flush_kernel(RankArgs a, const uint32_t *__restrict__ pos, int level,
+                                                            int value)
 {
-	uint32_t best = 32, c1 = 0;
-	for (uint32_t k = i + 1; k < m && c1 <= (uint32_t)t; ++k) {
-		if (key[k] != kk) {
-			break;
+	const uint32_t m = a.ctrl->lv[level].m;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+		const uint32_t p = pos[i];
+		if (p & PFLAG) {
+			a.lstar[p & PMASK] = (uint8_t)value;
 		}
-		const uint32_t q = pos[k];
-		if (q - p > D) {
-			break;
-		}
-		++c1;
-		uint32_t l = 1;
-		while (l < best && x[p + l] == x[q + l]) {
-			++l;
-		}
-		best = l;
 	}
-	return c1 >= 2 ? best : 0u;
 }
 
-/* ---- one level: test, prune, re-key, compact -------------------------------------------- */
-__global__ void __launch_bounds__(LV_THREADS) x3_rank_level_kernel(RankArgs a, const uint32_t *__restrict__ keyIn,
-                                                                    const uint32_t *__restrict__ posIn,
-                                                                    uint32_t *__restrict__ keyOut,
-                                                                    uint32_t *__restrict__ posOut, int L, int ticket)
+/* ---- one level: test, prune, re-key, compact ----------------------------------------------
+ * Bit 31 of a position word says "this element passed the previous level": Lstar is written
+ * once per position, at the level where it stops passing (or by the level-1 rare path, the
+ * flush after the last level, or level 32). */
+template <bool FIRST>
+__global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a, const uint32_t *__restrict__ keyIn,
+                                                                       const uint32_t *__restrict__ posIn,
+                                                                       uint32_t *__restrict__ keyOut,
+                                                                       uint32_t *__restrict__ posOut, int L, int ticket)
 {
+	__shared__ __align__(16) uint32_t sk[LV_TILE + 256];
+	__shared__ __align__(16) uint32_t sp[LV_TILE + 256];
 	__shared__ uint32_t hist[4][256];
+	__shared__ uint32_t actbits[LV_TILE / 32];
 	__shared__ unsigned long long ws[LV_THREADS / 32 + 1];
 	__shared__ int wsi[LV_THREADS / 32];
 	__shared__ uint32_t s_tile;
 	__shared__ unsigned long long s_excl;
 
-	const int tid = threadIdx.x, lane = tid & 31;
-	const uint32_t m = a.ctrl->m[L];
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t m = a.ctrl->lv[L].m;
 	const uint32_t ntiles = (m + LV_TILE - 1) / LV_TILE;
 	const uint32_t D = a.D, n_out = a.n_out;
-	const uint32_t la = (uint32_t)a.t + 1u; /* look-ahead of the test */
+	const uint32_t la = (uint32_t)a.t + 1u; /* look-ahead of the test, <= 255 */
 	const bool emit = L < 32;
 	/* digits of the new keys that can be non-zero: ranks are below m */
 	int ndig = 1;
@@ -373,8 +374,8 @@ __global__ void __launch_bounds__(LV_THREADS) x3_rank_level_kernel(RankArgs a, c
 	}
 	if (m == 0) {
 		if (blockIdx.x == 0 && tid == 0) {
-			a.ctrl->m[L + 1] = 0;
-			a.ctrl->groups[L + 1] = 0;
+			a.ctrl->lv[L + 1].m = 0;
+			a.ctrl->lv[L + 1].groups = 0;
 		}
 		return;
 	}
@@ -393,7 +394,9 @@ __global__ void __launch_bounds__(LV_THREADS) x3_rank_level_kernel(RankArgs a, c
 		if (tile >= ntiles) {
 			break;
 		}
-		const uint32_t i0 = tile * LV_TILE + tid * LV_ITEMS;
+		const uint32_t base = tile * LV_TILE;
+		const uint32_t i0 = base + tid * LV_ITEMS;
+		/* my 8 consecutive elements stay in registers; the tile and its look-ahead go to shared memory */
 		uint32_t k[LV_ITEMS], p[LV_ITEMS];
 		if (i0 + LV_ITEMS <= m) {
 			const uint4 k0 = *reinterpret_cast<const uint4 *>(keyIn + i0), k1 = *reinterpret_cast<const uint4 *>(keyIn + i0 + 4);
@@ -404,72 +407,131 @@ __global__ void __launch_bounds__(LV_THREADS) x3_rank_level_kernel(RankArgs a, c
 #pragma unroll
 			for (int e = 0; e < LV_ITEMS; ++e) {
 				const bool v = i0 + e < m;
-				k[e] = v ? keyIn[i0 + e] : 0u;
+				k[e] = v ? keyIn[i0 + e] : KEY_NONE;
 				p[e] = v ? posIn[i0 + e] : 0u;
 			}
 		}
-		/* the test: does the (t+1)-th next element of the array share the gram within D? */
-		uint32_t actm = 0;
-		int mylast = -1;
+		*reinterpret_cast<uint4 *>(sk + tid * LV_ITEMS) = make_uint4(k[0], k[1], k[2], k[3]);
+		*reinterpret_cast<uint4 *>(sk + tid * LV_ITEMS + 4) = make_uint4(k[4], k[5], k[6], k[7]);
+		*reinterpret_cast<uint4 *>(sp + tid * LV_ITEMS) = make_uint4(p[0], p[1], p[2], p[3]);
+		*reinterpret_cast<uint4 *>(sp + tid * LV_ITEMS + 4) = make_uint4(p[4], p[5], p[6], p[7]);
+		if ((uint32_t)tid < la) {
+			const uint32_t i = base + LV_TILE + tid;
+			sk[LV_TILE + tid] = i < m ? keyIn[i] : KEY_NONE;
+			sp[LV_TILE + tid] = i < m ? posIn[i] : 0u;
+		}
+		__syncthreads();
+		/* the test, element idx = 256 e + tid (conflict-free): does the (t+1)-th next element of the
+		 * array share the gram within D? */
 #pragma unroll
 		for (int e = 0; e < LV_ITEMS; ++e) {
-			const uint32_t i = i0 + e;
-			if (i >= m) {
-				break;
+			const uint32_t idx = e * LV_THREADS + tid;
+			const uint32_t kk = sk[idx], pw = sp[idx];
+			const uint32_t pp = pw & PMASK;
+			const bool valid = base + idx < m;
+			const bool out = pp < n_out;
+			bool pass;
+			if (FIRST) {
+				/* level-1 keys carry 4 bytes; the gram is the low byte (KEY_NONE is no sentinel here) */
+				pass = valid && out && base + idx + la < m && ((sk[idx + la] ^ kk) & 255u) == 0u && sp[idx + la] - pp <= D;
+				if (valid && out && !pass) {
+					/* the byte has c1 <= t followers within D: tc* = c1 - 1, so Lstar = #{L : count_L >= c1}
+					 * = the smallest LCP32 over those followers, 0 when c1 < 2 (backend.c:76-78 collapsed).
+					 * The first 4 bytes of every follower sit in its key. */
+					const uint32_t room = m - 1u - (base + idx);
+					const uint32_t lim = room < (uint32_t)a.t ? room : (uint32_t)a.t;
+					uint32_t best = 32, c1 = 0;
+					for (uint32_t j = 1; j <= lim; ++j) {
+						const uint32_t kf = sk[idx + j];
+						if (((kf ^ kk) & 255u) != 0u) {
+							break;
+						}
+						const uint32_t q = sp[idx + j];
+						if (q - pp > D) {
+							break;
+						}
+						++c1;
+						const uint32_t df = kf ^ kk;
+						uint32_t l = df != 0u ? (uint32_t)(__ffs((int)df) - 1) >> 3 : 4u;
+						if (l == 4u) {
+							while (l < best && a.x[pp + l] == a.x[q + l]) {
+								++l;
+							}
+						}
+						best = min(best, l);
+					}
+					a.lstar[pp] = (uint8_t)(c1 >= 2 ? best : 0u);
+				}
+			} else {
+				pass = valid && out && sk[idx + la] == kk && (sp[idx + la] & PMASK) - pp <= D;
 			}
-			const uint32_t j = i + la;
-			bool pass = false;
-			if (j < m && __ldg(keyIn + j) == k[e]) {
-				pass = __ldg(posIn + j) - p[e] <= D;
+			if (!FIRST && (pw & PFLAG) && !pass) {
+				a.lstar[pp] = (uint8_t)(L - 1); /* passed level L-1, stops here */
 			}
-			const bool out = p[e] < n_out;
-			if (L == 1 && !pass && out) {
-				a.lstar[p[e]] = (uint8_t)rank_rare(a.x, keyIn, posIn, i, m, k[e], p[e], D, a.t);
+			if (L == 32 && pass) {
+				a.lstar[pp] = 32;
 			}
-			if (pass && out) {
-				a.lstar[p[e]] = (uint8_t)L;
-				actm |= 1u << e;
-				mylast = (int)i;
+			const uint32_t am = __ballot_sync(FULL_MASK, pass);
+			if (lane == 0) {
+				actbits[e * (LV_THREADS / 32) + warp] = am;
 			}
 		}
 		if (!emit) {
 			__syncthreads();
 			continue;
 		}
+		__syncthreads();
+		const uint32_t actm = (actbits[tid >> 2] >> ((tid & 3) * 8)) & 0xffu;
+		const int mylast = actm != 0 ? (int)i0 + (31 - __clz((int)actm)) : -1;
 		/* last passed element in front of mine; in front of the tile: pretend its neighbour passed
 		 * (a superset of the exact rule, at most t+1 extra elements per tile) */
-		const int prevlast = block_excl_max(mylast, (int)(tile * LV_TILE) - 1, wsi);
+		const int prevlast = block_excl_max(mylast, (int)base - 1, wsi);
 		bool have = prevlast >= 0;
 		uint32_t rk = 0, rp = 0;
 		if (have) {
-			rk = __ldg(keyIn + prevlast);
-			rp = __ldg(posIn + prevlast);
+			if (prevlast >= (int)base) {
+				rk = sk[prevlast - (int)base];
+				rp = sp[prevlast - (int)base] & PMASK;
+			} else {
+				rk = __ldg(keyIn + prevlast);
+				rp = __ldg(posIn + prevlast) & PMASK;
+			}
+			if (FIRST) {
+				rk &= 255u;
+			}
 		}
 		uint32_t partm = 0, headm = 0;
-		uint32_t kprev = i0 > 0 && i0 <= m ? __ldg(keyIn + i0 - 1) : ~k[0];
+		uint32_t kprev = tid > 0 ? sk[tid * LV_ITEMS - 1] : (base > 0 ? __ldg(keyIn + base - 1) : ~k[0]);
+		if (FIRST) {
+			kprev &= 255u; /* element 0 is a head by its index */
+		}
 #pragma unroll
 		for (int e = 0; e < LV_ITEMS; ++e) {
 			if (i0 + e < m) {
+				const uint32_t pp = p[e] & PMASK;
 				if ((actm >> e) & 1u) {
 					have = true;
-					rk = k[e];
-					rp = p[e];
+					rp = pp;
 				}
-				if (have && rk == k[e] && p[e] - rp <= D) {
+				const uint32_t ke = FIRST ? k[e] & 255u : k[e];
+				if ((actm >> e) & 1u) {
+					rk = ke;
+				}
+				if (have && rk == ke && pp - rp <= D) {
 					partm |= 1u << e;
 				}
-				if (k[e] != kprev || i0 + e == 0) {
+				if (ke != kprev || i0 + e == 0) {
 					headm |= 1u << e;
 				}
-				kprev = k[e];
+				kprev = ke;
 			}
 		}
 		/* chained scan of (kept, heads) over the tiles */
-		const unsigned long long mine = (unsigned long long)__popc(partm) | ((unsigned long long)__popc(headm) << 32);
+		const unsigned long long mine = (unsigned long long)__popc(partm) | ((unsigned long long)__popc(headm) << 16);
 		unsigned long long total;
 		const unsigned long long ex = block_excl_sum(mine, ws, &total);
 		if (tid < 32) {
-			const unsigned long long pk = (total & 0xffffffull) | ((total >> 32) << 24);
+			const unsigned long long pk = (total & 0xffffull) | (((total >> 16) & 0xffffull) << 24);
 			const unsigned long long ep = (unsigned long long)L << 50;
 			unsigned long long excl = 0;
 			if (tile == 0) {
@@ -515,22 +577,23 @@ __global__ void __launch_bounds__(LV_THREADS) x3_rank_level_kernel(RankArgs a, c
 				s_excl = excl;
 				if (tile == ntiles - 1) {
 					const unsigned long long tot = excl + pk;
-					a.ctrl->m[L + 1] = (uint32_t)(tot & 0xffffffull);
-					a.ctrl->groups[L + 1] = (uint32_t)((tot >> 24) & 0xffffffull);
+					a.ctrl->lv[L + 1].m = (uint32_t)(tot & 0xffffffull);
+					a.ctrl->lv[L + 1].groups = (uint32_t)((tot >> 24) & 0xffffffull);
 				}
 			}
 		}
 		__syncthreads();
 		const unsigned long long tex = s_excl;
-		uint32_t dst = (uint32_t)(tex & 0xffffffull) + (uint32_t)(ex & 0xffffffffull);
-		uint32_t hcount = (uint32_t)((tex >> 24) & 0xffffffull) + (uint32_t)(ex >> 32);
+		uint32_t dst = (uint32_t)(tex & 0xffffffull) + (uint32_t)(ex & 0xffffull);
+		uint32_t hcount = (uint32_t)((tex >> 24) & 0xffffffull) + (uint32_t)((ex >> 16) & 0xffffull);
 #pragma unroll
 		for (int e = 0; e < LV_ITEMS; ++e) {
 			hcount += (headm >> e) & 1u;
 			if ((partm >> e) & 1u) {
-				const uint32_t nk = ((hcount - 1u) << 8) | (uint32_t)__ldg(a.x + p[e] + L);
+				const uint32_t pp = p[e] & PMASK;
+				const uint32_t nk = ((hcount - 1u) << 8) | (FIRST ? (k[e] >> 8) & 255u : (uint32_t)__ldg(a.x + pp + L));
 				keyOut[dst] = nk;
-				posOut[dst] = p[e];
+				posOut[dst] = pp | (((actm >> e) & 1u) ? PFLAG : 0u);
 				++dst;
 				atomicAdd(&hist[0][nk & 255u], 1u);
 				for (int j = 1; j < ndig; ++j) {
@@ -681,15 +744,20 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 		int cur = 0;
 		uint32_t m = a.M;
 		for (int L = 1; L <= 32; ++L) {
-			x3_rank_level_kernel<<<grid_for((m + LV_TILE - 1) / LV_TILE), LV_THREADS, 0, stream>>>(
-			    a, s.key[cur], s.pos[cur], s.key[cur ^ 1], s.pos[cur ^ 1], L, ticket);
+			const int lgrid = grid_for((m + LV_TILE - 1) / LV_TILE);
+			if (L == 1) {
+				x3_rank_level_kernel<true><<<lgrid, LV_THREADS, 0, stream>>>(a, s.key[cur], s.pos[cur], s.key[cur ^ 1],
+				                                                             s.pos[cur ^ 1], L, ticket);
+			} else {
+				x3_rank_level_kernel<false><<<lgrid, LV_THREADS, 0, stream>>>(a, s.key[cur], s.pos[cur], s.key[cur ^ 1],
+				                                                              s.pos[cur ^ 1], L, ticket);
+			}
 			++ticket;
 			++nl;
 			if (L == 32) {
 				break;
 			}
-			if ((e = cudaMemcpyAsync(s.h_back, &s.ctrl->m[L + 1], 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-			if ((e = cudaMemcpyAsync(s.h_back + 1, &s.ctrl->groups[L + 1], 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+			if ((e = cudaMemcpyAsync(s.h_back, &s.ctrl->lv[L + 1], 8, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
 			if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
 			const uint32_t mn = s.h_back[0], groups = s.h_back[1];
 			const int np = radix_passes(groups);
@@ -698,7 +766,12 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 				        a0 / CH, L, m, mn, groups, np);
 			}
 			if (mn < (uint32_t)prm.t + 2u) {
-				break; /* nobody can pass the next level */
+				/* nobody can pass the next level: whoever passed this one keeps it */
+				if (mn > 0) {
+					x3_rank_flush_kernel<<<1, 256, 0, stream>>>(a, s.pos[cur ^ 1], L + 1, L);
+					++nl;
+				}
+				break;
 			}
 			int src = cur ^ 1;
 			for (int pass = 0; pass < np; ++pass) {
