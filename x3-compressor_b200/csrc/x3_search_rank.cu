@@ -198,17 +198,21 @@ __global__ void __launch_bounds__(256) x3_rank_bytehist_kernel(RankArgs a)
 }
 
 /* ---- one stable 8-bit radix pass -------------------------------------------------------
- * INIT: the elements are the positions 0 .. M-1 themselves, key = x[pos] (level 1). */
+ * INIT: the elements are the positions 0 .. M-1 themselves, key = 4 bytes of x (level 1).
+ * A tile is ranked with warp-level digit matching, put in digit order in shared memory while
+ * the chained per-digit prefix of the tiles in front resolves, then copied out in runs. */
 template <bool INIT>
-__global__ void __launch_bounds__(RS_THREADS) x3_rank_radix_kernel(RankArgs a, const uint32_t *__restrict__ keyIn,
-                                                                    const uint32_t *__restrict__ posIn,
-                                                                    uint32_t *__restrict__ keyOut,
-                                                                    uint32_t *__restrict__ posOut, int level, int pass,
-                                                                    int ticket, uint32_t epoch)
+__global__ void __launch_bounds__(RS_THREADS, 4) x3_rank_radix_kernel(RankArgs a, const uint32_t *__restrict__ keyIn,
+                                                                       const uint32_t *__restrict__ posIn,
+                                                                       uint32_t *__restrict__ keyOut,
+                                                                       uint32_t *__restrict__ posOut, int level, int pass,
+                                                                       int ticket, uint32_t epoch)
 {
 	__shared__ uint32_t gbase[256];
 	__shared__ uint32_t wcnt[RS_WARPS][256];
+	__shared__ uint32_t lbase[256];
 	__shared__ uint32_t tbase[256];
+	__shared__ uint32_t skey[RS_TILE], spos[RS_TILE];
 	__shared__ uint32_t s_tile;
 	__shared__ uint32_t wsum[RS_WARPS + 1];
 
@@ -262,7 +266,7 @@ __global__ void __launch_bounds__(RS_THREADS) x3_rank_radix_kernel(RankArgs a, c
 			const bool valid = i < m;
 			if (INIT) {
 				/* level-1 key: the byte (the sort digit) with its three successors on top, so that the
-				 * level-1 kernel needs no gathers (4 <= W - 33 - ... bytes behind any element are readable) */
+				 * level-1 kernel needs no gathers */
 				const uint32_t *xw = reinterpret_cast<const uint32_t *>(a.x) + (i >> 2);
 				key[k] = valid ? __funnelshift_r(__ldg(xw), __ldg(xw + 1), 8 * (i & 3)) : 0u;
 				pos[k] = i;
@@ -270,6 +274,10 @@ __global__ void __launch_bounds__(RS_THREADS) x3_rank_radix_kernel(RankArgs a, c
 				key[k] = valid ? keyIn[i] : 0u;
 				pos[k] = valid ? posIn[i] : 0u;
 			}
+		}
+#pragma unroll
+		for (int k = 0; k < RS_ITEMS; ++k) {
+			const bool valid = base + 32 * k + lane < m;
 			const uint32_t d = valid ? ((key[k] >> shift) & 255u) : 256u;
 			const uint32_t peers = __match_any_sync(FULL_MASK, d);
 			const int leader = __ffs(peers) - 1;
@@ -283,22 +291,52 @@ __global__ void __launch_bounds__(RS_THREADS) x3_rank_radix_kernel(RankArgs a, c
 			__syncwarp();
 		}
 		__syncthreads();
-		/* digit tid: offsets of the warps inside the tile, tile total, look-back */
+		/* digit tid: offsets of the warps inside the tile, the tile total (published at once for the
+		 * tiles behind), and the digit's first slot in the tile's sorted order */
+		unsigned long long *mine = a.st_radix + (size_t)tile * 256 + tid;
+		const unsigned long long ep = (unsigned long long)epoch << 32;
+		uint32_t run = 0;
 		{
-			uint32_t run = 0;
 #pragma unroll
 			for (int w = 0; w < RS_WARPS; ++w) {
 				const uint32_t c = wcnt[w][tid];
 				wcnt[w][tid] = run;
 				run += c;
 			}
-			unsigned long long *mine = a.st_radix + (size_t)tile * 256 + tid;
-			const unsigned long long ep = (unsigned long long)epoch << 32;
+			st_status(mine, ep | ((tile == 0 ? ST_INC : ST_AGG) << 30) | run);
+			uint32_t inc = run;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t o = __shfl_up_sync(FULL_MASK, inc, d);
+				if (lane >= d) {
+					inc += o;
+				}
+			}
+			if (lane == 31) {
+				wsum[warp] = inc;
+			}
+			__syncthreads();
+			uint32_t before = 0;
+			for (int w = 0; w < warp; ++w) {
+				before += wsum[w];
+			}
+			lbase[tid] = before + inc - run;
+		}
+		__syncthreads();
+		/* the tile in digit order */
+#pragma unroll
+		for (int k = 0; k < RS_ITEMS; ++k) {
+			if (off[k] != 0xffffffffu) {
+				const uint32_t d = off[k] >> 16;
+				const uint32_t idx = lbase[d] + wcnt[warp][d] + (off[k] & 0xffffu);
+				skey[idx] = key[k];
+				spos[idx] = pos[k];
+			}
+		}
+		/* chained prefix of digit tid over the tiles in front */
+		{
 			uint32_t excl = 0;
-			if (tile == 0) {
-				st_status(mine, ep | (ST_INC << 30) | run);
-			} else {
-				st_status(mine, ep | (ST_AGG << 30) | run);
+			if (tile != 0) {
 				const unsigned long long *look = mine - 256;
 				for (;;) {
 					const unsigned long long s = ld_status(look);
@@ -313,17 +351,15 @@ __global__ void __launch_bounds__(RS_THREADS) x3_rank_radix_kernel(RankArgs a, c
 				}
 				st_status(mine, ep | (ST_INC << 30) | (excl + run));
 			}
-			tbase[tid] = gbase[tid] + excl;
+			tbase[tid] = gbase[tid] + excl - lbase[tid];
 		}
 		__syncthreads();
-#pragma unroll
-		for (int k = 0; k < RS_ITEMS; ++k) {
-			if (off[k] != 0xffffffffu) {
-				const uint32_t d = off[k] >> 16;
-				const uint32_t dst = tbase[d] + wcnt[warp][d] + (off[k] & 0xffffu);
-				keyOut[dst] = key[k];
-				posOut[dst] = pos[k];
-			}
+		const uint32_t cnt = m - tile * RS_TILE < RS_TILE ? m - tile * RS_TILE : RS_TILE;
+		for (uint32_t j = tid; j < cnt; j += RS_THREADS) {
+			const uint32_t kk = skey[j];
+			const uint32_t dst = tbase[(kk >> shift) & 255u] + j;
+			keyOut[dst] = kk;
+			posOut[dst] = spos[j];
 		}
 		__syncthreads();
 	}
@@ -526,22 +562,44 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 				kprev = ke;
 			}
 		}
+		/* the byte that extends each kept gram (one gather per element; level 1 has it in the key),
+		 * fetched before the scans so that its latency overlaps them */
+		uint32_t nb[2] = {0u, 0u};
+#pragma unroll
+		for (int e = 0; e < LV_ITEMS; ++e) {
+			if ((partm >> e) & 1u) {
+				const uint32_t by = FIRST ? (k[e] >> 8) & 255u : (uint32_t)__ldg(a.x + (p[e] & PMASK) + L);
+				nb[e >> 2] |= by << (8 * (e & 3));
+			}
+		}
 		/* chained scan of (kept, heads) over the tiles */
 		const unsigned long long mine = (unsigned long long)__popc(partm) | ((unsigned long long)__popc(headm) << 16);
 		unsigned long long total;
 		const unsigned long long ex = block_excl_sum(mine, ws, &total);
+		const unsigned long long pk = (total & 0xffffull) | (((total >> 16) & 0xffffull) << 24);
+		const unsigned long long ep = (unsigned long long)L << 50;
+		if (tid == 0) {
+			/* the tile's own counts are out at once for the tiles behind */
+			st_status(a.st_level + tile, ep | ((tile == 0 ? ST_INC : ST_AGG) << 48) | pk);
+		}
+		/* the kept elements, compacted in tile order into the (now free) staging arrays; keys carry
+		 * the tile-local group rank until the prefix over the tiles in front is known */
+		{
+			uint32_t lidx = (uint32_t)(ex & 0xffffull);
+			uint32_t hloc = (uint32_t)((ex >> 16) & 0xffffull);
+#pragma unroll
+			for (int e = 0; e < LV_ITEMS; ++e) {
+				hloc += (headm >> e) & 1u;
+				if ((partm >> e) & 1u) {
+					sk[lidx] = ((hloc - 1u) << 8) | ((nb[e >> 2] >> (8 * (e & 3))) & 255u);
+					sp[lidx] = (p[e] & PMASK) | (((actm >> e) & 1u) ? PFLAG : 0u);
+					++lidx;
+				}
+			}
+		}
 		if (tid < 32) {
-			const unsigned long long pk = (total & 0xffffull) | (((total >> 16) & 0xffffull) << 24);
-			const unsigned long long ep = (unsigned long long)L << 50;
 			unsigned long long excl = 0;
-			if (tile == 0) {
-				if (lane == 0) {
-					st_status(a.st_level + tile, ep | (ST_INC << 48) | pk);
-				}
-			} else {
-				if (lane == 0) {
-					st_status(a.st_level + tile, ep | (ST_AGG << 48) | pk);
-				}
+			if (tile != 0) {
 				int look = (int)tile - 1;
 				for (;;) {
 					const int idx = look - lane;
@@ -583,21 +641,27 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 			}
 		}
 		__syncthreads();
-		const unsigned long long tex = s_excl;
-		uint32_t dst = (uint32_t)(tex & 0xffffffull) + (uint32_t)(ex & 0xffffull);
-		uint32_t hcount = (uint32_t)((tex >> 24) & 0xffffffull) + (uint32_t)((ex >> 16) & 0xffffull);
-#pragma unroll
-		for (int e = 0; e < LV_ITEMS; ++e) {
-			hcount += (headm >> e) & 1u;
-			if ((partm >> e) & 1u) {
-				const uint32_t pp = p[e] & PMASK;
-				const uint32_t nk = ((hcount - 1u) << 8) | (FIRST ? (k[e] >> 8) & 255u : (uint32_t)__ldg(a.x + pp + L));
-				keyOut[dst] = nk;
-				posOut[dst] = pp | (((actm >> e) & 1u) ? PFLAG : 0u);
-				++dst;
-				atomicAdd(&hist[0][nk & 255u], 1u);
-				for (int j = 1; j < ndig; ++j) {
-					atomicAdd(&hist[j][(nk >> (8 * j)) & 255u], 1u);
+		{
+			const unsigned long long tex = s_excl;
+			const uint32_t dst0 = (uint32_t)(tex & 0xffffffull);
+			const uint32_t hadd = (uint32_t)((tex >> 24) & 0xffffffull) << 8;
+			const uint32_t cnt = (uint32_t)(total & 0xffffull);
+			for (uint32_t j0 = 0; j0 < cnt; j0 += LV_THREADS) {
+				const uint32_t j = j0 + tid;
+				const bool on = j < cnt;
+				uint32_t nk = 0;
+				if (on) {
+					nk = sk[j] + hadd;
+					keyOut[dst0 + j] = nk;
+					posOut[dst0 + j] = sp[j];
+				}
+				/* digit histograms of the new keys, one shared-memory add per distinct digit of the warp */
+				for (int dgt = 0; dgt < ndig; ++dgt) {
+					const uint32_t d = on ? (nk >> (8 * dgt)) & 255u : 256u;
+					const uint32_t peers = __match_any_sync(FULL_MASK, d);
+					if (on && lane == __ffs(peers) - 1) {
+						atomicAdd(&hist[dgt][d], (uint32_t)__popc(peers));
+					}
 				}
 			}
 		}
