@@ -9,12 +9,14 @@ BASELINE.json configs[1], the 10 192 446-byte dickens-shaped synthetic text with
 default flags (-t 15 -w 8).  One position = one input byte = one unit.
 
   value     positions searched per second (MB/s, 1e6 B), input already resident in HBM,
-            CUDA events around the kernel launches only, max over ranks
+            CUDA events around the search (all its kernel launches), max over ranks
   e2e       the same through the C ABI a host binds (x3s_search_host: pinned host
-            buffers in, Lstar out; H2D + kernel + D2H inside the timed region)
-  roofline  dominant kernel against the measured HBM peak (algorithmic bytes:
-            2 B/position + the window halo) -- the path is integer-issue bound, so
-            `pair_tests_per_s` and `alu_lane_ops_frac` are reported beside it
+            buffers in, Lstar out; H2D + kernels + D2H inside the timed region)
+  roofline  the dominant kernel (x3_rank_radix_kernel, one stable 8-bit radix pass of the
+            rank search) against the measured HBM peak: 16 algorithmic bytes per element
+            (8 read + 8 written), elements and device time taken live from the library's
+            per-launch CUDA events (X3_RANK_PROFILE); the whole search against its own
+            algorithmic bytes (2 B/position + halo) is in `search`
   cpu_baseline / --impl reference
             the UNMODIFIED reference find_best_match (oracle/_ref/libx3ref.so, compiled
             from /root/reference by oracle/Makefile) timed on the host cores over a
@@ -289,6 +291,13 @@ def run_b200(args):
     barrier()
     dev_ms = sum(e0.elapsed_time(e1) for (e0, e1) in ev)
     lstar_dev = d_l.cpu().numpy()
+    # one extra search with an event around every launch: per-kernel-family device time
+    os.environ["X3_RANK_PROFILE"] = "1"
+    step_device()
+    torch.cuda.synchronize()
+    del os.environ["X3_RANK_PROFILE"]
+    prof_rank = pkg.rank_profile(local)
+    prof_total_ms = sum(v[0] for v in prof_rank.values())
 
     # ---- (2) end to end through the C ABI with host buffers ----------------------------
     L = pkg.lib()
@@ -343,20 +352,29 @@ def run_b200(args):
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
-    algo_bytes = 2 * n + (W_BYTES - 2)      # 1 B read + 1 B written per position + halo
-    achieved = algo_bytes / (ms_per_step * 1e-3) / 1e9
-    pair_tests = n * D / (ms_per_step * 1e-3)
-    # ALU-pipe bound of the interior loop: 17.4 ALU-pipe warp instructions per
-    # 1024 pair tests, one per 2 cycles per SM sub-partition, at the SM clock seen under load
-    sm_mhz = clocks.get("sm_mhz") or 1965.0
-    alu_bound = 148 * 4 * 1024 / (17.4 * 2.0) * sm_mhz * 1e6
+    # dominant kernel: the radix pass.  One element = one 4-byte key + one 4-byte position word,
+    # read once and written once per pass: 16 algorithmic bytes.
+    radix_ms, radix_el, radix_n = prof_rank["radix"]
+    level_ms, level_el, level_n = prof_rank["level"]
+    rbytes = 16.0 * radix_el / max(radix_n, 1)
+    achieved = 16.0 * radix_el / (radix_ms * 1e-3) / 1e9 if radix_ms > 0 else 0.0
+    algo_bytes = 2 * n + (W_BYTES - 2)      # the whole search: 1 B read + 1 B written per position + halo
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel": "x3_lcp_stream_kernel<4,6>",
-                "algorithmic_bytes_per_launch": algo_bytes,
-                "note": "2 B move per 8159 pair tests: the path is bound by the integer ALU pipe, not HBM "
-                        "(SURVEY.md 8(d)); alu_bound_frac = pair_tests_per_s / ALU-pipe bound of the loop",
-                "pair_tests_per_s": pair_tests, "alu_bound_pair_tests_per_s": alu_bound,
-                "alu_bound_frac": pair_tests / alu_bound}
+                "traffic": None, "peak_source": peak_src, "kernel": "x3_rank_radix_kernel",
+                "algorithmic_bytes_per_launch": rbytes, "launches_per_search": radix_n,
+                "avg_launch_ms": radix_ms / max(radix_n, 1), "share_of_search": radix_ms / max(prof_total_ms, 1e-9),
+                "measured": "CUDA events around every launch of one extra search (X3_RANK_PROFILE=1), "
+                            "elements from the level sizes the device recorded",
+                "level_kernel": {"kernel": "x3_rank_level_kernel", "launches_per_search": level_n,
+                                 "ms_per_search": level_ms, "elements": level_el,
+                                 "algorithmic_bytes_per_element": "8 read + 1 gathered + up to 8 written + 1 Lstar",
+                                 "achieved_GBps_at_18B": 18.0 * level_el / (level_ms * 1e-3) / 1e9 if level_ms > 0 else None},
+                "search": {"algorithmic_bytes": algo_bytes, "achieved_GBps": algo_bytes / (ms_per_step * 1e-3) / 1e9,
+                           "frac": algo_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+                           "element_visits_per_position": level_el / n,
+                           "equivalent_pair_tests_per_s": n * D / (ms_per_step * 1e-3),
+                           "note": "the rank search visits sum_L m_L elements instead of testing n*(W-33) pairs; "
+                                   "its internal traffic is ~16 B per element per radix pass"}}
     prof = ROOT / "profiles" / "traffic.json"
     if prof.exists():
         try:
@@ -396,7 +414,8 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(len(x_host)) * world,
                 "d2h_bytes_per_step": int(n) * world, "ms_per_step": e2e_s / args.steps * 1e3,
                 "api": "x3s_search_host (include/x3_search.h), pinned host buffers"},
-        # per search: probe kernel + the two stream-kernel instantiations (one of them exits at once)
+        # kernels of this library launched inside the two timed regions (the device leg issues the
+        # same launches per search as the end-to-end leg, whose count the library reports)
         "gpu_launches": e2e_launches + args.steps * (e2e_launches // max(1, args.steps)),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,

@@ -36,10 +36,11 @@ extern "C" {
 #define X3S_MAX_T        254  /* u8 cells saturate at 255; lossless while t <= 254 */
 
 /* kernel variants */
-#define X3S_KERNEL_DEFAULT   0 /* the production kernel: "stream" (fast path when t <= 15 and no H) */
+#define X3S_KERNEL_DEFAULT   0 /* production choice: the rank search for Lstar alone, the stream kernel when the
+                                * 32-bin table H is requested (or W - 33 > 2^23) */
 #define X3S_KERNEL_NAIVE     1 /* one thread per position, byte loop; cross-check only */
 #define X3S_KERNEL_BITSLICED 2 /* first bit-sliced version (thread-private u8 histograms); kept for comparison */
-#define X3S_KERNEL_STREAM    3 /* same as DEFAULT */
+#define X3S_KERNEL_STREAM    3 /* brute-force pair-test kernel (bit-sliced, ALU bound); fast path when t <= 15 and no H */
 #define X3S_KERNEL_STREAM_FULL 4 /* stream kernel, u8 counters forced (what H != NULL or t > 15 selects) */
 #define X3S_KERNEL_RANK      5 /* occurrence-rank search: sorts positions by L-gram level by level; Lstar only
                                 * (d_H must be NULL), cost independent of W and t */
@@ -74,8 +75,10 @@ size_t x3s_required_bytes(size_t n_positions, size_t W);
  *   d_x      device pointer, 16-byte aligned, x3s_required_bytes() readable
  *   d_lstar  device pointer, n_positions bytes (may not be NULL)
  *   d_H      device pointer, n_positions*32 bytes, or NULL (production mode)
- *   stream   cudaStream_t as void* (NULL = default stream); the call is
- *            asynchronous with respect to the host
+ *   stream   cudaStream_t as void* (NULL = default stream).  The work is queued on it and the
+ *            results are ordered behind it; the brute-force kernels return at once, the rank
+ *            search returns when its last level has been queued (it reads level sizes back
+ *            while queueing, so the call lasts about as long as the search)
  */
 int x3s_search_device(int device, const void *d_x, size_t n_positions, size_t W, int t,
                       void *d_lstar, void *d_H, void *stream, int variant);
@@ -100,6 +103,16 @@ int x3s_set_devices(const int *ids, int count);
 /* Pinned host memory helpers (so FFI callers can avoid pageable copies). */
 void *x3s_host_alloc(size_t bytes);
 void  x3s_host_free(void *p);
+
+/*
+ * Measurement hook of the rank search.  With the environment variable X3_RANK_PROFILE=1 the
+ * library brackets every launch of a rank search with CUDA events (and synchronises at the
+ * end of the search); this call returns, for the last such search on `device`, the device
+ * time, the number of 8-byte elements the launches were sized for and the launch count of
+ * one kernel family: kind 0 = radix passes (x3_rank_radix_kernel), 1 = level kernels
+ * (x3_rank_level_kernel), 2 = set-up.  Returns X3S_ERR_ARG for a bad device/kind.
+ */
+int x3s_rank_profile(int device, int kind, double *ms, double *elements, int *launches);
 
 /* Frees every cached device/staging buffer. */
 void x3s_release(void);

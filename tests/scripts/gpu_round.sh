@@ -27,9 +27,9 @@ cat $OUT/bench_n1.json
 tail -3 $OUT/bench_n1.err
 
 echo "== per-config kernel timing"
-for cfg in C2 C4; do
-	timeout 200 python tests/gpu_quick.py 8000000 8192 0 nocheck $cfg 2>&1 | tail -1
-done > $OUT/quick.log 2>&1
+for v in 0 3; do for cfg in C2 C4; do
+	timeout 200 python tests/gpu_quick.py 8000000 8192 $v nocheck $cfg 2>&1 | tail -1
+done; done > $OUT/quick.log 2>&1
 cat $OUT/quick.log
 
 echo "== ncu launch list (same command as the bench, fewer steps)"
@@ -37,8 +37,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 	--log-file $OUT/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/launches_bench.log 2>&1
 echo "launch list exit $?"
 
-echo "== ncu --set full, production kernel on the C2 workload"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:x3_lcp_stream_kernel -c 2 \
-	-f -o $OUT/stream_full python tests/gpu_quick.py 10192446 8192 0 nocheck C2 > $OUT/ncu_full.log 2>&1
+echo "== ncu --set full, production kernels (rank search) on the C2 workload: first 10 launches"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:x3_rank -c 10 \
+	-f -o $OUT/rank_full python tests/gpu_quick.py 10192446 8192 0 nocheck C2 > $OUT/ncu_full.log 2>&1
 echo "ncu full exit $?"
 ls -la $OUT

@@ -70,6 +70,8 @@ def lib() -> C.CDLL:
     L.x3s_host_alloc.restype = C.c_void_p
     L.x3s_host_alloc.argtypes = [C.c_size_t]
     L.x3s_host_free.argtypes = [C.c_void_p]
+    L.x3s_rank_profile.restype = C.c_int
+    L.x3s_rank_profile.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.x3s_release.restype = None
     L.x3s_set_devices.restype = C.c_int
     L.x3s_set_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
@@ -96,6 +98,17 @@ def lib() -> C.CDLL:
 
 def device_count() -> int:
     return int(lib().x3s_device_count())
+
+
+def rank_profile(device: int = 0):
+    """Per-kernel-family device time of the last rank search run with X3_RANK_PROFILE=1:
+    {family: (ms, elements, launches)}."""
+    out = {}
+    for kind, name in enumerate(("radix", "level", "setup")):
+        ms, el, nl = C.c_double(), C.c_double(), C.c_int()
+        _check(lib().x3s_rank_profile(device, kind, C.byref(ms), C.byref(el), C.byref(nl)))
+        out[name] = (ms.value, el.value, nl.value)
+    return out
 
 
 def set_devices(ids):

@@ -16,6 +16,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -76,10 +78,19 @@ int ensure_kernel_init(int device)
 		CU_TRY(x3k_init_device());
 		Scratch &sc = g_scratch[device];
 		CU_TRY(cudaMalloc((void **)&sc.counter, 256));
-		CU_TRY(cudaMalloc((void **)&sc.deep, (size_t)x3k_stream_max_grid() * X3K_DEEP_BYTES_PER_CTA));
-		CU_TRY(cudaMemset(sc.deep, 0, (size_t)x3k_stream_max_grid() * X3K_DEEP_BYTES_PER_CTA));
 		CU_TRY(cudaEventCreateWithFlags(&sc.last, cudaEventDisableTiming));
 		g_kernel_inited[device] = true;
+	}
+	return X3S_OK;
+}
+
+/* the brute-force stream kernel's deep histogram rows: only when that kernel is going to run */
+int ensure_stream_scratch(int device)
+{
+	Scratch &sc = g_scratch[device];
+	if (sc.deep == nullptr) {
+		CU_TRY(cudaMalloc((void **)&sc.deep, (size_t)x3k_stream_max_grid() * X3K_DEEP_BYTES_PER_CTA));
+		CU_TRY(cudaMemset(sc.deep, 0, (size_t)x3k_stream_max_grid() * X3K_DEEP_BYTES_PER_CTA));
 	}
 	return X3S_OK;
 }
@@ -88,6 +99,14 @@ int ensure_kernel_init(int device)
 int launch_on(int device, int variant, X3SearchParams &prm, cudaStream_t stream, int *launches)
 {
 	Scratch &sc = g_scratch[device];
+	const bool rank = variant == X3S_KERNEL_RANK ||
+	                  (variant == X3S_KERNEL_DEFAULT && prm.H == nullptr && prm.D <= x3k_rank_max_distances());
+	if (!rank && variant != X3S_KERNEL_NAIVE && variant != X3S_KERNEL_BITSLICED) {
+		const int rc = ensure_stream_scratch(device);
+		if (rc != X3S_OK) {
+			return rc;
+		}
+	}
 	prm.tile_counter = sc.counter;
 	prm.deep = sc.deep;
 	prm.ntiles = 0;
@@ -235,21 +254,22 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 		a[g] = g == G ? n : cut;
 	}
 
-	int launches = 0;
 	const size_t total = n + W; /* bytes the caller guarantees behind x */
-	for (int g = 0; g < G; ++g) {
+	std::vector<int> shard_launches(G, 0);
+	std::vector<int> shard_rc(G, X3S_OK);
+	std::vector<std::string> shard_err(G);
+	/* one shard: upload the slice with its trailing halo, search, bring Lstar back */
+	auto shard = [&](int g) -> int {
 		const int dev = g_ids.empty() ? g : g_ids[g];
 		DevState &ds = g_dev[dev];
 		const size_t np = a[g + 1] - a[g];
 		if (np == 0) {
-			continue;
+			return X3S_OK;
 		}
 		CU_TRY(cudaSetDevice(dev));
-		lap("cudaSetDevice");
-		rc = ensure_kernel_init(dev);
-		lap("kernel init + scratch");
-		if (rc != X3S_OK) {
-			return rc;
+		int rc2 = ensure_kernel_init(dev);
+		if (rc2 != X3S_OK) {
+			return rc2;
 		}
 		if (!ds.inited) {
 			CU_TRY(cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking));
@@ -259,26 +279,20 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 			ds.inited = true;
 		}
 		const size_t need = x3k_required_bytes(np, W);
-		rc = grow(&ds.d_x, &ds.cap_x, need);
-		if (rc != X3S_OK) {
-			return rc;
+		if ((rc2 = grow(&ds.d_x, &ds.cap_x, need)) != X3S_OK) {
+			return rc2;
 		}
-		rc = grow(&ds.d_l, &ds.cap_l, np);
-		if (rc != X3S_OK) {
-			return rc;
+		if ((rc2 = grow(&ds.d_l, &ds.cap_l, np)) != X3S_OK) {
+			return rc2;
 		}
-		if (H != nullptr) {
-			rc = grow(&ds.d_h, &ds.cap_h, np * 32);
-			if (rc != X3S_OK) {
-				return rc;
-			}
+		if (H != nullptr && (rc2 = grow(&ds.d_h, &ds.cap_h, np * 32)) != X3S_OK) {
+			return rc2;
 		}
 		/* slice + trailing halo: position p reads x[p .. p+W-2] (backend.c:66-74) */
 		size_t have = np + W;
 		if (a[g] + have > total) {
 			have = total - a[g];
 		}
-		lap("buffers");
 		CU_TRY(cudaEventRecord(ds.ev[0], ds.stream));
 		CU_TRY(cudaMemcpyAsync(ds.d_x, (const uint8_t *)x + a[g], have, cudaMemcpyHostToDevice, ds.stream));
 		if (need > have) {
@@ -292,9 +306,8 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 		prm.t = t;
 		prm.lstar = ds.d_l;
 		prm.H = H != nullptr ? ds.d_h : nullptr;
-		rc = launch_on(dev, variant, prm, ds.stream, &launches);
-		if (rc != X3S_OK) {
-			return rc;
+		if ((rc2 = launch_on(dev, variant, prm, ds.stream, &shard_launches[g])) != X3S_OK) {
+			return rc2;
 		}
 		CU_TRY(cudaEventRecord(ds.ev[2], ds.stream));
 		CU_TRY(cudaMemcpyAsync((uint8_t *)lstar + a[g], ds.d_l, np, cudaMemcpyDeviceToHost, ds.stream));
@@ -303,6 +316,39 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 			                       ds.stream));
 		}
 		CU_TRY(cudaEventRecord(ds.ev[3], ds.stream));
+		return X3S_OK;
+	};
+	if (G == 1) {
+		rc = shard(0);
+		lap("shard queued");
+		if (rc != X3S_OK) {
+			return rc;
+		}
+	} else {
+		/* one submitting thread per GPU: the rank search waits on its own read-backs while it
+		 * queues levels, which must not hold up the other GPUs */
+		std::vector<std::thread> thr;
+		for (int g = 0; g < G; ++g) {
+			thr.emplace_back([&, g]() {
+				shard_rc[g] = shard(g);
+				if (shard_rc[g] != X3S_OK) {
+					shard_err[g] = g_err; /* thread-local message of the worker */
+				}
+			});
+		}
+		for (auto &th : thr) {
+			th.join();
+		}
+		lap("shards queued");
+		for (int g = 0; g < G; ++g) {
+			if (shard_rc[g] != X3S_OK) {
+				return fail(shard_rc[g], "GPU shard %d: %s", g, shard_err[g].c_str());
+			}
+		}
+	}
+	int launches = 0;
+	for (int g = 0; g < G; ++g) {
+		launches += shard_launches[g];
 	}
 
 	x3s_timing tm;
@@ -347,6 +393,15 @@ int x3s_set_devices(const int *ids, int count)
 		}
 	}
 	g_ids.assign(ids, ids + count);
+	return X3S_OK;
+}
+
+int x3s_rank_profile(int device, int kind, double *ms, double *elements, int *launches)
+{
+	if (ms == nullptr || elements == nullptr || launches == nullptr ||
+	    x3k_rank_profile(device, kind, ms, elements, launches) != 0) {
+		return fail(X3S_ERR_ARG, "x3s_rank_profile: bad device, kind or null pointer");
+	}
 	return X3S_OK;
 }
 

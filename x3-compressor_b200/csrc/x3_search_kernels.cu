@@ -478,7 +478,10 @@ cudaError_t x3k_launch(int variant, const X3SearchParams &prm, cudaStream_t stre
 	if (launches != nullptr && (variant == 1 || variant == 2)) {
 		*launches += 1;
 	}
-	if (variant == 5) {
+	/* production choice: the rank search whenever only Lstar is wanted (its cost does not grow with
+	 * the window or with t); the brute-force stream kernel for the 32-bin table and for windows
+	 * beyond the rank search's chunking */
+	if (variant == 5 || (variant == 0 && prm.H == nullptr && prm.D <= x3k_rank_max_distances())) {
 		return x3k_launch_rank(prm, stream, launches);
 	}
 	if (variant == 1) {

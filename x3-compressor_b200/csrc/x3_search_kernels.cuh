@@ -43,6 +43,7 @@ cudaError_t x3k_launch(int variant, const X3SearchParams &prm, cudaStream_t stre
 cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int *launches);
 uint32_t x3k_rank_max_distances(void);
 void x3k_rank_release(int device);
+int x3k_rank_profile(int device, int kind, double *ms, double *elements, int *launches);
 
 /* One-time per-device setup (opt-in shared memory size). */
 cudaError_t x3k_init_device(void);

@@ -40,6 +40,7 @@
  */
 #include "x3_search_device.cuh"
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 
@@ -63,6 +64,8 @@ struct RankCtrl {
 	struct {
 		uint32_t m;             /* length of the level-L array (lv[1].m = M) */
 		uint32_t groups;        /* rank range of the level-L keys (lv[1].groups = 1) */
+		uint32_t src0;          /* buffer the level-(L-1) kernel wrote the unsorted array to */
+		uint32_t buf;           /* buffer that holds it sorted: src0 ^ (radix passes & 1) */
 	} lv[36];
 	uint32_t tickets[256];      /* one tile dispenser per launch */
 	uint32_t hist[34][4][256];  /* digit histograms of the level-L keys */
@@ -76,6 +79,7 @@ struct RankArgs {
 	uint32_t D;
 	int t;
 	RankCtrl *ctrl;
+	uint32_t *key0, *key1, *pos0, *pos1; /* the two element buffers the levels and radix passes ping-pong between */
 	unsigned long long *st_level; /* [tiles of the level kernel] */
 	unsigned long long *st_radix; /* [tiles of the radix kernel][256] */
 };
@@ -162,6 +166,16 @@ __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long l
 	asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+/* 8-bit radix passes that sort keys (rank << 8 | byte) with rank < groups */
+__host__ __device__ __forceinline__ int radix_passes(uint32_t groups)
+{
+	int bits = 8;
+	while (groups > 1 && ((groups - 1) >> (bits - 8)) != 0) {
+		++bits;
+	}
+	return (bits + 7) / 8;
+}
+
 /* ---- level 1 set-up: byte histogram of the M elements ---------------------------------- */
 
 __global__ void __launch_bounds__(256) x3_rank_bytehist_kernel(RankArgs a)
@@ -189,6 +203,8 @@ __global__ void __launch_bounds__(256) x3_rank_bytehist_kernel(RankArgs a)
 		if (threadIdx.x == 0) {
 			a.ctrl->lv[1].m = a.M;
 			a.ctrl->lv[1].groups = 1;
+			a.ctrl->lv[1].src0 = 1; /* the one level-1 pass lands in buffer 0 */
+			a.ctrl->lv[1].buf = 0;
 		}
 	}
 	__syncthreads();
@@ -202,11 +218,8 @@ __global__ void __launch_bounds__(256) x3_rank_bytehist_kernel(RankArgs a)
  * A tile is ranked with warp-level digit matching, put in digit order in shared memory while
  * the chained per-digit prefix of the tiles in front resolves, then copied out in runs. */
 template <bool INIT>
-__global__ void __launch_bounds__(RS_THREADS, 4) x3_rank_radix_kernel(RankArgs a, const uint32_t *__restrict__ keyIn,
-                                                                       const uint32_t *__restrict__ posIn,
-                                                                       uint32_t *__restrict__ keyOut,
-                                                                       uint32_t *__restrict__ posOut, int level, int pass,
-                                                                       int ticket, uint32_t epoch)
+__global__ void __launch_bounds__(RS_THREADS, 4) x3_rank_radix_kernel(RankArgs a, int level, int pass, int ticket,
+                                                                       uint32_t epoch)
 {
 	__shared__ uint32_t gbase[256];
 	__shared__ uint32_t wcnt[RS_WARPS][256];
@@ -218,6 +231,14 @@ __global__ void __launch_bounds__(RS_THREADS, 4) x3_rank_radix_kernel(RankArgs a
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t m = a.ctrl->lv[level].m;
+	if (!INIT && (m < (uint32_t)a.t + 2u || pass >= radix_passes(a.ctrl->lv[level].groups))) {
+		return; /* nobody can pass this level any more / the keys have no such digit */
+	}
+	const uint32_t src = INIT ? 1u : a.ctrl->lv[level].src0 ^ (uint32_t)(pass & 1);
+	const uint32_t *__restrict__ keyIn = src ? a.key1 : a.key0;
+	const uint32_t *__restrict__ posIn = src ? a.pos1 : a.pos0;
+	uint32_t *__restrict__ keyOut = src ? a.key0 : a.key1;
+	uint32_t *__restrict__ posOut = src ? a.pos0 : a.pos1;
 	const uint32_t ntiles = (m + RS_TILE - 1) / RS_TILE;
 	const int shift = 8 * pass;
 	const uint32_t lt = (1u << lane) - 1u;
@@ -365,28 +386,12 @@ __global__ void __launch_bounds__(RS_THREADS, 4) x3_rank_radix_kernel(RankArgs a
 	}
 }
 
-/* After the last level that ran: every element that passed it keeps that level. */
-__global__ void __launch_bounds__(256) x3_rank_flush_kernel(RankArgs a, const uint32_t *__restrict__ pos, int level,
-                                                            int value)
-{
-	const uint32_t m = a.ctrl->lv[level].m;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-		const uint32_t p = pos[i];
-		if (p & PFLAG) {
-			a.lstar[p & PMASK] = (uint8_t)value;
-		}
-	}
-}
-
 /* ---- one level: test, prune, re-key, compact ----------------------------------------------
  * Bit 31 of a position word says "this element passed the previous level": Lstar is written
  * once per position, at the level where it stops passing (or by the level-1 rare path, the
  * flush after the last level, or level 32). */
 template <bool FIRST>
-__global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a, const uint32_t *__restrict__ keyIn,
-                                                                       const uint32_t *__restrict__ posIn,
-                                                                       uint32_t *__restrict__ keyOut,
-                                                                       uint32_t *__restrict__ posOut, int L, int ticket)
+__global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a, int L, int ticket)
 {
 	__shared__ __align__(16) uint32_t sk[LV_TILE + 256];
 	__shared__ __align__(16) uint32_t sp[LV_TILE + 256];
@@ -403,18 +408,32 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 	const uint32_t D = a.D, n_out = a.n_out;
 	const uint32_t la = (uint32_t)a.t + 1u; /* look-ahead of the test, <= 255 */
 	const bool emit = L < 32;
-	/* digits of the new keys that can be non-zero: ranks are below m */
-	int ndig = 1;
-	while (ndig < 4 && ((m - 1u) >> (8 * (ndig - 1))) != 0u) {
-		++ndig;
-	}
-	if (m == 0) {
-		if (blockIdx.x == 0 && tid == 0) {
-			a.ctrl->lv[L + 1].m = 0;
-			a.ctrl->lv[L + 1].groups = 0;
+	if (!FIRST && m < la + 1u) {
+		/* nobody can pass this level (the radix passes did not run either): whoever passed the
+		 * previous one keeps it, and the search is over */
+		if (blockIdx.x == 0) {
+			const uint32_t *__restrict__ pu = a.ctrl->lv[L].src0 ? a.pos1 : a.pos0;
+			for (uint32_t i = tid; i < m; i += LV_THREADS) {
+				const uint32_t pw = pu[i];
+				if (pw & PFLAG) {
+					a.lstar[pw & PMASK] = (uint8_t)(L - 1);
+				}
+			}
+			if (tid == 0) {
+				a.ctrl->lv[L + 1].m = 0;
+				a.ctrl->lv[L + 1].groups = 0;
+			}
 		}
 		return;
 	}
+	const uint32_t inb = a.ctrl->lv[L].buf;
+	const uint32_t *__restrict__ keyIn = inb ? a.key1 : a.key0;
+	const uint32_t *__restrict__ posIn = inb ? a.pos1 : a.pos0;
+	uint32_t *__restrict__ keyOut = inb ? a.key0 : a.key1;
+	uint32_t *__restrict__ posOut = inb ? a.pos0 : a.pos1;
+	/* digits of the new keys that can be non-zero: ranks are below the number of L-grams */
+	const uint32_t rbound = L == 1 ? (m < 256u ? m : 256u) : (L == 2 ? (m < 65536u ? m : 65536u) : m);
+	const int ndig = radix_passes(rbound);
 #pragma unroll
 	for (int j = 0; j < 4; ++j) {
 		hist[j][tid] = 0;
@@ -635,8 +654,11 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 				s_excl = excl;
 				if (tile == ntiles - 1) {
 					const unsigned long long tot = excl + pk;
+					const uint32_t g = (uint32_t)((tot >> 24) & 0xffffffull);
 					a.ctrl->lv[L + 1].m = (uint32_t)(tot & 0xffffffull);
-					a.ctrl->lv[L + 1].groups = (uint32_t)((tot >> 24) & 0xffffffull);
+					a.ctrl->lv[L + 1].groups = g;
+					a.ctrl->lv[L + 1].src0 = inb ^ 1u;
+					a.ctrl->lv[L + 1].buf = inb ^ 1u ^ (uint32_t)(radix_passes(g) & 1);
 				}
 			}
 		}
@@ -685,8 +707,18 @@ struct RankScratch {
 	RankCtrl *ctrl = nullptr;
 	unsigned long long *st_level = nullptr;
 	unsigned long long *st_radix = nullptr;
-	uint32_t *h_back = nullptr; /* pinned: m and groups of the next level */
+	uint32_t *h_back = nullptr;       /* pinned: lv[L + 1] as read back after level L */
+	cudaEvent_t ev[36] = {nullptr};   /* ev[L]: that read-back has landed */
 	int sms = 0;
+	/* X3_RANK_PROFILE: device time per kernel family of the last search */
+	cudaEvent_t pev[520];
+	int pkind[260];
+	int plevel[260], ppass[260];
+	int npev = 0;
+	bool pev_made = false;
+	double prof_ms[4] = {0, 0, 0, 0};     /* [0] radix passes, [1] level kernels, [2] set-up, [3] unused */
+	double prof_elems[4] = {0, 0, 0, 0};  /* elements those launches processed */
+	int prof_launches[4] = {0, 0, 0, 0};
 };
 RankScratch g_rank[64];
 
@@ -696,7 +728,10 @@ cudaError_t rank_ensure(int dev, uint32_t M)
 	cudaError_t e;
 	if (s.ctrl == nullptr) {
 		if ((e = cudaMalloc((void **)&s.ctrl, sizeof(RankCtrl))) != cudaSuccess) return e;
-		if ((e = cudaMallocHost((void **)&s.h_back, 64)) != cudaSuccess) return e;
+		if ((e = cudaMallocHost((void **)&s.h_back, 36 * 16)) != cudaSuccess) return e;
+		for (int i = 0; i < 36; ++i) {
+			if ((e = cudaEventCreateWithFlags(&s.ev[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+		}
 		if ((e = cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
 	}
 	if (M <= s.cap) {
@@ -722,15 +757,6 @@ cudaError_t rank_ensure(int dev, uint32_t M)
 	return cudaSuccess;
 }
 
-int radix_passes(uint32_t groups)
-{
-	int bits = 8;
-	while (groups > 1 && ((groups - 1) >> (bits - 8)) != 0) {
-		++bits;
-	}
-	return (bits + 7) / 8;
-}
-
 } /* namespace */
 
 /* largest number of distances the rank search takes (chunks must keep room for positions) */
@@ -750,13 +776,40 @@ void x3k_rank_release(int dev)
 	cudaFree(s.st_radix);
 	cudaFree(s.ctrl);
 	cudaFreeHost(s.h_back);
+	for (int i = 0; i < 36; ++i) {
+		if (s.ev[i] != nullptr) {
+			cudaEventDestroy(s.ev[i]);
+		}
+	}
+	if (s.pev_made) {
+		for (int i = 0; i < 520; ++i) {
+			cudaEventDestroy(s.pev[i]);
+		}
+	}
 	s = RankScratch();
 }
 
+/* Device time of the last profiled search on `dev` (X3_RANK_PROFILE=1): kind 0 = radix passes,
+ * 1 = level kernels, 2 = set-up (byte histogram).  `elements` is what the launches were sized
+ * for, an upper bound of what they processed. */
+int x3k_rank_profile(int dev, int kind, double *ms, double *elements, int *launches)
+{
+	if (dev < 0 || dev >= 64 || kind < 0 || kind >= 4) {
+		return -1;
+	}
+	const RankScratch &s = g_rank[dev];
+	*ms = s.prof_ms[kind];
+	*elements = s.prof_elems[kind];
+	*launches = s.prof_launches[kind];
+	return 0;
+}
+
 /*
- * Lstar for positions [0, prm.n) by the rank method.  The launches are issued on `stream`,
- * but the call returns only after the last level of the last chunk has reported its size
- * (one 8-byte read-back per level decides how many radix passes follow).
+ * Lstar for positions [0, prm.n) by the rank method.  Everything the levels need to know about
+ * each other (sizes, buffers, whether the search is over) lives in device memory, so the launches
+ * are simply queued on `stream`; the host only reads the size of level L-1 back before it queues
+ * level L (two levels of work stay queued behind that wait), to size the grids and to stop
+ * queueing once the search has ended.
  */
 cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int *launches)
 {
@@ -774,12 +827,29 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 	int dev = 0;
 	if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
 	const bool trace = getenv("X3_TRACE") != nullptr;
+	const bool profile = getenv("X3_RANK_PROFILE") != nullptr;
 	const uint32_t D = prm.D;
 	const unsigned long long CH = (unsigned long long)((RANK_MAX_M - D) & ~4095u);
 	const unsigned long long first = prm.n < CH ? prm.n : CH;
+	const auto wall0 = std::chrono::steady_clock::now();
 	if ((e = rank_ensure(dev, (uint32_t)(first + D))) != cudaSuccess) return e;
 	RankScratch &s = g_rank[dev];
+	if (trace) {
+		fprintf(stderr, "x3k_launch_rank: scratch for %llu elements ready after %.3f ms\n", first + D,
+		        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
+	}
+	if (profile && !s.pev_made) {
+		for (int i = 0; i < 520; ++i) {
+			if ((e = cudaEventCreate(&s.pev[i])) != cudaSuccess) return e;
+		}
+		s.pev_made = true;
+	}
+	for (int k = 0; k < 4; ++k) {
+		s.prof_ms[k] = s.prof_elems[k] = 0;
+		s.prof_launches[k] = 0;
+	}
 	int nl = 0;
+	const uint32_t lim = (uint32_t)prm.t + 2u; /* fewer elements than this: nobody can pass */
 
 	for (unsigned long long a0 = 0; a0 < prm.n; a0 += CH) {
 		RankArgs a;
@@ -790,6 +860,10 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 		a.D = D;
 		a.t = prm.t;
 		a.ctrl = s.ctrl;
+		a.key0 = s.key[0];
+		a.key1 = s.key[1];
+		a.pos0 = s.pos[0];
+		a.pos1 = s.pos[1];
 		a.st_level = s.st_level;
 		a.st_radix = s.st_radix;
 		const uint32_t lv_tiles = (a.M + LV_TILE - 1) / LV_TILE, rs_tiles = (a.M + RS_TILE - 1) / RS_TILE;
@@ -799,59 +873,98 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 		int ticket = 0;
 		const int maxgrid = s.sms * 8;
 		auto grid_for = [&](uint32_t tiles) { return (int)(tiles < (uint32_t)maxgrid ? (tiles > 0 ? tiles : 1) : maxgrid); };
+		s.npev = 0;
+		auto mark = [&](int kind, int level, int pass) {
+			/* profile mode: an event in front of every launch (and one behind the last) */
+			if (profile && s.npev < 259) {
+				cudaEventRecord(s.pev[s.npev], stream);
+				s.pkind[s.npev] = kind;
+				s.plevel[s.npev] = level;
+				s.ppass[s.npev] = pass;
+				++s.npev;
+			}
+		};
 
+		mark(2, 1, 0);
 		x3_rank_bytehist_kernel<<<grid_for((a.M + 65535) / 65536), 256, 0, stream>>>(a);
-		x3_rank_radix_kernel<true><<<grid_for(rs_tiles), RS_THREADS, 0, stream>>>(a, nullptr, nullptr, s.key[0], s.pos[0], 1, 0,
-		                                                                        ticket, (uint32_t)ticket + 1u);
+		mark(0, 1, 0);
+		x3_rank_radix_kernel<true><<<grid_for(rs_tiles), RS_THREADS, 0, stream>>>(a, 1, 0, ticket, (uint32_t)ticket + 1u);
 		++ticket;
 		nl += 2;
-		int cur = 0;
-		uint32_t m = a.M;
+		uint32_t known = a.M; /* upper bound of the size of the level about to be queued */
 		for (int L = 1; L <= 32; ++L) {
-			const int lgrid = grid_for((m + LV_TILE - 1) / LV_TILE);
+			if (L >= 3) {
+				/* lv[L-1] as level L-2 left it: its size bounds level L, and tells whether level L-1
+				 * (already queued) was the last one */
+				if ((e = cudaEventSynchronize(s.ev[L - 2])) != cudaSuccess) return e;
+				known = s.h_back[4 * (L - 2)];
+				if (trace) {
+					fprintf(stderr, "x3k_launch_rank: chunk %llu level %d: %u elements, %u groups\n", a0 / CH, L - 1,
+					        known, s.h_back[4 * (L - 2) + 1]);
+				}
+				if (known < lim) {
+					break;
+				}
+			}
+			mark(1, L, 0);
 			if (L == 1) {
-				x3_rank_level_kernel<true><<<lgrid, LV_THREADS, 0, stream>>>(a, s.key[cur], s.pos[cur], s.key[cur ^ 1],
-				                                                             s.pos[cur ^ 1], L, ticket);
+				x3_rank_level_kernel<true><<<grid_for((known + LV_TILE - 1) / LV_TILE), LV_THREADS, 0, stream>>>(a, L, ticket);
 			} else {
-				x3_rank_level_kernel<false><<<lgrid, LV_THREADS, 0, stream>>>(a, s.key[cur], s.pos[cur], s.key[cur ^ 1],
-				                                                              s.pos[cur ^ 1], L, ticket);
+				x3_rank_level_kernel<false><<<grid_for((known + LV_TILE - 1) / LV_TILE), LV_THREADS, 0, stream>>>(a, L, ticket);
 			}
 			++ticket;
 			++nl;
 			if (L == 32) {
 				break;
 			}
-			if ((e = cudaMemcpyAsync(s.h_back, &s.ctrl->lv[L + 1], 8, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-			if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
-			const uint32_t mn = s.h_back[0], groups = s.h_back[1];
-			const int np = radix_passes(groups);
-			if (trace) {
-				fprintf(stderr, "x3k_launch_rank: chunk %llu level %d: %u elements -> %u kept, %u groups, %d radix passes\n",
-				        a0 / CH, L, m, mn, groups, np);
-			}
-			if (mn < (uint32_t)prm.t + 2u) {
-				/* nobody can pass the next level: whoever passed this one keeps it */
-				if (mn > 0) {
-					x3_rank_flush_kernel<<<1, 256, 0, stream>>>(a, s.pos[cur ^ 1], L + 1, L);
-					++nl;
-				}
-				break;
-			}
-			int src = cur ^ 1;
+			if ((e = cudaMemcpyAsync(s.h_back + 4 * L, &s.ctrl->lv[L + 1], 16, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+			if ((e = cudaEventRecord(s.ev[L], stream)) != cudaSuccess) return e;
+			/* the level-(L+1) keys have at most min(256^L, known) ranks: queue that many passes; a pass
+			 * the real rank range does not need returns at once */
+			const uint32_t rbound = L == 1 ? (known < 256u ? known : 256u) : (L == 2 ? (known < 65536u ? known : 65536u) : known);
+			const int np = radix_passes(rbound);
 			for (int pass = 0; pass < np; ++pass) {
-				x3_rank_radix_kernel<false><<<grid_for((mn + RS_TILE - 1) / RS_TILE), RS_THREADS, 0, stream>>>(
-				    a, s.key[src], s.pos[src], s.key[src ^ 1], s.pos[src ^ 1], L + 1, pass, ticket, (uint32_t)ticket + 1u);
+				mark(0, L + 1, pass);
+				x3_rank_radix_kernel<false><<<grid_for((known + RS_TILE - 1) / RS_TILE), RS_THREADS, 0, stream>>>(
+				    a, L + 1, pass, ticket, (uint32_t)ticket + 1u);
 				++ticket;
 				++nl;
-				src ^= 1;
 			}
-			cur = src;
-			m = mn;
 		}
 		if ((e = cudaGetLastError()) != cudaSuccess) return e;
+		if (profile) {
+			mark(3, 0, 0);
+			if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+			RankCtrl *hc = (RankCtrl *)malloc(sizeof(RankCtrl));
+			if (hc == nullptr) return cudaErrorMemoryAllocation;
+			if ((e = cudaMemcpy(hc, s.ctrl, sizeof(RankCtrl), cudaMemcpyDeviceToHost)) != cudaSuccess) {
+				free(hc);
+				return e;
+			}
+			for (int i = 0; i + 1 < s.npev; ++i) {
+				float ms = 0.f;
+				if (cudaEventElapsedTime(&ms, s.pev[i], s.pev[i + 1]) != cudaSuccess) {
+					continue;
+				}
+				/* elements the launch really processed, from the level sizes the device recorded */
+				const int kind = s.pkind[i], lv = s.plevel[i];
+				double el = hc->lv[lv].m;
+				if (kind == 0 && lv > 1 && (hc->lv[lv].m < lim || s.ppass[i] >= radix_passes(hc->lv[lv].groups))) {
+					el = 0; /* a pass that returned at once */
+				}
+				s.prof_ms[kind] += ms;
+				s.prof_elems[kind] += el;
+				s.prof_launches[kind] += el > 0 ? 1 : 0;
+			}
+			free(hc);
+		}
 	}
 	if (launches != nullptr) {
 		*launches += nl;
+	}
+	if (trace) {
+		fprintf(stderr, "x3k_launch_rank: %d launches queued after %.3f ms\n", nl,
+		        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
 	}
 	return cudaGetLastError();
 }
