@@ -65,7 +65,7 @@ for name, n, W, t in big:
         if best is None or tm.kernel_ms < best.kernel_ms:
             best = tm
     if W <= 65536:
-        ref, _, tms = pkg.search_host(a, W=W, t=t, ngpus=1, variant=pkg.KERNEL_DEFAULT)
+        ref, _, tms = pkg.search_host(a, W=W, t=t, ngpus=1, variant=pkg.KERNEL_STREAM)
         report(name, n, W, t, ls, ref, best, "stream")
         print(f"    stream kernel: {tms.kernel_ms:.3f} ms", flush=True)
     else:

@@ -390,9 +390,15 @@ __global__ void __launch_bounds__(RS_THREADS, 4) x3_rank_radix_kernel(RankArgs a
  * Bit 31 of a position word says "this element passed the previous level": Lstar is written
  * once per position, at the level where it stops passing (or by the level-1 rare path, the
  * flush after the last level, or level 32). */
-template <bool FIRST>
+template <int LK>
 __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a, int L, int ticket)
 {
+	/* LK = min(L, 4).  Keys of levels 1-3 carry the bytes behind the gram in their upper bits
+	 * (level 1: b3 b2 b1 | b0; level 2: b3 b2 | rank8 b1; level 3: b3 | rank16 b2), put there by the
+	 * position-ordered level-1 pass for free; the radix passes only sort the low `gram` bits, so the
+	 * first byte gather happens at level 4, when the arrays are small. */
+	constexpr bool FIRST = LK == 1;
+	constexpr uint32_t KM = LK == 1 ? 0xffu : (LK == 2 ? 0xffffu : (LK == 3 ? 0xffffffu : 0xffffffffu));
 	__shared__ __align__(16) uint32_t sk[LV_TILE + 256];
 	__shared__ __align__(16) uint32_t sp[LV_TILE + 256];
 	__shared__ uint32_t hist[4][256];
@@ -487,7 +493,6 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 			const bool out = pp < n_out;
 			bool pass;
 			if (FIRST) {
-				/* level-1 keys carry 4 bytes; the gram is the low byte (KEY_NONE is no sentinel here) */
 				pass = valid && out && base + idx + la < m && ((sk[idx + la] ^ kk) & 255u) == 0u && sp[idx + la] - pp <= D;
 				if (valid && out && !pass) {
 					/* the byte has c1 <= t followers within D: tc* = c1 - 1, so Lstar = #{L : count_L >= c1}
@@ -518,7 +523,9 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 					a.lstar[pp] = (uint8_t)(c1 >= 2 ? best : 0u);
 				}
 			} else {
-				pass = valid && out && sk[idx + la] == kk && (sp[idx + la] & PMASK) - pp <= D;
+				/* masked compare: no sentinel value exists, so the array bound is checked */
+				pass = valid && out && base + idx + la < m && ((sk[idx + la] ^ kk) & KM) == 0u &&
+				       (sp[idx + la] & PMASK) - pp <= D;
 			}
 			if (!FIRST && (pw & PFLAG) && !pass) {
 				a.lstar[pp] = (uint8_t)(L - 1); /* passed level L-1, stops here */
@@ -551,15 +558,11 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 				rk = __ldg(keyIn + prevlast);
 				rp = __ldg(posIn + prevlast) & PMASK;
 			}
-			if (FIRST) {
-				rk &= 255u;
-			}
+			rk &= KM;
 		}
 		uint32_t partm = 0, headm = 0;
 		uint32_t kprev = tid > 0 ? sk[tid * LV_ITEMS - 1] : (base > 0 ? __ldg(keyIn + base - 1) : ~k[0]);
-		if (FIRST) {
-			kprev &= 255u; /* element 0 is a head by its index */
-		}
+		kprev &= KM; /* element 0 is a head by its index */
 #pragma unroll
 		for (int e = 0; e < LV_ITEMS; ++e) {
 			if (i0 + e < m) {
@@ -568,7 +571,7 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 					have = true;
 					rp = pp;
 				}
-				const uint32_t ke = FIRST ? k[e] & 255u : k[e];
+				const uint32_t ke = k[e] & KM;
 				if ((actm >> e) & 1u) {
 					rk = ke;
 				}
@@ -587,7 +590,10 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 #pragma unroll
 		for (int e = 0; e < LV_ITEMS; ++e) {
 			if ((partm >> e) & 1u) {
-				const uint32_t by = FIRST ? (k[e] >> 8) & 255u : (uint32_t)__ldg(a.x + (p[e] & PMASK) + L);
+				const uint32_t by = LK == 1 ? (k[e] >> 8) & 255u
+				                  : LK == 2 ? (k[e] >> 16) & 255u
+				                  : LK == 3 ? k[e] >> 24
+				                            : (uint32_t)__ldg(a.x + (p[e] & PMASK) + L);
 				nb[e >> 2] |= by << (8 * (e & 3));
 			}
 		}
@@ -610,7 +616,11 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 			for (int e = 0; e < LV_ITEMS; ++e) {
 				hloc += (headm >> e) & 1u;
 				if ((partm >> e) & 1u) {
-					sk[lidx] = ((hloc - 1u) << 8) | ((nb[e >> 2] >> (8 * (e & 3))) & 255u);
+					/* bytes still ahead stay on top of the new (rank, byte) gram.  Sums, not ORs: the local
+					 * rank is -1 for elements of a group that began in an earlier tile, and only becomes a
+					 * real rank (mod 2^32) once the tiles in front are added at copy-out */
+					const uint32_t upper = LK == 1 ? k[e] & 0xffff0000u : (LK == 2 ? k[e] & 0xff000000u : 0u);
+					sk[lidx] = upper + ((hloc - 1u) << 8) + ((nb[e >> 2] >> (8 * (e & 3))) & 255u);
 					sp[lidx] = (p[e] & PMASK) | (((actm >> e) & 1u) ? PFLAG : 0u);
 					++lidx;
 				}
@@ -907,10 +917,15 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 				}
 			}
 			mark(1, L, 0);
+			const int lgrid = grid_for((known + LV_TILE - 1) / LV_TILE);
 			if (L == 1) {
-				x3_rank_level_kernel<true><<<grid_for((known + LV_TILE - 1) / LV_TILE), LV_THREADS, 0, stream>>>(a, L, ticket);
+				x3_rank_level_kernel<1><<<lgrid, LV_THREADS, 0, stream>>>(a, L, ticket);
+			} else if (L == 2) {
+				x3_rank_level_kernel<2><<<lgrid, LV_THREADS, 0, stream>>>(a, L, ticket);
+			} else if (L == 3) {
+				x3_rank_level_kernel<3><<<lgrid, LV_THREADS, 0, stream>>>(a, L, ticket);
 			} else {
-				x3_rank_level_kernel<false><<<grid_for((known + LV_TILE - 1) / LV_TILE), LV_THREADS, 0, stream>>>(a, L, ticket);
+				x3_rank_level_kernel<4><<<lgrid, LV_THREADS, 0, stream>>>(a, L, ticket);
 			}
 			++ticket;
 			++nl;
