@@ -1,0 +1,55 @@
+"""BASELINE.json configs C2..C5 at full size through the production search (C ABI, host buffers):
+kernel time, end-to-end time, Lstar checksum, sampled bands against the oracle, and (C2..C4) bit
+identity with the brute-force kernel.
+
+    python tests/gpu_configs.py [C2,C3,C4,C5]
+"""
+import hashlib
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+import __graft_entry__ as g  # noqa: E402
+import oracle_lib as ol  # noqa: E402
+
+pkg = g.load_package()
+corpus = g.load_submodule("corpus")
+CFG = {"C2": (None, 8192, 15), "C3": (50_000_000, 1 << 20, 64), "C4": (None, 8192, 15), "C5": (None, 8192, 15)}
+names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["C2", "C3", "C4", "C5"]
+out = {}
+for name in names:
+    size, W, t = CFG[name]
+    t0 = time.time()
+    data = np.frombuffer(corpus.generate(name, size) if size else corpus.generate(name), dtype=np.uint8)
+    n = len(data)
+    gen_s = time.time() - t0
+    best = None
+    for rep in range(3):
+        ls, _, tm = pkg.search_host(data, W=W, t=t, ngpus=1, variant=pkg.KERNEL_DEFAULT)
+        if best is None or tm.kernel_ms < best[0]:
+            best = (tm.kernel_ms, tm.total_ms, tm.h2d_ms, tm.d2h_ms, tm.launches)
+    rec = {"bytes": n, "W": W, "t": t, "kernel_ms": best[0], "total_ms": best[1], "h2d_ms": best[2], "d2h_ms": best[3],
+           "launches": best[4], "search_MB_per_s": n / best[0] / 1e3, "e2e_MB_per_s": n / best[1] / 1e3,
+           "lstar_sha256": hashlib.sha256(ls.tobytes()).hexdigest(),
+           "lstar_mean": float(ls.mean()), "generate_s": gen_s}
+    # sampled bands against the oracle (the CPU needs m * (W - 33) steps per band)
+    m = 2000 if W > 100000 else 20000
+    ok = True
+    for a in (0, n // 2, n - m):
+        _, ref = ol.table(data, W, t, p0=a, p1=a + m)
+        ok = ok and bool(np.array_equal(ls[a:a + m], ref))
+    rec["oracle_bands_ok"] = ok
+    if W <= 65536 and n <= 60_000_000:
+        bf, _, tmb = pkg.search_host(data, W=W, t=t, ngpus=1, variant=pkg.KERNEL_STREAM)
+        rec["equals_brute_force"] = bool(np.array_equal(bf, ls))
+        rec["brute_force_kernel_ms"] = tmb.kernel_ms
+    out[name] = rec
+    print(name, json.dumps(rec), flush=True)
+(ROOT / "gpurun_out").mkdir(exist_ok=True)
+(ROOT / "gpurun_out" / "configs.json").write_text(json.dumps(out, indent=1))
