@@ -107,6 +107,18 @@ def test_rank_search_equals_oracle_threshold_sweep(pkg, corpus, t):
     _assert_rank_same(pkg, _inputs(corpus, "binary", 20000), 8192, t)
 
 
+@pytest.mark.parametrize("kind,n,W,t", [("text", 30000, 8192, 15), ("zeros", 9000, 1024, 3), ("period", 20000, 8192, 15),
+                                        ("binary", 40000, 8192, 15), ("rand2", 12000, 100, 50)])
+def test_rank_search_without_tail_kernel(pkg, corpus, monkeypatch, kind, n, W, t):
+    """X3_RANK_NO_TAIL keeps small arrays on the multi-launch path (level + radix kernels): both
+    ways of finishing a search give the oracle's table."""
+    data = _inputs(corpus, kind, n)
+    monkeypatch.setenv("X3_RANK_NO_TAIL", "1")
+    _assert_rank_same(pkg, data, W, t)
+    monkeypatch.delenv("X3_RANK_NO_TAIL")
+    _assert_rank_same(pkg, data, W, t)
+
+
 def test_rank_search_rejects_table_request(pkg):
     with pytest.raises(pkg.X3SearchError):
         pkg.search_host(np.zeros(100, dtype=np.uint8), W=8192, t=15, variant=pkg.KERNEL_RANK, want_table=True)

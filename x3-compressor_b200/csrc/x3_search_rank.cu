@@ -709,6 +709,298 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 	}
 }
 
+/* ---- the tail: every remaining level of a small array in one launch ------------------------
+ * Once an array has shrunk to TL_CAP elements the levels cost launches, not bandwidth (a long
+ * run of one byte keeps a few thousand elements alive through all 32 levels).  One CTA then
+ * takes the sorted level-L0 array into shared memory and runs test / prune / re-key / radix sort
+ * for every remaining level there, with the same rules as the level and radix kernels. */
+constexpr int TL_THREADS = 1024;
+constexpr int TL_WARPS = TL_THREADS / 32;
+constexpr int TL_ITEMS = 8;
+constexpr int TL_CAP = TL_THREADS * TL_ITEMS;
+constexpr size_t TL_SMEM = (size_t)4 * TL_CAP * 4 + (size_t)TL_WARPS * 256 * 4 + 256 * 4 + (TL_CAP / 32) * 4;
+
+__device__ __forceinline__ unsigned long long tl_excl_sum(unsigned long long v, unsigned long long *ws,
+                                                          unsigned long long *total)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	unsigned long long inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const unsigned long long o = __shfl_up_sync(FULL_MASK, inc, d);
+		if (lane >= d) {
+			inc += o;
+		}
+	}
+	if (lane == 31) {
+		ws[warp] = inc;
+	}
+	__syncthreads();
+	if (warp == 0) {
+		const unsigned long long w = ws[lane];
+		unsigned long long wi = w;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const unsigned long long o = __shfl_up_sync(FULL_MASK, wi, d);
+			if (lane >= d) {
+				wi += o;
+			}
+		}
+		ws[lane] = wi - w;
+		if (lane == 31) {
+			ws[32] = wi;
+		}
+	}
+	__syncthreads();
+	const unsigned long long res = ws[warp] + inc - v;
+	*total = ws[32];
+	__syncthreads();
+	return res;
+}
+
+__device__ __forceinline__ int tl_excl_max(int v, int ident, int *ws)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int inc = v;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const int o = __shfl_up_sync(FULL_MASK, inc, d);
+		if (lane >= d) {
+			inc = max(inc, o);
+		}
+	}
+	if (lane == 31) {
+		ws[warp] = inc;
+	}
+	__syncthreads();
+	if (warp == 0) {
+		const int w = ws[lane];
+		int wi = w;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const int o = __shfl_up_sync(FULL_MASK, wi, d);
+			if (lane >= d) {
+				wi = max(wi, o);
+			}
+		}
+		/* exclusive over the warps */
+		int ex = __shfl_up_sync(FULL_MASK, wi, 1);
+		if (lane == 0) {
+			ex = ident;
+		}
+		ws[lane] = max(ex, ident);
+	}
+	__syncthreads();
+	int ex = __shfl_up_sync(FULL_MASK, inc, 1);
+	if (lane == 0) {
+		ex = ident;
+	}
+	const int res = max(ws[warp], ex);
+	__syncthreads();
+	return res;
+}
+
+__global__ void __launch_bounds__(TL_THREADS, 1) x3_rank_tail_kernel(RankArgs a, int L0)
+{
+	extern __shared__ __align__(16) uint8_t tl_smem[];
+	/* two (key, position) buffers: buffer c at words [2 c TL_CAP, 2 (c+1) TL_CAP) */
+	uint32_t *const sm32 = reinterpret_cast<uint32_t *>(tl_smem);
+#define TL_K(c) (sm32 + (size_t)(c) * 2 * TL_CAP)
+#define TL_P(c) (sm32 + (size_t)(c) * 2 * TL_CAP + TL_CAP)
+	uint32_t(*wcnt)[256] = reinterpret_cast<uint32_t(*)[256]>(sm32 + 4 * TL_CAP);
+	uint32_t *dbase = reinterpret_cast<uint32_t *>(wcnt + TL_WARPS);
+	uint32_t *actbits = dbase + 256;
+	__shared__ unsigned long long ws[33];
+	__shared__ int wsi[32];
+
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t D = a.D, n_out = a.n_out;
+	const uint32_t la = (uint32_t)a.t + 1u;
+	const uint32_t lt = (1u << lane) - 1u;
+	uint32_t m = a.ctrl->lv[L0].m;
+	if (m == 0 || m > (uint32_t)TL_CAP) {
+		return; /* the search ended earlier (m == 0); m > TL_CAP cannot happen (the host queues this
+		         * kernel only behind a level whose size was at most TL_CAP) */
+	}
+	int cur = 0;
+	{
+		/* fewer than t+2 elements: the radix passes did not run, the array is where the level kernel left it */
+		const uint32_t from = m < la + 1u ? a.ctrl->lv[L0].src0 : a.ctrl->lv[L0].buf;
+		const uint32_t *__restrict__ gk = from ? a.key1 : a.key0;
+		const uint32_t *__restrict__ gp = from ? a.pos1 : a.pos0;
+		for (uint32_t i = tid; i < m; i += TL_THREADS) {
+			TL_K(0)[i] = gk[i];
+			TL_P(0)[i] = gp[i];
+		}
+	}
+	__syncthreads();
+
+	for (int L = L0; L <= 32; ++L) {
+		uint32_t *K = TL_K(cur), *P = TL_P(cur), *KO = TL_K(cur ^ 1), *PO = TL_P(cur ^ 1);
+		if (m < la + 1u) {
+			/* nobody can pass this level: whoever passed the previous one keeps it */
+			for (uint32_t i = tid; i < m; i += TL_THREADS) {
+				const uint32_t pw = P[i];
+				if (pw & PFLAG) {
+					a.lstar[pw & PMASK] = (uint8_t)(L - 1);
+				}
+			}
+			break;
+		}
+		const uint32_t KM = L == 1 ? 0xffu : (L == 2 ? 0xffffu : (L == 3 ? 0xffffffu : 0xffffffffu));
+		/* the test (striped: conflict-free) */
+#pragma unroll
+		for (int e = 0; e < TL_ITEMS; ++e) {
+			const uint32_t i = e * TL_THREADS + tid;
+			bool pass = false;
+			if (i < m) {
+				const uint32_t kk = K[i], pw = P[i];
+				const uint32_t pp = pw & PMASK;
+				pass = pp < n_out && i + la < m && ((K[i + la] ^ kk) & KM) == 0u && (P[i + la] & PMASK) - pp <= D;
+				if ((pw & PFLAG) && !pass) {
+					a.lstar[pp] = (uint8_t)(L - 1);
+				}
+				if (L == 32 && pass) {
+					a.lstar[pp] = 32;
+				}
+			}
+			const uint32_t am = __ballot_sync(FULL_MASK, pass);
+			if (lane == 0) {
+				actbits[e * TL_WARPS + warp] = am;
+			}
+		}
+		__syncthreads();
+		if (L == 32) {
+			break;
+		}
+		/* prune and re-key (blocked: thread owns 8 consecutive elements) */
+		const uint32_t i0 = tid * TL_ITEMS;
+		const uint32_t actm = (actbits[tid >> 2] >> ((tid & 3) * 8)) & 0xffu;
+		const int mylast = actm != 0 ? (int)i0 + (31 - __clz((int)actm)) : -1;
+		const int prevlast = tl_excl_max(mylast, -1, wsi);
+		bool have = prevlast >= 0;
+		uint32_t rk = 0, rp = 0;
+		if (have) {
+			rk = K[prevlast] & KM;
+			rp = P[prevlast] & PMASK;
+		}
+		uint32_t partm = 0, headm = 0;
+		uint32_t kprev = i0 > 0 && i0 <= m ? K[i0 - 1] & KM : 0u;
+		uint32_t k[TL_ITEMS], p[TL_ITEMS];
+#pragma unroll
+		for (int e = 0; e < TL_ITEMS; ++e) {
+			k[e] = 0;
+			p[e] = 0;
+			if (i0 + e < m) {
+				k[e] = K[i0 + e];
+				p[e] = P[i0 + e];
+				const uint32_t pp = p[e] & PMASK;
+				const uint32_t ke = k[e] & KM;
+				if ((actm >> e) & 1u) {
+					have = true;
+					rp = pp;
+					rk = ke;
+				}
+				if (have && rk == ke && pp - rp <= D) {
+					partm |= 1u << e;
+				}
+				if (i0 + e == 0 || ke != kprev) {
+					headm |= 1u << e;
+				}
+				kprev = ke;
+			}
+		}
+		const unsigned long long mine = (unsigned long long)__popc(partm) | ((unsigned long long)__popc(headm) << 32);
+		unsigned long long total;
+		const unsigned long long ex = tl_excl_sum(mine, ws, &total);
+		{
+			uint32_t dst = (uint32_t)(ex & 0xffffffffull);
+			uint32_t hcount = (uint32_t)(ex >> 32);
+#pragma unroll
+			for (int e = 0; e < TL_ITEMS; ++e) {
+				hcount += (headm >> e) & 1u;
+				if ((partm >> e) & 1u) {
+					const uint32_t pp = p[e] & PMASK;
+					const uint32_t by = L == 1 ? (k[e] >> 8) & 255u
+					                  : L == 2 ? (k[e] >> 16) & 255u
+					                  : L == 3 ? k[e] >> 24
+					                           : (uint32_t)__ldg(a.x + pp + L);
+					const uint32_t upper = L == 1 ? k[e] & 0xffff0000u : (L == 2 ? k[e] & 0xff000000u : 0u);
+					KO[dst] = upper + ((hcount - 1u) << 8) + by;
+					PO[dst] = pp | (((actm >> e) & 1u) ? PFLAG : 0u);
+					++dst;
+				}
+			}
+		}
+		__syncthreads();
+		m = (uint32_t)(total & 0xffffffffull);
+		const uint32_t groups = (uint32_t)(total >> 32);
+		cur ^= 1;
+		if (m < la + 1u) {
+			continue; /* the next iteration writes the survivors out and stops */
+		}
+		/* stable LSD radix sort of the survivors by (rank, byte), 8 bits per pass, all in shared memory */
+		const int np = radix_passes(groups);
+		for (int pass = 0; pass < np; ++pass) {
+			uint32_t *SK = TL_K(cur), *SP = TL_P(cur), *DK = TL_K(cur ^ 1), *DP = TL_P(cur ^ 1);
+			const int shift = 8 * pass;
+			for (int j = tid; j < TL_WARPS * 256; j += TL_THREADS) {
+				(&wcnt[0][0])[j] = 0;
+			}
+			__syncthreads();
+			uint32_t key[TL_ITEMS], pos[TL_ITEMS], off[TL_ITEMS];
+#pragma unroll
+			for (int q = 0; q < TL_ITEMS; ++q) {
+				const uint32_t i = warp * (32 * TL_ITEMS) + 32 * q + lane;
+				const bool valid = i < m;
+				key[q] = valid ? SK[i] : 0u;
+				pos[q] = valid ? SP[i] : 0u;
+				const uint32_t d = valid ? ((key[q] >> shift) & 255u) : 256u;
+				const uint32_t peers = __match_any_sync(FULL_MASK, d);
+				const int leader = __ffs(peers) - 1;
+				uint32_t old = 0;
+				if (lane == leader && valid) {
+					old = wcnt[warp][d];
+					wcnt[warp][d] = old + __popc(peers);
+				}
+				old = __shfl_sync(FULL_MASK, old, leader);
+				off[q] = valid ? (old + __popc(peers & lt)) | (d << 16) : 0xffffffffu;
+				__syncwarp();
+			}
+			__syncthreads();
+			/* digit tid (first 256 threads): offsets of the warps, then the digit's first slot */
+			unsigned long long run = 0;
+			if (tid < 256) {
+				uint32_t r = 0;
+#pragma unroll 8
+				for (int w = 0; w < TL_WARPS; ++w) {
+					const uint32_t c = wcnt[w][tid];
+					wcnt[w][tid] = r;
+					r += c;
+				}
+				run = r;
+			}
+			unsigned long long tot2;
+			const unsigned long long dex = tl_excl_sum(run, ws, &tot2);
+			if (tid < 256) {
+				dbase[tid] = (uint32_t)dex;
+			}
+			__syncthreads();
+#pragma unroll
+			for (int q = 0; q < TL_ITEMS; ++q) {
+				if (off[q] != 0xffffffffu) {
+					const uint32_t d = off[q] >> 16;
+					const uint32_t dst = dbase[d] + wcnt[warp][d] + (off[q] & 0xffffu);
+					DK[dst] = key[q];
+					DP[dst] = pos[q];
+				}
+			}
+			__syncthreads();
+			cur ^= 1;
+		}
+	}
+}
+
 /* ---- per-device scratch ------------------------------------------------------------------ */
 struct RankScratch {
 	uint32_t cap = 0; /* elements */
@@ -743,6 +1035,7 @@ cudaError_t rank_ensure(int dev, uint32_t M)
 			if ((e = cudaEventCreateWithFlags(&s.ev[i], cudaEventDisableTiming)) != cudaSuccess) return e;
 		}
 		if ((e = cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+		if ((e = cudaFuncSetAttribute(x3_rank_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM)) != cudaSuccess) return e;
 	}
 	if (M <= s.cap) {
 		return cudaSuccess;
@@ -838,6 +1131,7 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 	if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
 	const bool trace = getenv("X3_TRACE") != nullptr;
 	const bool profile = getenv("X3_RANK_PROFILE") != nullptr;
+	const bool no_tail = getenv("X3_RANK_NO_TAIL") != nullptr; /* testing knob: never changes results */
 	const uint32_t D = prm.D;
 	const unsigned long long CH = (unsigned long long)((RANK_MAX_M - D) & ~4095u);
 	const unsigned long long first = prm.n < CH ? prm.n : CH;
@@ -913,6 +1207,13 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 					        known, s.h_back[4 * (L - 2) + 1]);
 				}
 				if (known < lim) {
+					break;
+				}
+				if (known <= (uint32_t)TL_CAP && !no_tail) {
+					/* small enough for one CTA: every remaining level in one launch */
+					mark(1, L, 0);
+					x3_rank_tail_kernel<<<1, TL_THREADS, TL_SMEM, stream>>>(a, L);
+					++nl;
 					break;
 				}
 			}
