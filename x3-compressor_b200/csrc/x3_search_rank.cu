@@ -43,6 +43,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace {
 
@@ -80,6 +81,8 @@ struct RankArgs {
 	int t;
 	RankCtrl *ctrl;
 	uint32_t *key0, *key1, *pos0, *pos1; /* the two element buffers the levels and radix passes ping-pong between */
+	volatile uint32_t *report;    /* pinned host memory: [4 L] = {size, groups} of level L+1, then `seq` */
+	uint32_t seq;                 /* tag of this chunk's reports */
 	unsigned long long *st_level; /* [tiles of the level kernel] */
 	unsigned long long *st_radix; /* [tiles of the radix kernel][256] */
 };
@@ -428,6 +431,10 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 			if (tid == 0) {
 				a.ctrl->lv[L + 1].m = 0;
 				a.ctrl->lv[L + 1].groups = 0;
+				a.report[4 * L] = 0;
+				a.report[4 * L + 1] = 0;
+				__threadfence_system();
+				a.report[4 * L + 2] = a.seq;
 			}
 		}
 		return;
@@ -669,6 +676,11 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 					a.ctrl->lv[L + 1].groups = g;
 					a.ctrl->lv[L + 1].src0 = inb ^ 1u;
 					a.ctrl->lv[L + 1].buf = inb ^ 1u ^ (uint32_t)(radix_passes(g) & 1);
+					/* the host sizes the launches two levels on from this (zero-copy, no stream traffic) */
+					a.report[4 * L] = (uint32_t)(tot & 0xffffffull);
+					a.report[4 * L + 1] = g;
+					__threadfence_system();
+					a.report[4 * L + 2] = a.seq;
 				}
 			}
 		}
@@ -1009,8 +1021,8 @@ struct RankScratch {
 	RankCtrl *ctrl = nullptr;
 	unsigned long long *st_level = nullptr;
 	unsigned long long *st_radix = nullptr;
-	uint32_t *h_back = nullptr;       /* pinned: lv[L + 1] as read back after level L */
-	cudaEvent_t ev[36] = {nullptr};   /* ev[L]: that read-back has landed */
+	uint32_t *h_back = nullptr;       /* pinned, device-visible: the level kernels report lv[L + 1] here */
+	uint32_t seq = 0;                 /* tag of the current chunk's reports */
 	int sms = 0;
 	/* X3_RANK_PROFILE: device time per kernel family of the last search */
 	cudaEvent_t pev[520];
@@ -1030,10 +1042,8 @@ cudaError_t rank_ensure(int dev, uint32_t M)
 	cudaError_t e;
 	if (s.ctrl == nullptr) {
 		if ((e = cudaMalloc((void **)&s.ctrl, sizeof(RankCtrl))) != cudaSuccess) return e;
-		if ((e = cudaMallocHost((void **)&s.h_back, 36 * 16)) != cudaSuccess) return e;
-		for (int i = 0; i < 36; ++i) {
-			if ((e = cudaEventCreateWithFlags(&s.ev[i], cudaEventDisableTiming)) != cudaSuccess) return e;
-		}
+		if ((e = cudaHostAlloc((void **)&s.h_back, 36 * 16, cudaHostAllocMapped)) != cudaSuccess) return e;
+		memset(s.h_back, 0, 36 * 16);
 		if ((e = cudaDeviceGetAttribute(&s.sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
 		if ((e = cudaFuncSetAttribute(x3_rank_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_SMEM)) != cudaSuccess) return e;
 	}
@@ -1079,11 +1089,6 @@ void x3k_rank_release(int dev)
 	cudaFree(s.st_radix);
 	cudaFree(s.ctrl);
 	cudaFreeHost(s.h_back);
-	for (int i = 0; i < 36; ++i) {
-		if (s.ev[i] != nullptr) {
-			cudaEventDestroy(s.ev[i]);
-		}
-	}
 	if (s.pev_made) {
 		for (int i = 0; i < 520; ++i) {
 			cudaEventDestroy(s.pev[i]);
@@ -1170,6 +1175,13 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 		a.pos1 = s.pos[1];
 		a.st_level = s.st_level;
 		a.st_radix = s.st_radix;
+		{
+			void *dp = nullptr;
+			if ((e = cudaHostGetDevicePointer(&dp, s.h_back, 0)) != cudaSuccess) return e;
+			a.report = (volatile uint32_t *)dp;
+		}
+		s.seq = s.seq + 1u == 0u ? 1u : s.seq + 1u;
+		a.seq = s.seq;
 		const uint32_t lv_tiles = (a.M + LV_TILE - 1) / LV_TILE, rs_tiles = (a.M + RS_TILE - 1) / RS_TILE;
 		if ((e = cudaMemsetAsync(s.ctrl, 0, sizeof(RankCtrl), stream)) != cudaSuccess) return e;
 		if ((e = cudaMemsetAsync(s.st_level, 0, (size_t)lv_tiles * 8, stream)) != cudaSuccess) return e;
@@ -1200,8 +1212,17 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 			if (L >= 3) {
 				/* lv[L-1] as level L-2 left it: its size bounds level L, and tells whether level L-1
 				 * (already queued) was the last one */
-				if ((e = cudaEventSynchronize(s.ev[L - 2])) != cudaSuccess) return e;
-				known = s.h_back[4 * (L - 2)];
+				volatile uint32_t *rep = s.h_back + 4 * (L - 2);
+				for (unsigned spins = 0; rep[2] != a.seq; ++spins) {
+					if ((spins & 0xfffffu) == 0xfffffu) {
+						/* a kernel that died would never report: do not spin on a failed stream */
+						const cudaError_t q = cudaStreamQuery(stream);
+						if (q != cudaErrorNotReady && rep[2] != a.seq) {
+							return q == cudaSuccess ? cudaErrorUnknown : q;
+						}
+					}
+				}
+				known = rep[0];
 				if (trace) {
 					fprintf(stderr, "x3k_launch_rank: chunk %llu level %d: %u elements, %u groups\n", a0 / CH, L - 1,
 					        known, s.h_back[4 * (L - 2) + 1]);
@@ -1233,8 +1254,6 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 			if (L == 32) {
 				break;
 			}
-			if ((e = cudaMemcpyAsync(s.h_back + 4 * L, &s.ctrl->lv[L + 1], 16, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-			if ((e = cudaEventRecord(s.ev[L], stream)) != cudaSuccess) return e;
 			/* the level-(L+1) keys have at most min(256^L, known) ranks: queue that many passes; a pass
 			 * the real rank range does not need returns at once */
 			const uint32_t rbound = L == 1 ? (known < 256u ? known : 256u) : (L == 2 ? (known < 65536u ? known : 65536u) : known);
