@@ -157,6 +157,20 @@ __device__ __forceinline__ int block_excl_max(int v, int ident, int *ws)
 	return max(before, ex);
 }
 
+/* Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-serialization
+ * attribute may start while its predecessor in the stream is still draining; it must not touch
+ * anything the predecessor wrote before this returns (predecessor complete, memory flushed). */
+__device__ __forceinline__ void pdl_wait()
+{
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+/* lets the next kernel of the stream begin launching (it still waits in pdl_wait) */
+__device__ __forceinline__ void pdl_launch_dependents()
+{
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p)
 {
 	unsigned long long v;
@@ -184,6 +198,7 @@ __host__ __device__ __forceinline__ int radix_passes(uint32_t groups)
 __global__ void __launch_bounds__(256) x3_rank_bytehist_kernel(RankArgs a)
 {
 	__shared__ uint32_t h[256];
+	pdl_launch_dependents();
 	h[threadIdx.x] = 0;
 	__syncthreads();
 	const uint32_t nvec = a.M / 16;
@@ -233,6 +248,8 @@ __global__ void __launch_bounds__(RS_THREADS, 4) x3_rank_radix_kernel(RankArgs a
 	__shared__ uint32_t wsum[RS_WARPS + 1];
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	pdl_wait(); /* programmatic dependent launch: everything above overlapped the previous kernel's tail */
+	pdl_launch_dependents();
 	const uint32_t m = a.ctrl->lv[level].m;
 	if (!INIT && (m < (uint32_t)a.t + 2u || pass >= radix_passes(a.ctrl->lv[level].groups))) {
 		return; /* nobody can pass this level any more / the keys have no such digit */
@@ -412,6 +429,8 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 	__shared__ unsigned long long s_excl;
 
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	pdl_wait();
+	pdl_launch_dependents();
 	const uint32_t m = a.ctrl->lv[L].m;
 	const uint32_t ntiles = (m + LV_TILE - 1) / LV_TILE;
 	const uint32_t D = a.D, n_out = a.n_out;
@@ -829,6 +848,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) x3_rank_tail_kernel(RankArgs a,
 	const uint32_t D = a.D, n_out = a.n_out;
 	const uint32_t la = (uint32_t)a.t + 1u;
 	const uint32_t lt = (1u << lane) - 1u;
+	pdl_wait();
 	uint32_t m = a.ctrl->lv[L0].m;
 	if (m == 0 || m > (uint32_t)TL_CAP) {
 		return; /* the search ended earlier (m == 0); m > TL_CAP cannot happen (the host queues this
@@ -1013,6 +1033,24 @@ __global__ void __launch_bounds__(TL_THREADS, 1) x3_rank_tail_kernel(RankArgs a,
 	}
 }
 
+/* kernel launch behind another kernel of the same stream with programmatic dependent launch */
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, bool pdl,
+                       Args... args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3((unsigned)grid);
+	cfg.blockDim = dim3((unsigned)block);
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr;
+	cfg.numAttrs = pdl ? 1 : 0;
+	return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 /* ---- per-device scratch ------------------------------------------------------------------ */
 struct RankScratch {
 	uint32_t cap = 0; /* elements */
@@ -1137,6 +1175,9 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 	const bool trace = getenv("X3_TRACE") != nullptr;
 	const bool profile = getenv("X3_RANK_PROFILE") != nullptr;
 	const bool no_tail = getenv("X3_RANK_NO_TAIL") != nullptr; /* testing knob: never changes results */
+	/* programmatic dependent launch between the kernels of a chunk; the profile mode's events would
+	 * sit between the kernels, so it keeps plain launches */
+	const bool pdl = getenv("X3_RANK_NO_PDL") == nullptr && !profile;
 	const uint32_t D = prm.D;
 	const unsigned long long CH = (unsigned long long)((RANK_MAX_M - D) & ~4095u);
 	const unsigned long long first = prm.n < CH ? prm.n : CH;
@@ -1204,7 +1245,8 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 		mark(2, 1, 0);
 		x3_rank_bytehist_kernel<<<grid_for((a.M + 65535) / 65536), 256, 0, stream>>>(a);
 		mark(0, 1, 0);
-		x3_rank_radix_kernel<true><<<grid_for(rs_tiles), RS_THREADS, 0, stream>>>(a, 1, 0, ticket, (uint32_t)ticket + 1u);
+		if ((e = launch_pdl(x3_rank_radix_kernel<true>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 1, 0, ticket,
+		                    (uint32_t)ticket + 1u)) != cudaSuccess) return e;
 		++ticket;
 		nl += 2;
 		uint32_t known = a.M; /* upper bound of the size of the level about to be queued */
@@ -1233,7 +1275,7 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 				if (known <= (uint32_t)TL_CAP && !no_tail) {
 					/* small enough for one CTA: every remaining level in one launch */
 					mark(1, L, 0);
-					x3_rank_tail_kernel<<<1, TL_THREADS, TL_SMEM, stream>>>(a, L);
+					if ((e = launch_pdl(x3_rank_tail_kernel, 1, TL_THREADS, TL_SMEM, stream, pdl, a, L)) != cudaSuccess) return e;
 					++nl;
 					break;
 				}
@@ -1241,14 +1283,15 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 			mark(1, L, 0);
 			const int lgrid = grid_for((known + LV_TILE - 1) / LV_TILE);
 			if (L == 1) {
-				x3_rank_level_kernel<1><<<lgrid, LV_THREADS, 0, stream>>>(a, L, ticket);
+				e = launch_pdl(x3_rank_level_kernel<1>, lgrid, LV_THREADS, 0, stream, pdl, a, L, ticket);
 			} else if (L == 2) {
-				x3_rank_level_kernel<2><<<lgrid, LV_THREADS, 0, stream>>>(a, L, ticket);
+				e = launch_pdl(x3_rank_level_kernel<2>, lgrid, LV_THREADS, 0, stream, pdl, a, L, ticket);
 			} else if (L == 3) {
-				x3_rank_level_kernel<3><<<lgrid, LV_THREADS, 0, stream>>>(a, L, ticket);
+				e = launch_pdl(x3_rank_level_kernel<3>, lgrid, LV_THREADS, 0, stream, pdl, a, L, ticket);
 			} else {
-				x3_rank_level_kernel<4><<<lgrid, LV_THREADS, 0, stream>>>(a, L, ticket);
+				e = launch_pdl(x3_rank_level_kernel<4>, lgrid, LV_THREADS, 0, stream, pdl, a, L, ticket);
 			}
+			if (e != cudaSuccess) return e;
 			++ticket;
 			++nl;
 			if (L == 32) {
@@ -1260,8 +1303,8 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 			const int np = radix_passes(rbound);
 			for (int pass = 0; pass < np; ++pass) {
 				mark(0, L + 1, pass);
-				x3_rank_radix_kernel<false><<<grid_for((known + RS_TILE - 1) / RS_TILE), RS_THREADS, 0, stream>>>(
-				    a, L + 1, pass, ticket, (uint32_t)ticket + 1u);
+				if ((e = launch_pdl(x3_rank_radix_kernel<false>, grid_for((known + RS_TILE - 1) / RS_TILE), RS_THREADS, 0, stream,
+				                    pdl, a, L + 1, pass, ticket, (uint32_t)ticket + 1u)) != cudaSuccess) return e;
 				++ticket;
 				++nl;
 			}
