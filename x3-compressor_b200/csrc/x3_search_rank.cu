@@ -419,8 +419,8 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 	 * first byte gather happens at level 4, when the arrays are small. */
 	constexpr bool FIRST = LK == 1;
 	constexpr uint32_t KM = LK == 1 ? 0xffu : (LK == 2 ? 0xffffu : (LK == 3 ? 0xffffffu : 0xffffffffu));
-	__shared__ __align__(16) uint32_t sk[LV_TILE + 256];
-	__shared__ __align__(16) uint32_t sp[LV_TILE + 256];
+	__shared__ __align__(16) uint32_t sk[LV_TILE + 256 + 8]; /* + look-ahead (<= 255) + the rare walk's read-ahead */
+	__shared__ __align__(16) uint32_t sp[LV_TILE + 256 + 8];
 	__shared__ uint32_t hist[4][256];
 	__shared__ uint32_t actbits[LV_TILE / 32];
 	__shared__ unsigned long long ws[LV_THREADS / 32 + 1];
@@ -527,24 +527,31 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 					const uint32_t room = m - 1u - (base + idx);
 					const uint32_t lim = room < (uint32_t)a.t ? room : (uint32_t)a.t;
 					uint32_t best = 32, c1 = 0;
-					for (uint32_t j = 1; j <= lim; ++j) {
-						const uint32_t kf = sk[idx + j];
-						if (((kf ^ kk) & 255u) != 0u) {
-							break;
+					bool done = false;
+					for (uint32_t j = 1; j <= lim && !done; j += 4) {
+						/* four followers per round: their shared-memory loads are independent */
+						uint32_t kf[4], q[4];
+#pragma unroll
+						for (int u = 0; u < 4; ++u) {
+							kf[u] = sk[idx + j + u];
+							q[u] = sp[idx + j + u];
 						}
-						const uint32_t q = sp[idx + j];
-						if (q - pp > D) {
-							break;
-						}
-						++c1;
-						const uint32_t df = kf ^ kk;
-						uint32_t l = df != 0u ? (uint32_t)(__ffs((int)df) - 1) >> 3 : 4u;
-						if (l == 4u) {
-							while (l < best && a.x[pp + l] == a.x[q + l]) {
-								++l;
+#pragma unroll
+						for (int u = 0; u < 4; ++u) {
+							if (done || j + u > lim || ((kf[u] ^ kk) & 255u) != 0u || q[u] - pp > D) {
+								done = true;
+							} else {
+								++c1;
+								const uint32_t df = kf[u] ^ kk;
+								uint32_t l = df != 0u ? (uint32_t)(__ffs((int)df) - 1) >> 3 : 4u;
+								if (l == 4u) {
+									while (l < best && a.x[pp + l] == a.x[q[u] + l]) {
+										++l;
+									}
+								}
+								best = min(best, l);
 							}
 						}
-						best = min(best, l);
 					}
 					a.lstar[pp] = (uint8_t)(c1 >= 2 ? best : 0u);
 				}
