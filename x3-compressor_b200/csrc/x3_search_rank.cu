@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(256) x3_rank_bytehist_kernel(RankArgs a)
  * A tile is ranked with warp-level digit matching, put in digit order in shared memory while
  * the chained per-digit prefix of the tiles in front resolves, then copied out in runs. */
 template <bool INIT>
-__global__ void __launch_bounds__(RS_THREADS, 4) x3_rank_radix_kernel(RankArgs a, int level, int pass, int ticket,
+__global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a, int level, int pass, int ticket,
                                                                        uint32_t epoch)
 {
 	__shared__ uint32_t gbase[256];
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(RS_THREADS, 4) x3_rank_radix_kernel(RankArgs a
 			break;
 		}
 		const uint32_t base = tile * RS_TILE + warp * (32 * RS_ITEMS);
-		uint32_t key[RS_ITEMS], pos[RS_ITEMS], off[RS_ITEMS];
+		uint32_t key[RS_ITEMS], off[RS_ITEMS];
 #pragma unroll
 		for (int k = 0; k < RS_ITEMS; ++k) {
 			const uint32_t i = base + 32 * k + lane;
@@ -310,10 +310,8 @@ __global__ void __launch_bounds__(RS_THREADS, 4) x3_rank_radix_kernel(RankArgs a
 				 * level-1 kernel needs no gathers */
 				const uint32_t *xw = reinterpret_cast<const uint32_t *>(a.x) + (i >> 2);
 				key[k] = valid ? __funnelshift_r(__ldg(xw), __ldg(xw + 1), 8 * (i & 3)) : 0u;
-				pos[k] = i;
 			} else {
 				key[k] = valid ? keyIn[i] : 0u;
-				pos[k] = valid ? posIn[i] : 0u;
 			}
 		}
 #pragma unroll
@@ -371,7 +369,7 @@ __global__ void __launch_bounds__(RS_THREADS, 4) x3_rank_radix_kernel(RankArgs a
 				const uint32_t d = off[k] >> 16;
 				const uint32_t idx = lbase[d] + wcnt[warp][d] + (off[k] & 0xffffu);
 				skey[idx] = key[k];
-				spos[idx] = pos[k];
+				spos[idx] = INIT ? base + 32 * k + lane : posIn[base + 32 * k + lane];
 			}
 		}
 		/* chained prefix of digit tid over the tiles in front */
