@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 	__shared__ __align__(16) uint32_t sk[LV_TILE + 256 + 8]; /* + look-ahead (<= 255) + the rare walk's read-ahead */
 	__shared__ __align__(16) uint32_t sp[LV_TILE + 256 + 8];
 	__shared__ uint32_t hist[4][256];
-	__shared__ uint32_t actbits[LV_TILE / 32];
+	__shared__ uint32_t actbits[LV_TILE / 32], rarebits[LV_TILE / 32];
 	__shared__ unsigned long long ws[LV_THREADS / 32 + 1];
 	__shared__ int wsi[LV_THREADS / 32];
 	__shared__ uint32_t s_tile;
@@ -518,40 +518,11 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 			bool pass;
 			if (FIRST) {
 				pass = valid && out && base + idx + la < m && ((sk[idx + la] ^ kk) & 255u) == 0u && sp[idx + la] - pp <= D;
-				if (valid && out && !pass) {
-					/* the byte has c1 <= t followers within D: tc* = c1 - 1, so Lstar = #{L : count_L >= c1}
-					 * = the smallest LCP32 over those followers, 0 when c1 < 2 (backend.c:76-78 collapsed).
-					 * The first 4 bytes of every follower sit in its key. */
-					const uint32_t room = m - 1u - (base + idx);
-					const uint32_t lim = room < (uint32_t)a.t ? room : (uint32_t)a.t;
-					uint32_t best = 32, c1 = 0;
-					bool done = false;
-					for (uint32_t j = 1; j <= lim && !done; j += 4) {
-						/* four followers per round: their shared-memory loads are independent */
-						uint32_t kf[4], q[4];
-#pragma unroll
-						for (int u = 0; u < 4; ++u) {
-							kf[u] = sk[idx + j + u];
-							q[u] = sp[idx + j + u];
-						}
-#pragma unroll
-						for (int u = 0; u < 4; ++u) {
-							if (done || j + u > lim || ((kf[u] ^ kk) & 255u) != 0u || q[u] - pp > D) {
-								done = true;
-							} else {
-								++c1;
-								const uint32_t df = kf[u] ^ kk;
-								uint32_t l = df != 0u ? (uint32_t)(__ffs((int)df) - 1) >> 3 : 4u;
-								if (l == 4u) {
-									while (l < best && a.x[pp + l] == a.x[q[u] + l]) {
-										++l;
-									}
-								}
-								best = min(best, l);
-							}
-						}
-					}
-					a.lstar[pp] = (uint8_t)(c1 >= 2 ? best : 0u);
+				/* elements that do not pass are settled by the rare walk below, after the tile's counts
+				 * are out (it only writes Lstar, and its length varies a lot from tile to tile) */
+				const uint32_t rm = __ballot_sync(FULL_MASK, valid && out && !pass);
+				if (lane == 0) {
+					rarebits[e * (LV_THREADS / 32) + warp] = rm;
 				}
 			} else {
 				/* masked compare: no sentinel value exists, so the array bound is checked */
@@ -637,6 +608,51 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 		if (tid == 0) {
 			/* the tile's own counts are out at once for the tiles behind */
 			st_status(a.st_level + tile, ep | ((tile == 0 ? ST_INC : ST_AGG) << 48) | pk);
+		}
+		if (FIRST) {
+			/* The rare walk: an element that did not pass has c1 <= t followers with its byte within D:
+			 * tc* = c1 - 1, so Lstar = #{L : count_L >= c1} = the smallest LCP32 over those followers,
+			 * 0 when c1 < 2 (backend.c:76-78 collapsed).  The first 4 bytes of every follower sit in
+			 * its key.  The tiles behind are not waiting for this: the counts are already published. */
+#pragma unroll 1
+			for (int e = 0; e < LV_ITEMS; ++e) {
+				if (((rarebits[e * (LV_THREADS / 32) + warp] >> lane) & 1u) == 0u) {
+					continue;
+				}
+				const uint32_t idx = e * LV_THREADS + tid;
+				const uint32_t kk = sk[idx], pp = sp[idx];
+				const uint32_t room = m - 1u - (base + idx);
+				const uint32_t lim = room < (uint32_t)a.t ? room : (uint32_t)a.t;
+				uint32_t best = 32, c1 = 0;
+				bool done = false;
+				for (uint32_t j = 1; j <= lim && !done; j += 4) {
+					/* four followers per round: their shared-memory loads are independent */
+					uint32_t kf[4], q[4];
+#pragma unroll
+					for (int u = 0; u < 4; ++u) {
+						kf[u] = sk[idx + j + u];
+						q[u] = sp[idx + j + u];
+					}
+#pragma unroll
+					for (int u = 0; u < 4; ++u) {
+						if (done || j + u > lim || ((kf[u] ^ kk) & 255u) != 0u || q[u] - pp > D) {
+							done = true;
+						} else {
+							++c1;
+							const uint32_t df = kf[u] ^ kk;
+							uint32_t l = df != 0u ? (uint32_t)(__ffs((int)df) - 1) >> 3 : 4u;
+							if (l == 4u) {
+								while (l < best && a.x[pp + l] == a.x[q[u] + l]) {
+									++l;
+								}
+							}
+							best = min(best, l);
+						}
+					}
+				}
+				a.lstar[pp] = (uint8_t)(c1 >= 2 ? best : 0u);
+			}
+			__syncthreads(); /* the staging below reuses sk / sp */
 		}
 		/* the kept elements, compacted in tile order into the (now free) staging arrays; keys carry
 		 * the tile-local group rank until the prefix over the tiles in front is known */
