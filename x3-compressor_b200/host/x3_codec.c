@@ -341,11 +341,57 @@ static size_t parse_step(struct x3_codec *c, uint8_t *p, uint8_t *ptr, uint8_t *
 
 struct ring {
 	struct step_rec *rec;
+	uint64_t mask; /* RING_SIZE - 1, or all ones when rec holds every record (stage timing aid) */
 	_Atomic uint64_t head; /* records published by the parser */
 	_Atomic uint64_t tail; /* records consumed by the coder */
 	_Atomic int done;
 	struct coder_state *cs;
 };
+
+/*
+ * Lookahead of the coder: the records behind the one being coded are already in the ring, and what
+ * a tag event will look up is a function of the records alone (context1 = the previous hit's tag).
+ * Two stages of cache hints run ahead of code_step(); they never change what is coded.
+ *   far  (2 LOOK steps ahead): the pair-map slot of (context1, tag) and the line of ctx1[context1]
+ *   near (LOOK steps ahead):   the pair's id if it is registered already -> the line of ctx0[id];
+ *                              the item tables behind ctx1[context1]
+ */
+#define LOOK 6u
+
+static inline uint32_t rec_context1(const struct ring *rg, uint64_t j)
+{
+	if (j == 0) {
+		return 0;
+	}
+	const struct step_rec *pr = &rg->rec[(j - 1) & rg->mask];
+	return (pr->b & REC_HIT) ? pr->a : 0u; /* x3.c:389-390,423-424 */
+}
+
+static inline void look_far(const struct ring *rg, uint64_t j)
+{
+	const struct step_rec *r = &rg->rec[j & rg->mask];
+	if (r->b & REC_HIT) {
+		const struct x3_codec *c = rg->cs->c;
+		const uint32_t context1 = rec_context1(rg, j);
+		x3_pairmap_prefetch(c->pairs, context1, r->a);
+		x3_ctx_prefetch(c->ctx1, context1, r->a, 0);
+	}
+}
+
+static inline void look_near(const struct ring *rg, uint64_t j)
+{
+	const struct step_rec *r = &rg->rec[j & rg->mask];
+	if (r->b & REC_HIT) {
+		const struct x3_codec *c = rg->cs->c;
+		const uint32_t context1 = rec_context1(rg, j);
+		x3_ctx_prefetch(c->ctx1, context1, r->a, 1);
+		/* the pair this event registers is the NEXT tag event's ctx0 id */
+		const int64_t id = x3_pairmap_query(c->pairs, context1, r->a);
+		if (id >= 0) {
+			x3_ctx_prefetch(c->ctx0, (uint32_t)id, 0, 0);
+		}
+	}
+}
 
 static void *coder_thread(void *arg)
 {
@@ -365,6 +411,12 @@ static void *coder_thread(void *arg)
 			}
 		}
 		for (; tail < head; ++tail) {
+			if (tail + 2 * LOOK < head) {
+				look_far(rg, tail + 2 * LOOK);
+			}
+			if (tail + LOOK < head) {
+				look_near(rg, tail + LOOK);
+			}
 			code_step(rg->cs, &rg->rec[tail & (RING_SIZE - 1)]);
 		}
 		atomic_store_explicit(&rg->tail, tail, memory_order_release);
@@ -395,7 +447,18 @@ void *x3_compress(struct x3_codec *c, char *base, size_t isize, x3_fbm_fn fbm, s
 			p += parse_step(c, p, ptr, end, fbm, &all[nrec++]);
 		}
 		clock_gettime(CLOCK_MONOTONIC, &t1);
+		struct ring lin;
+		lin.rec = all;
+		lin.mask = ~(uint64_t)0;
+		lin.cs = &cs;
+		const int look = getenv("X3_NO_LOOKAHEAD") == NULL;
 		for (size_t i = 0; i < nrec; ++i) {
+			if (look && i + 2 * LOOK < nrec) {
+				look_far(&lin, i + 2 * LOOK);
+			}
+			if (look && i + LOOK < nrec) {
+				look_near(&lin, i + LOOK);
+			}
 			code_step(&cs, &all[i]);
 		}
 		clock_gettime(CLOCK_MONOTONIC, &t2);
@@ -415,6 +478,7 @@ void *x3_compress(struct x3_codec *c, char *base, size_t isize, x3_fbm_fn fbm, s
 		if (rg.rec == NULL) {
 			abort();
 		}
+		rg.mask = RING_SIZE - 1;
 		atomic_init(&rg.head, 0);
 		atomic_init(&rg.tail, 0);
 		atomic_init(&rg.done, 0);

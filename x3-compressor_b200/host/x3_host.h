@@ -103,6 +103,9 @@ struct x3_ctxset *x3_ctxset_create(void);
 void x3_ctxset_destroy(struct x3_ctxset *s);
 struct x3_ctx *x3_ctxset_get(struct x3_ctxset *s, uint32_t id); /* grows on demand (ctx_enlarge) */
 int64_t x3_ctx_find(struct x3_ctxset *s, uint32_t id, uint32_t tag); /* item index or -1 (context.c:20-40) */
+/* cache hints for a lookup a few steps ahead: the context's line (with_items = 0), then what a
+ * lookup of `tag` in it will touch (with_items = 1, once the line has arrived) */
+void x3_ctx_prefetch(const struct x3_ctxset *s, uint32_t id, uint32_t tag, int with_items);
 void x3_ctx_add(struct x3_ctxset *s, uint32_t id, uint32_t tag);     /* ctx_add_tag, context.c:42-56 */
 void x3_ctx_inc(struct x3_ctxset *s, uint32_t id, uint32_t item);    /* ctx_item_inc_freq, context.c:88-93 */
 uint64_t x3_ctx_cum(const struct x3_ctx *c, uint32_t item);
@@ -114,6 +117,7 @@ struct x3_pairmap *x3_pairmap_create(void);
 void x3_pairmap_destroy(struct x3_pairmap *m);
 int64_t x3_pairmap_query(const struct x3_pairmap *m, uint32_t t0, uint32_t t1); /* -1 if absent */
 uint32_t x3_pairmap_add(struct x3_pairmap *m, uint32_t t0, uint32_t t1);
+void x3_pairmap_prefetch(const struct x3_pairmap *m, uint32_t t0, uint32_t t1);
 uint32_t x3_pairmap_elems(const struct x3_pairmap *m);
 
 /* ---- dictionary: reference dict.c --------------------------------------------------

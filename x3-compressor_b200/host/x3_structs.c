@@ -402,6 +402,14 @@ static inline int64_t hmap_get(const struct hmap *h, uint64_t key)
 	}
 }
 
+/* cache hints for a lookup that will happen a few steps from now */
+static inline void hmap_prefetch(const struct hmap *h, uint64_t key)
+{
+	const uint64_t i = mix64(key) & h->mask;
+	__builtin_prefetch(&h->key[i], 0, 1);
+	__builtin_prefetch(&h->val[i], 0, 1);
+}
+
 static void hmap_put_nogrow(struct hmap *h, uint64_t key, uint32_t val)
 {
 	const uint64_t k1 = key + 1;
@@ -496,6 +504,26 @@ struct x3_ctx *x3_ctxset_get(struct x3_ctxset *s, uint32_t id)
 		s->size = ns;
 	}
 	return &s->arr[id];
+}
+
+void x3_ctx_prefetch(const struct x3_ctxset *s, uint32_t id, uint32_t tag, int with_items)
+{
+	if (id >= s->size) {
+		return;
+	}
+	const struct x3_ctx *c = &s->arr[id];
+	if (!with_items) {
+		__builtin_prefetch(c, 1, 1);
+		return;
+	}
+	/* the context's line is (being) fetched: reach for what find / cum / inc will touch behind it */
+	if (c->items > CTX_LINEAR) {
+		hmap_prefetch(&s->map, ((uint64_t)id << 32) | tag);
+	}
+	if (c->cap) {
+		__builtin_prefetch(c->u.big.tag, 0, 1);
+		__builtin_prefetch(c->u.big.freq, 1, 1);
+	}
 }
 
 int64_t x3_ctx_find(struct x3_ctxset *s, uint32_t id, uint32_t tag)
@@ -634,6 +662,11 @@ void x3_pairmap_destroy(struct x3_pairmap *m)
 int64_t x3_pairmap_query(const struct x3_pairmap *m, uint32_t t0, uint32_t t1)
 {
 	return hmap_get(&m->map, ((uint64_t)t0 << 32) | t1);
+}
+
+void x3_pairmap_prefetch(const struct x3_pairmap *m, uint32_t t0, uint32_t t1)
+{
+	hmap_prefetch(&m->map, ((uint64_t)t0 << 32) | t1);
 }
 
 uint32_t x3_pairmap_add(struct x3_pairmap *m, uint32_t t0, uint32_t t1)
