@@ -28,10 +28,12 @@ def lcp32(x: np.ndarray, a: int, b: int) -> int:
     return k
 
 
-def lstar_rank(x: np.ndarray, n: int, W: int, t: int, tile: int | None = None, stats: list | None = None) -> np.ndarray:
+def lstar_rank(x: np.ndarray, n: int, W: int, t: int, tile: int | None = None, stats: list | None = None,
+               direct_level2: bool = False) -> np.ndarray:
     """x: padded input (n data bytes, then at least W zero bytes).  tile: when given, the
     participant rule is evaluated the way the kernel does it (exact inside a tile of `tile`
-    consecutive array entries, conservative at the tile start)."""
+    consecutive array entries, conservative at the tile start).  direct_level2: level 2 keeps
+    every element (the kernels sort level 2 from x instead of pruning after level 1)."""
     ls = np.zeros(n, dtype=np.uint8)
     D = W - 33 if W > 33 else 0
     if t <= 0 or D == 0 or n == 0:
@@ -68,7 +70,9 @@ def lstar_rank(x: np.ndarray, n: int, W: int, t: int, tile: int | None = None, s
         if L == 32 or not act.any():
             break
         # participants of level L+1: within D behind an element that passed (same L-gram)
-        if tile is None:
+        if direct_level2 and L == 1:
+            part = np.ones(m, dtype=bool)
+        elif tile is None:
             last = np.maximum.accumulate(np.where(act, i, -1))
             lc = np.maximum(last, 0)
             part = (last >= 0) & (key[lc] == key) & (pos - pos[lc] <= D)

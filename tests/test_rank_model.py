@@ -35,3 +35,5 @@ def test_rank_model_equals_oracle(corpus, kind, n, W, t):
     assert np.array_equal(lstar_rank(x, len(a), W, t), ref)
     # the kernel's tile-local participant rule (a superset) gives the same table
     assert np.array_equal(lstar_rank(x, len(a), W, t, tile=64), ref)
+    # ... and so does keeping every element for level 2 (the kernels sort level 2 from x)
+    assert np.array_equal(lstar_rank(x, len(a), W, t, tile=64, direct_level2=True), ref)

@@ -219,23 +219,36 @@ __global__ void __launch_bounds__(256) x3_rank_bytehist_kernel(RankArgs a)
 			atomicAdd(&h[a.x[i]], 1u);
 		}
 		if (threadIdx.x == 0) {
+			/* level 1: all M positions by their byte; its one pass lands in buffer 0 */
 			a.ctrl->lv[1].m = a.M;
 			a.ctrl->lv[1].groups = 1;
-			a.ctrl->lv[1].src0 = 1; /* the one level-1 pass lands in buffer 0 */
+			a.ctrl->lv[1].src0 = 1;
 			a.ctrl->lv[1].buf = 0;
+			/* level 2: all M positions again, sorted from scratch by (b0, b1): the first pass (digit b1)
+			 * reads x and lands in buffer 1, the second (digit b0) sorts it into buffer 0 */
+			a.ctrl->lv[2].m = a.M;
+			a.ctrl->lv[2].groups = 256;
+			a.ctrl->lv[2].src0 = 0;
+			a.ctrl->lv[2].buf = 0;
+			/* the b1 digits are the bytes x[1 .. M]: the same histogram, one byte out, one byte in */
+			atomicAdd(&a.ctrl->hist[2][0][a.x[a.M]], 1u);
+			atomicSub(&a.ctrl->hist[2][0][a.x[0]], 1u);
 		}
 	}
 	__syncthreads();
 	if (h[threadIdx.x] != 0) {
 		atomicAdd(&a.ctrl->hist[1][0][threadIdx.x], h[threadIdx.x]);
+		atomicAdd(&a.ctrl->hist[2][0][threadIdx.x], h[threadIdx.x]);
+		atomicAdd(&a.ctrl->hist[2][1][threadIdx.x], h[threadIdx.x]);
 	}
 }
 
 /* ---- one stable 8-bit radix pass -------------------------------------------------------
- * INIT: the elements are the positions 0 .. M-1 themselves, key = 4 bytes of x (level 1).
+ * INIT 1 / 2: the elements are the positions 0 .. M-1 themselves, the key is made of the 4 bytes
+ * x[p..p+3] (level 1: sorted by b0; level 2: first of the two passes that sort by (b0, b1)).
  * A tile is ranked with warp-level digit matching, put in digit order in shared memory while
  * the chained per-digit prefix of the tiles in front resolves, then copied out in runs. */
-template <bool INIT>
+template <int INIT>
 __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a, int level, int pass, int ticket,
                                                                        uint32_t epoch)
 {
@@ -254,7 +267,7 @@ __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a
 	if (!INIT && (m < (uint32_t)a.t + 2u || pass >= radix_passes(a.ctrl->lv[level].groups))) {
 		return; /* nobody can pass this level any more / the keys have no such digit */
 	}
-	const uint32_t src = INIT ? 1u : a.ctrl->lv[level].src0 ^ (uint32_t)(pass & 1);
+	const uint32_t src = INIT == 1 ? 1u : (INIT == 2 ? 0u : a.ctrl->lv[level].src0 ^ (uint32_t)(pass & 1));
 	const uint32_t *__restrict__ keyIn = src ? a.key1 : a.key0;
 	const uint32_t *__restrict__ posIn = src ? a.pos1 : a.pos0;
 	uint32_t *__restrict__ keyOut = src ? a.key0 : a.key1;
@@ -309,7 +322,9 @@ __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a
 				/* level-1 key: the byte (the sort digit) with its three successors on top, so that the
 				 * level-1 kernel needs no gathers */
 				const uint32_t *xw = reinterpret_cast<const uint32_t *>(a.x) + (i >> 2);
-				key[k] = valid ? __funnelshift_r(__ldg(xw), __ldg(xw + 1), 8 * (i & 3)) : 0u;
+				const uint32_t w4 = valid ? __funnelshift_r(__ldg(xw), __ldg(xw + 1), 8 * (i & 3)) : 0u;
+				/* level 1: b3 b2 b1 | b0.  level 2: b3 b2 | b0 b1 (sorted by b1 here, by b0 in the next pass) */
+				key[k] = INIT == 1 ? w4 : (w4 & 0xffff0000u) | ((w4 & 255u) << 8) | ((w4 >> 8) & 255u);
 			} else {
 				key[k] = valid ? keyIn[i] : 0u;
 			}
@@ -404,6 +419,96 @@ __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a
 	}
 }
 
+/* ---- level 1: the first byte ----------------------------------------------------------------
+ * Reads the positions sorted by their byte (buffer 0).  A position passes level 1 when the
+ * (t+1)-th next position with its byte lies within D; Lstar of every searched position was
+ * preset to 1, deeper levels raise it.  A position that does NOT pass has c1 <= t followers
+ * within D: tc* = c1 - 1, so Lstar = #{L : count_L >= c1} = the smallest LCP32 over those
+ * followers, 0 when c1 < 2 (backend.c:76-78 collapsed) -- settled here by walking them; the first
+ * 4 bytes of every follower sit in its key.  Nothing is handed on: level 2 is sorted from x. */
+__global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_first_kernel(RankArgs a)
+{
+	__shared__ __align__(16) uint32_t sk[LV_TILE + 256 + 8]; /* + look-ahead (<= 255) + the walk's read-ahead */
+	__shared__ __align__(16) uint32_t sp[LV_TILE + 256 + 8];
+	const int tid = threadIdx.x;
+	pdl_wait();
+	pdl_launch_dependents();
+	const uint32_t m = a.M;
+	const uint32_t ntiles = (m + LV_TILE - 1) / LV_TILE;
+	const uint32_t D = a.D, n_out = a.n_out;
+	const uint32_t la = (uint32_t)a.t + 1u;
+	const uint32_t *__restrict__ keyIn = a.key0;
+	const uint32_t *__restrict__ posIn = a.pos0;
+	for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		const uint32_t base = tile * LV_TILE;
+		const uint32_t i0 = base + tid * LV_ITEMS;
+		if (i0 + LV_ITEMS <= m) {
+			*reinterpret_cast<uint4 *>(sk + tid * LV_ITEMS) = *reinterpret_cast<const uint4 *>(keyIn + i0);
+			*reinterpret_cast<uint4 *>(sk + tid * LV_ITEMS + 4) = *reinterpret_cast<const uint4 *>(keyIn + i0 + 4);
+			*reinterpret_cast<uint4 *>(sp + tid * LV_ITEMS) = *reinterpret_cast<const uint4 *>(posIn + i0);
+			*reinterpret_cast<uint4 *>(sp + tid * LV_ITEMS + 4) = *reinterpret_cast<const uint4 *>(posIn + i0 + 4);
+		} else {
+#pragma unroll
+			for (int e = 0; e < LV_ITEMS; ++e) {
+				const bool v = i0 + e < m;
+				sk[tid * LV_ITEMS + e] = v ? keyIn[i0 + e] : 0u;
+				sp[tid * LV_ITEMS + e] = v ? posIn[i0 + e] : 0u;
+			}
+		}
+		if ((uint32_t)tid < la) {
+			const uint32_t i = base + LV_TILE + tid;
+			sk[LV_TILE + tid] = i < m ? keyIn[i] : 0u;
+			sp[LV_TILE + tid] = i < m ? posIn[i] : 0u;
+		}
+		__syncthreads();
+#pragma unroll 1
+		for (int e = 0; e < LV_ITEMS; ++e) {
+			const uint32_t idx = e * LV_THREADS + tid;
+			if (base + idx >= m) {
+				break;
+			}
+			const uint32_t kk = sk[idx], pp = sp[idx];
+			if (pp >= n_out) {
+				continue; /* the positions behind the searched range are followers only */
+			}
+			if (base + idx + la < m && ((sk[idx + la] ^ kk) & 255u) == 0u && sp[idx + la] - pp <= D) {
+				continue; /* passes: Lstar >= 1 */
+			}
+			const uint32_t room = m - 1u - (base + idx);
+			const uint32_t lim = room < (uint32_t)a.t ? room : (uint32_t)a.t;
+			uint32_t best = 32, c1 = 0;
+			bool done = false;
+			for (uint32_t j = 1; j <= lim && !done; j += 4) {
+				/* four followers per round: their shared-memory loads are independent */
+				uint32_t kf[4], q[4];
+#pragma unroll
+				for (int u = 0; u < 4; ++u) {
+					kf[u] = sk[idx + j + u];
+					q[u] = sp[idx + j + u];
+				}
+#pragma unroll
+				for (int u = 0; u < 4; ++u) {
+					if (done || j + u > lim || ((kf[u] ^ kk) & 255u) != 0u || q[u] - pp > D) {
+						done = true;
+					} else {
+						++c1;
+						const uint32_t df = kf[u] ^ kk;
+						uint32_t l = df != 0u ? (uint32_t)(__ffs((int)df) - 1) >> 3 : 4u;
+						if (l == 4u) {
+							while (l < best && a.x[pp + l] == a.x[q[u] + l]) {
+								++l;
+							}
+						}
+						best = min(best, l);
+					}
+				}
+			}
+			a.lstar[pp] = (uint8_t)(c1 >= 2 ? best : 0u);
+		}
+		__syncthreads();
+	}
+}
+
 /* ---- one level: test, prune, re-key, compact ----------------------------------------------
  * Bit 31 of a position word says "this element passed the previous level": Lstar is written
  * once per position, at the level where it stops passing (or by the level-1 rare path, the
@@ -411,16 +516,15 @@ __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a
 template <int LK>
 __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a, int L, int ticket)
 {
-	/* LK = min(L, 4).  Keys of levels 1-3 carry the bytes behind the gram in their upper bits
-	 * (level 1: b3 b2 b1 | b0; level 2: b3 b2 | rank8 b1; level 3: b3 | rank16 b2), put there by the
-	 * position-ordered level-1 pass for free; the radix passes only sort the low `gram` bits, so the
-	 * first byte gather happens at level 4, when the arrays are small. */
-	constexpr bool FIRST = LK == 1;
-	constexpr uint32_t KM = LK == 1 ? 0xffu : (LK == 2 ? 0xffffu : (LK == 3 ? 0xffffffu : 0xffffffffu));
+	/* LK = min(L, 4), L >= 2.  Keys of levels 2 and 3 carry the bytes behind the gram in their upper
+	 * bits (level 2: b3 b2 | b0 b1; level 3: b3 | rank16 b2), put there by the position-ordered passes
+	 * that read x; the radix passes only sort the low `gram` bits, so the first byte gather happens at
+	 * level 4, when the arrays are small. */
+	constexpr uint32_t KM = LK == 2 ? 0xffffu : (LK == 3 ? 0xffffffu : 0xffffffffu);
 	__shared__ __align__(16) uint32_t sk[LV_TILE + 256 + 8]; /* + look-ahead (<= 255) + the rare walk's read-ahead */
 	__shared__ __align__(16) uint32_t sp[LV_TILE + 256 + 8];
 	__shared__ uint32_t hist[4][256];
-	__shared__ uint32_t actbits[LV_TILE / 32], rarebits[LV_TILE / 32];
+	__shared__ uint32_t actbits[LV_TILE / 32];
 	__shared__ unsigned long long ws[LV_THREADS / 32 + 1];
 	__shared__ int wsi[LV_THREADS / 32];
 	__shared__ uint32_t s_tile;
@@ -434,7 +538,7 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 	const uint32_t D = a.D, n_out = a.n_out;
 	const uint32_t la = (uint32_t)a.t + 1u; /* look-ahead of the test, <= 255 */
 	const bool emit = L < 32;
-	if (!FIRST && m < la + 1u) {
+	if (m < la + 1u) {
 		/* nobody can pass this level (the radix passes did not run either): whoever passed the
 		 * previous one keeps it, and the search is over */
 		if (blockIdx.x == 0) {
@@ -516,20 +620,10 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 			const bool valid = base + idx < m;
 			const bool out = pp < n_out;
 			bool pass;
-			if (FIRST) {
-				pass = valid && out && base + idx + la < m && ((sk[idx + la] ^ kk) & 255u) == 0u && sp[idx + la] - pp <= D;
-				/* elements that do not pass are settled by the rare walk below, after the tile's counts
-				 * are out (it only writes Lstar, and its length varies a lot from tile to tile) */
-				const uint32_t rm = __ballot_sync(FULL_MASK, valid && out && !pass);
-				if (lane == 0) {
-					rarebits[e * (LV_THREADS / 32) + warp] = rm;
-				}
-			} else {
-				/* masked compare: no sentinel value exists, so the array bound is checked */
-				pass = valid && out && base + idx + la < m && ((sk[idx + la] ^ kk) & KM) == 0u &&
-				       (sp[idx + la] & PMASK) - pp <= D;
-			}
-			if (!FIRST && (pw & PFLAG) && !pass) {
+			/* masked compare: no sentinel value exists, so the array bound is checked */
+			pass = valid && out && base + idx + la < m && ((sk[idx + la] ^ kk) & KM) == 0u &&
+			       (sp[idx + la] & PMASK) - pp <= D;
+			if ((pw & PFLAG) && !pass) {
 				a.lstar[pp] = (uint8_t)(L - 1); /* passed level L-1, stops here */
 			}
 			if (L == 32 && pass) {
@@ -592,8 +686,7 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 #pragma unroll
 		for (int e = 0; e < LV_ITEMS; ++e) {
 			if ((partm >> e) & 1u) {
-				const uint32_t by = LK == 1 ? (k[e] >> 8) & 255u
-				                  : LK == 2 ? (k[e] >> 16) & 255u
+				const uint32_t by = LK == 2 ? (k[e] >> 16) & 255u
 				                  : LK == 3 ? k[e] >> 24
 				                            : (uint32_t)__ldg(a.x + (p[e] & PMASK) + L);
 				nb[e >> 2] |= by << (8 * (e & 3));
@@ -609,51 +702,6 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 			/* the tile's own counts are out at once for the tiles behind */
 			st_status(a.st_level + tile, ep | ((tile == 0 ? ST_INC : ST_AGG) << 48) | pk);
 		}
-		if (FIRST) {
-			/* The rare walk: an element that did not pass has c1 <= t followers with its byte within D:
-			 * tc* = c1 - 1, so Lstar = #{L : count_L >= c1} = the smallest LCP32 over those followers,
-			 * 0 when c1 < 2 (backend.c:76-78 collapsed).  The first 4 bytes of every follower sit in
-			 * its key.  The tiles behind are not waiting for this: the counts are already published. */
-#pragma unroll 1
-			for (int e = 0; e < LV_ITEMS; ++e) {
-				if (((rarebits[e * (LV_THREADS / 32) + warp] >> lane) & 1u) == 0u) {
-					continue;
-				}
-				const uint32_t idx = e * LV_THREADS + tid;
-				const uint32_t kk = sk[idx], pp = sp[idx];
-				const uint32_t room = m - 1u - (base + idx);
-				const uint32_t lim = room < (uint32_t)a.t ? room : (uint32_t)a.t;
-				uint32_t best = 32, c1 = 0;
-				bool done = false;
-				for (uint32_t j = 1; j <= lim && !done; j += 4) {
-					/* four followers per round: their shared-memory loads are independent */
-					uint32_t kf[4], q[4];
-#pragma unroll
-					for (int u = 0; u < 4; ++u) {
-						kf[u] = sk[idx + j + u];
-						q[u] = sp[idx + j + u];
-					}
-#pragma unroll
-					for (int u = 0; u < 4; ++u) {
-						if (done || j + u > lim || ((kf[u] ^ kk) & 255u) != 0u || q[u] - pp > D) {
-							done = true;
-						} else {
-							++c1;
-							const uint32_t df = kf[u] ^ kk;
-							uint32_t l = df != 0u ? (uint32_t)(__ffs((int)df) - 1) >> 3 : 4u;
-							if (l == 4u) {
-								while (l < best && a.x[pp + l] == a.x[q[u] + l]) {
-									++l;
-								}
-							}
-							best = min(best, l);
-						}
-					}
-				}
-				a.lstar[pp] = (uint8_t)(c1 >= 2 ? best : 0u);
-			}
-			__syncthreads(); /* the staging below reuses sk / sp */
-		}
 		/* the kept elements, compacted in tile order into the (now free) staging arrays; keys carry
 		 * the tile-local group rank until the prefix over the tiles in front is known */
 		{
@@ -666,7 +714,7 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 					/* bytes still ahead stay on top of the new (rank, byte) gram.  Sums, not ORs: the local
 					 * rank is -1 for elements of a group that began in an earlier tile, and only becomes a
 					 * real rank (mod 2^32) once the tiles in front are added at copy-out */
-					const uint32_t upper = LK == 1 ? k[e] & 0xffff0000u : (LK == 2 ? k[e] & 0xff000000u : 0u);
+					const uint32_t upper = LK == 2 ? k[e] & 0xff000000u : 0u;
 					sk[lidx] = upper + ((hloc - 1u) << 8) + ((nb[e >> 2] >> (8 * (e & 3))) & 255u);
 					sp[lidx] = (p[e] & PMASK) | (((actm >> e) & 1u) ? PFLAG : 0u);
 					++lidx;
@@ -1263,16 +1311,37 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 			}
 		};
 
+		/* Lstar = 1 wherever level 1 passes and nothing deeper does; the level-1 kernel writes the rest */
+		if ((e = cudaMemsetAsync(a.lstar, 1, a.n_out, stream)) != cudaSuccess) return e;
 		mark(2, 1, 0);
 		x3_rank_bytehist_kernel<<<grid_for((a.M + 65535) / 65536), 256, 0, stream>>>(a);
+		/* level 1: positions by byte (buffer 0), tested and, where the byte is rare, settled */
 		mark(0, 1, 0);
-		if ((e = launch_pdl(x3_rank_radix_kernel<true>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 1, 0, ticket,
+		if ((e = launch_pdl(x3_rank_radix_kernel<1>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 1, 0, ticket,
 		                    (uint32_t)ticket + 1u)) != cudaSuccess) return e;
 		++ticket;
-		nl += 2;
+		mark(1, 1, 0);
+		if ((e = launch_pdl(x3_rank_first_kernel, grid_for(lv_tiles), LV_THREADS, 0, stream, pdl, a)) != cudaSuccess) return e;
+		/* level 2: sorted from x by (b0, b1): digit b1 into buffer 1, digit b0 back into buffer 0 */
+		mark(0, 2, 0);
+		if ((e = launch_pdl(x3_rank_radix_kernel<2>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 2, 0, ticket,
+		                    (uint32_t)ticket + 1u)) != cudaSuccess) return e;
+		++ticket;
+		mark(0, 2, 1);
+		if ((e = launch_pdl(x3_rank_radix_kernel<0>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 2, 1, ticket,
+		                    (uint32_t)ticket + 1u)) != cudaSuccess) return e;
+		++ticket;
+		nl += 5;
 		uint32_t known = a.M; /* upper bound of the size of the level about to be queued */
-		for (int L = 1; L <= 32; ++L) {
-			if (L >= 3) {
+		for (int L = 2; L <= 32; ++L) {
+			if (L == 2 && known <= (uint32_t)TL_CAP && !no_tail) {
+				/* a small input: every level from 2 on in one launch */
+				mark(1, L, 0);
+				if ((e = launch_pdl(x3_rank_tail_kernel, 1, TL_THREADS, TL_SMEM, stream, pdl, a, L)) != cudaSuccess) return e;
+				++nl;
+				break;
+			}
+			if (L >= 4) {
 				/* lv[L-1] as level L-2 left it: its size bounds level L, and tells whether level L-1
 				 * (already queued) was the last one */
 				volatile uint32_t *rep = s.h_back + 4 * (L - 2);
@@ -1303,9 +1372,7 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 			}
 			mark(1, L, 0);
 			const int lgrid = grid_for((known + LV_TILE - 1) / LV_TILE);
-			if (L == 1) {
-				e = launch_pdl(x3_rank_level_kernel<1>, lgrid, LV_THREADS, 0, stream, pdl, a, L, ticket);
-			} else if (L == 2) {
+			if (L == 2) {
 				e = launch_pdl(x3_rank_level_kernel<2>, lgrid, LV_THREADS, 0, stream, pdl, a, L, ticket);
 			} else if (L == 3) {
 				e = launch_pdl(x3_rank_level_kernel<3>, lgrid, LV_THREADS, 0, stream, pdl, a, L, ticket);
@@ -1324,7 +1391,7 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 			const int np = radix_passes(rbound);
 			for (int pass = 0; pass < np; ++pass) {
 				mark(0, L + 1, pass);
-				if ((e = launch_pdl(x3_rank_radix_kernel<false>, grid_for((known + RS_TILE - 1) / RS_TILE), RS_THREADS, 0, stream,
+				if ((e = launch_pdl(x3_rank_radix_kernel<0>, grid_for((known + RS_TILE - 1) / RS_TILE), RS_THREADS, 0, stream,
 				                    pdl, a, L + 1, pass, ticket, (uint32_t)ticket + 1u)) != cudaSuccess) return e;
 				++ticket;
 				++nl;
