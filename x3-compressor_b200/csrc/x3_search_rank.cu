@@ -193,7 +193,7 @@ __host__ __device__ __forceinline__ int radix_passes(uint32_t groups)
 	return (bits + 7) / 8;
 }
 
-/* ---- level 1 set-up: byte histogram of the M elements ---------------------------------- */
+/* ---- set-up: byte histogram of the M elements (both digits of the level-2 sort) ---------------------------------- */
 
 __global__ void __launch_bounds__(256) x3_rank_bytehist_kernel(RankArgs a)
 {
@@ -219,13 +219,9 @@ __global__ void __launch_bounds__(256) x3_rank_bytehist_kernel(RankArgs a)
 			atomicAdd(&h[a.x[i]], 1u);
 		}
 		if (threadIdx.x == 0) {
-			/* level 1: all M positions by their byte; its one pass lands in buffer 0 */
-			a.ctrl->lv[1].m = a.M;
-			a.ctrl->lv[1].groups = 1;
-			a.ctrl->lv[1].src0 = 1;
-			a.ctrl->lv[1].buf = 0;
-			/* level 2: all M positions again, sorted from scratch by (b0, b1): the first pass (digit b1)
-			 * reads x and lands in buffer 1, the second (digit b0) sorts it into buffer 0 */
+			/* level 2: all M positions, sorted from x by (b0, b1): the first pass (digit b1) reads x and
+			 * lands in buffer 1 (level 1 is tested on that array), the second (digit b0) sorts it into
+			 * buffer 0 */
 			a.ctrl->lv[2].m = a.M;
 			a.ctrl->lv[2].groups = 256;
 			a.ctrl->lv[2].src0 = 0;
@@ -237,18 +233,17 @@ __global__ void __launch_bounds__(256) x3_rank_bytehist_kernel(RankArgs a)
 	}
 	__syncthreads();
 	if (h[threadIdx.x] != 0) {
-		atomicAdd(&a.ctrl->hist[1][0][threadIdx.x], h[threadIdx.x]);
 		atomicAdd(&a.ctrl->hist[2][0][threadIdx.x], h[threadIdx.x]);
 		atomicAdd(&a.ctrl->hist[2][1][threadIdx.x], h[threadIdx.x]);
 	}
 }
 
 /* ---- one stable 8-bit radix pass -------------------------------------------------------
- * INIT 1 / 2: the elements are the positions 0 .. M-1 themselves, the key is made of the 4 bytes
- * x[p..p+3] (level 1: sorted by b0; level 2: first of the two passes that sort by (b0, b1)).
+ * INIT: the first of the two passes that sort level 2 by (b0, b1): the elements are the positions
+ * 0 .. M-1 themselves, the key is made of the 4 bytes x[p..p+3], the digit is b1 = x[p+1].
  * A tile is ranked with warp-level digit matching, put in digit order in shared memory while
  * the chained per-digit prefix of the tiles in front resolves, then copied out in runs. */
-template <int INIT>
+template <bool INIT>
 __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a, int level, int pass, int ticket,
                                                                        uint32_t epoch)
 {
@@ -267,7 +262,7 @@ __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a
 	if (!INIT && (m < (uint32_t)a.t + 2u || pass >= radix_passes(a.ctrl->lv[level].groups))) {
 		return; /* nobody can pass this level any more / the keys have no such digit */
 	}
-	const uint32_t src = INIT == 1 ? 1u : (INIT == 2 ? 0u : a.ctrl->lv[level].src0 ^ (uint32_t)(pass & 1));
+	const uint32_t src = INIT ? 0u : a.ctrl->lv[level].src0 ^ (uint32_t)(pass & 1);
 	const uint32_t *__restrict__ keyIn = src ? a.key1 : a.key0;
 	const uint32_t *__restrict__ posIn = src ? a.pos1 : a.pos0;
 	uint32_t *__restrict__ keyOut = src ? a.key0 : a.key1;
@@ -323,8 +318,8 @@ __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a
 				 * level-1 kernel needs no gathers */
 				const uint32_t *xw = reinterpret_cast<const uint32_t *>(a.x) + (i >> 2);
 				const uint32_t w4 = valid ? __funnelshift_r(__ldg(xw), __ldg(xw + 1), 8 * (i & 3)) : 0u;
-				/* level 1: b3 b2 b1 | b0.  level 2: b3 b2 | b0 b1 (sorted by b1 here, by b0 in the next pass) */
-				key[k] = INIT == 1 ? w4 : (w4 & 0xffff0000u) | ((w4 & 255u) << 8) | ((w4 >> 8) & 255u);
+				/* b3 b2 | b0 b1: sorted by b1 here, by b0 in the next pass */
+				key[k] = (w4 & 0xffff0000u) | ((w4 & 255u) << 8) | ((w4 >> 8) & 255u);
 			} else {
 				key[k] = valid ? keyIn[i] : 0u;
 			}
@@ -420,12 +415,14 @@ __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a
 }
 
 /* ---- level 1: the first byte ----------------------------------------------------------------
- * Reads the positions sorted by their byte (buffer 0).  A position passes level 1 when the
- * (t+1)-th next position with its byte lies within D; Lstar of every searched position was
- * preset to 1, deeper levels raise it.  A position that does NOT pass has c1 <= t followers
- * within D: tc* = c1 - 1, so Lstar = #{L : count_L >= c1} = the smallest LCP32 over those
- * followers, 0 when c1 < 2 (backend.c:76-78 collapsed) -- settled here by walking them; the first
- * 4 bytes of every follower sit in its key.  Nothing is handed on: level 2 is sorted from x. */
+ * No sort of its own: the first of the two level-2 passes leaves the positions p ordered by
+ * (x[p+1], p), which IS the level-1 order of the positions q = p + 1 (key: b3 b2 | b0 b1 with
+ * b1 = x[q], b2 b3 = the two bytes behind it).  A position passes level 1 when the (t+1)-th next
+ * position with its byte lies within D; Lstar of every searched position was preset to 1, deeper
+ * levels raise it.  A position that does NOT pass has c1 <= t followers within D: tc* = c1 - 1,
+ * so Lstar = #{L : count_L >= c1} = the smallest LCP32 over those followers, 0 when c1 < 2
+ * (backend.c:76-78 collapsed) -- settled here by walking them.  Position 0 has no element (p = -1):
+ * its followers are the head of its byte's group, found through the digit histogram. */
 __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_first_kernel(RankArgs a)
 {
 	__shared__ __align__(16) uint32_t sk[LV_TILE + 256 + 8]; /* + look-ahead (<= 255) + the walk's read-ahead */
@@ -437,8 +434,34 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_first_kernel(RankArgs a
 	const uint32_t ntiles = (m + LV_TILE - 1) / LV_TILE;
 	const uint32_t D = a.D, n_out = a.n_out;
 	const uint32_t la = (uint32_t)a.t + 1u;
-	const uint32_t *__restrict__ keyIn = a.key0;
-	const uint32_t *__restrict__ posIn = a.pos0;
+	const uint32_t *__restrict__ keyIn = a.key1; /* the output of x3_rank_radix_kernel<INIT> */
+	const uint32_t *__restrict__ posIn = a.pos1;
+	const uint8_t *__restrict__ x = a.x;
+	if (blockIdx.x == 0 && tid == 0) {
+		/* position 0 */
+		const uint32_t b = x[0];
+		uint32_t gs = 0;
+		for (uint32_t v = 0; v < b; ++v) {
+			gs += a.ctrl->hist[2][0][v];
+		}
+		const uint32_t size = a.ctrl->hist[2][0][b];
+		if (!(size > (uint32_t)a.t && posIn[gs + (uint32_t)a.t] + 1u <= D)) {
+			uint32_t best = 32, c1 = 0;
+			for (uint32_t i = 0; i < size && i < (uint32_t)a.t; ++i) {
+				const uint32_t q = posIn[gs + i] + 1u;
+				if (q > D) {
+					break;
+				}
+				++c1;
+				uint32_t l = 1;
+				while (l < best && x[l] == x[q + l]) {
+					++l;
+				}
+				best = l;
+			}
+			a.lstar[0] = (uint8_t)(c1 >= 2 ? best : 0u);
+		}
+	}
 	for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 		const uint32_t base = tile * LV_TILE;
 		const uint32_t i0 = base + tid * LV_ITEMS;
@@ -468,7 +491,8 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_first_kernel(RankArgs a
 				break;
 			}
 			const uint32_t kk = sk[idx], pp = sp[idx];
-			if (pp >= n_out) {
+			const uint32_t qq = pp + 1u; /* the position this element stands for at level 1 */
+			if (qq >= n_out) {
 				continue; /* the positions behind the searched range are followers only */
 			}
 			if (base + idx + la < m && ((sk[idx + la] ^ kk) & 255u) == 0u && sp[idx + la] - pp <= D) {
@@ -492,10 +516,11 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_first_kernel(RankArgs a
 						done = true;
 					} else {
 						++c1;
-						const uint32_t df = kf[u] ^ kk;
-						uint32_t l = df != 0u ? (uint32_t)(__ffs((int)df) - 1) >> 3 : 4u;
-						if (l == 4u) {
-							while (l < best && a.x[pp + l] == a.x[q[u] + l]) {
+						/* bytes 1 and 2 of both positions sit in the key's upper half */
+						const uint32_t df = (kf[u] ^ kk) >> 16;
+						uint32_t l = df != 0u ? 1u + ((uint32_t)(__ffs((int)df) - 1) >> 3) : 3u;
+						if (l == 3u) {
+							while (l < best && x[qq + l] == x[q[u] + 1u + l]) {
 								++l;
 							}
 						}
@@ -503,7 +528,7 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_first_kernel(RankArgs a
 					}
 				}
 			}
-			a.lstar[pp] = (uint8_t)(c1 >= 2 ? best : 0u);
+			a.lstar[qq] = (uint8_t)(c1 >= 2 ? best : 0u);
 		}
 		__syncthreads();
 	}
@@ -1315,23 +1340,20 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 		if ((e = cudaMemsetAsync(a.lstar, 1, a.n_out, stream)) != cudaSuccess) return e;
 		mark(2, 1, 0);
 		x3_rank_bytehist_kernel<<<grid_for((a.M + 65535) / 65536), 256, 0, stream>>>(a);
-		/* level 1: positions by byte (buffer 0), tested and, where the byte is rare, settled */
-		mark(0, 1, 0);
-		if ((e = launch_pdl(x3_rank_radix_kernel<1>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 1, 0, ticket,
-		                    (uint32_t)ticket + 1u)) != cudaSuccess) return e;
-		++ticket;
-		mark(1, 1, 0);
-		if ((e = launch_pdl(x3_rank_first_kernel, grid_for(lv_tiles), LV_THREADS, 0, stream, pdl, a)) != cudaSuccess) return e;
-		/* level 2: sorted from x by (b0, b1): digit b1 into buffer 1, digit b0 back into buffer 0 */
+		/* level 2 is sorted from x by (b0, b1): digit b1 into buffer 1 -- which is also the level-1 order
+		 * of the positions p + 1, tested (and, where the byte is rare, settled) by the first kernel --
+		 * then digit b0 back into buffer 0 */
 		mark(0, 2, 0);
-		if ((e = launch_pdl(x3_rank_radix_kernel<2>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 2, 0, ticket,
+		if ((e = launch_pdl(x3_rank_radix_kernel<true>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 2, 0, ticket,
 		                    (uint32_t)ticket + 1u)) != cudaSuccess) return e;
 		++ticket;
+		mark(1, 2, 0);
+		if ((e = launch_pdl(x3_rank_first_kernel, grid_for(lv_tiles), LV_THREADS, 0, stream, pdl, a)) != cudaSuccess) return e;
 		mark(0, 2, 1);
-		if ((e = launch_pdl(x3_rank_radix_kernel<0>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 2, 1, ticket,
+		if ((e = launch_pdl(x3_rank_radix_kernel<false>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 2, 1, ticket,
 		                    (uint32_t)ticket + 1u)) != cudaSuccess) return e;
 		++ticket;
-		nl += 5;
+		nl += 4;
 		uint32_t known = a.M; /* upper bound of the size of the level about to be queued */
 		for (int L = 2; L <= 32; ++L) {
 			if (L == 2 && known <= (uint32_t)TL_CAP && !no_tail) {
@@ -1391,7 +1413,7 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 			const int np = radix_passes(rbound);
 			for (int pass = 0; pass < np; ++pass) {
 				mark(0, L + 1, pass);
-				if ((e = launch_pdl(x3_rank_radix_kernel<0>, grid_for((known + RS_TILE - 1) / RS_TILE), RS_THREADS, 0, stream,
+				if ((e = launch_pdl(x3_rank_radix_kernel<false>, grid_for((known + RS_TILE - 1) / RS_TILE), RS_THREADS, 0, stream,
 				                    pdl, a, L + 1, pass, ticket, (uint32_t)ticket + 1u)) != cudaSuccess) return e;
 				++ticket;
 				++nl;
