@@ -79,6 +79,9 @@ size_t x3s_required_bytes(size_t n_positions, size_t W);
  *            results are ordered behind it; the brute-force kernels return at once, the rank
  *            search returns when its last level has been queued (it reads level sizes back
  *            while queueing, so the call lasts about as long as the search)
+ * One search per device at a time: the library keeps one set of scratch buffers per device
+ * (searches issued from different streams are ordered behind each other; do not call this
+ * concurrently from several host threads for the same device).
  */
 int x3s_search_device(int device, const void *d_x, size_t n_positions, size_t W, int t,
                       void *d_lstar, void *d_H, void *stream, int variant);

@@ -146,6 +146,16 @@ def test_rank_search_chunked_input_equals_brute_force(pkg, corpus):
     assert np.array_equal(ls_rank, ls_bf), f"first difference at p={int(np.argmax(ls_rank != ls_bf))}"
 
 
+def test_rank_search_chunk_seam_large_window(pkg, corpus):
+    """A chunk seam with a 64 KB window and t = 20: the positions just in front of the seam take
+    their followers from the next chunk's data (the trailing halo of the chunk)."""
+    data = np.frombuffer(corpus.generate("C3", 17_400_000), dtype=np.uint8)
+    W, t = 65536, 20
+    ls_rank, _, _ = pkg.search_host(data, W=W, t=t, variant=pkg.KERNEL_RANK)
+    ls_bf, _, _ = pkg.search_host(data, W=W, t=t, variant=pkg.KERNEL_STREAM)
+    assert np.array_equal(ls_rank, ls_bf), f"first difference at p={int(np.argmax(ls_rank != ls_bf))}"
+
+
 def test_rank_search_max_window_sample(pkg, corpus):
     """-w 1024 -t 64 (C3's flags): brute force needs 10^12 pair tests here, so sampled bands
     are checked against the oracle."""
