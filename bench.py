@@ -289,8 +289,11 @@ def run_b200(args):
     for _ in range(max(3, args.warmup)):
         step_device()
     barrier()
+    # rank 0 samples its own GPU (the line it prints carries those clocks); more nvidia-smi loops
+    # than that only add driver traffic to the timed region
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     time.sleep(0.3)
     t_wall0 = time.time()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
