@@ -13,26 +13,40 @@
  * test is ONE lookup: the element k+1 places further on has the same L-gram and lies
  * within D.  Lstar(p) is the deepest level at which p passes (counts are monotone in L).
  *
- *   level 1   all M = n + D positions (the D positions behind the searched range are
- *             followers only), stable counting sort by the byte.  Positions whose byte
- *             occurs at most t times in their window (tc* < t) are settled here by
- *             walking their <= t followers: Lstar = min LCP32 (0 when fewer than 2).
- *   level L   x3_rank_level_kernel, one pass over the sorted array:
- *               passed(i) = key[i+t+1] == key[i] and pos[i+t+1] - pos[i] <= D  -> Lstar[pos] = L
+ *   level 2   all M = n + D positions (the D positions behind the searched range are
+ *             followers only) sorted from x by (b0 b1, position): x3_rank_bytehist_kernel,
+ *             x3_rank_radix_kernel<INIT> (digit b1 = x[p+1], reads x in position order, so the
+ *             key carries b2 b3 for free) and one ordinary pass (digit b0).
+ *   level 1   no sort of its own: the INIT pass leaves the positions p ordered by
+ *             (x[p+1], p), which is the level-1 order of q = p + 1.  x3_rank_first_kernel
+ *             tests every position there (Lstar is preset to 1) and settles the positions
+ *             whose byte occurs at most t times in their window (tc* < t) by walking their
+ *             <= t followers: Lstar = min LCP32 (0 when fewer than 2).
+ *   level L   x3_rank_level_kernel, one pass over the sorted array (tiles of 2048):
+ *               passed(i) = key[i+t+1] == key[i] and pos[i+t+1] - pos[i] <= D
  *               kept(i)   = i lies within D behind a passed element of its group
  *                           (anything else can never be a follower that matters; any
  *                           superset is exact because every kept element is a real
  *                           position with its real L-gram)
  *               new key   = (group rank << 8) | x[pos + L]; compacted with a single-pass
- *                           chained scan (decoupled look-back over tile aggregates)
+ *                           chained scan (decoupled look-back over tile aggregates, counts
+ *                           published before any slow work)
+ *               Lstar[pos] is written once, at the level where pos stops passing.
  *             then a stable LSD radix sort of the survivors by the new key
  *             (x3_rank_radix_kernel: one pass per 8 bits, per-digit decoupled look-back,
- *             warp-level match ranking), which restores (gram, position) order.
+ *             warp-level match ranking, tile reordered in shared memory), which restores
+ *             (gram, position) order.
+ *   tail      x3_rank_tail_kernel: once <= 8192 elements are left, one CTA runs every
+ *             remaining level in shared memory in a single launch.
  *
- * The work is sum_L m_L element visits instead of N * D pair tests: 3.5 N on text at the
+ * All per-level state lives in device memory; the kernels of a chunk are a pure
+ * kernel -> kernel chain launched with programmatic dependent launch, and the host only
+ * learns level sizes (zero-copy reports) to size grids and to stop queueing.
+ *
+ * The work is sum_L m_L element visits instead of N * D pair tests: 3.3 N on text at the
  * default window, and it does not grow with the window or with t.  Everything is plain
- * coalesced streaming over 4-byte keys and positions plus one byte gather per element, i.e.
- * bound by HBM/L2 bandwidth, not by the ALU pipe.
+ * coalesced streaming over 4-byte keys and positions (plus one byte gather per element from
+ * level 4 on), i.e. memory-system work, not ALU work.
  *
  * Inputs larger than 2^24 - D positions are searched chunk by chunk (ranks and chunk-relative
  * positions then fit 24 bits, so a key is 32 bits).  Lstar only: the 32-bin table H is the
@@ -1272,6 +1286,8 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 	/* programmatic dependent launch between the kernels of a chunk; the profile mode's events would
 	 * sit between the kernels, so it keeps plain launches */
 	const bool pdl = getenv("X3_RANK_NO_PDL") == nullptr && !profile;
+	/* levels of work that stay queued while the host waits for a level size (>= 1) */
+	const int lag = getenv("X3_RANK_LAG") != nullptr && atoi(getenv("X3_RANK_LAG")) >= 1 ? atoi(getenv("X3_RANK_LAG")) : 2;
 	const uint32_t D = prm.D;
 	const unsigned long long CH = (unsigned long long)((RANK_MAX_M - D) & ~4095u);
 	const unsigned long long first = prm.n < CH ? prm.n : CH;
@@ -1363,10 +1379,10 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 				++nl;
 				break;
 			}
-			if (L >= 4) {
-				/* lv[L-1] as level L-2 left it: its size bounds level L, and tells whether level L-1
-				 * (already queued) was the last one */
-				volatile uint32_t *rep = s.h_back + 4 * (L - 2);
+			if (L >= 2 + lag) {
+				/* lv[L-lag+1] as level L-lag left it: its size bounds level L, and tells whether the levels
+				 * queued since were the last ones */
+				volatile uint32_t *rep = s.h_back + 4 * (L - lag);
 				for (unsigned spins = 0; rep[2] != a.seq; ++spins) {
 					if ((spins & 0xfffffu) == 0xfffffu) {
 						/* a kernel that died would never report: do not spin on a failed stream */
@@ -1378,8 +1394,8 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 				}
 				known = rep[0];
 				if (trace) {
-					fprintf(stderr, "x3k_launch_rank: chunk %llu level %d: %u elements, %u groups\n", a0 / CH, L - 1,
-					        known, s.h_back[4 * (L - 2) + 1]);
+					fprintf(stderr, "x3k_launch_rank: chunk %llu level %d: %u elements, %u groups\n", a0 / CH, L - lag + 1,
+					        known, s.h_back[4 * (L - lag) + 1]);
 				}
 				if (known < lim) {
 					break;
