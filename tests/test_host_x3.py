@@ -55,6 +55,34 @@ def test_host_pass_emits_reference_stream_cpu(cpu_bin, corpus, case, tmp_path):
     _roundtrip(cpu_bin, corpus, case, tmp_path)
 
 
+@pytest.mark.parametrize("threads", ["1", "2", "4"])
+@pytest.mark.parametrize("case", SMALL[::4])
+def test_host_pass_pipelines_emit_reference_stream_cpu(cpu_bin, corpus, case, threads, tmp_path, monkeypatch):
+    """X3_THREADS = 1 (one thread), 2 (parse | code) and 4 (parse | ctx0 | ctx1 | code): every
+    pipeline shape emits the reference's stream (an explicit X3_THREADS also applies to small inputs)."""
+    monkeypatch.setenv("X3_THREADS", threads)
+    _roundtrip(cpu_bin, corpus, case, tmp_path)
+
+
+def test_host_pass_pipelines_agree_on_a_large_input(cpu_bin, corpus, tmp_path):
+    """1.2 MB (many ring wrap-arounds, dictionary growth, big contexts): the three pipeline shapes
+    emit one and the same stream, and it decodes back."""
+    data = corpus.generate("C5", 1_200_000)
+    src = tmp_path / "in.bin"
+    src.write_bytes(data)
+    streams = []
+    for threads in ("1", "2", "4"):
+        out = tmp_path / f"out{threads}.x3"
+        r = subprocess.run([str(cpu_bin), "-zf", str(src), str(out)], stderr=subprocess.PIPE, text=True,
+                           env={**os.environ, "X3_THREADS": threads})
+        assert r.returncode == 0, r.stderr[-800:]
+        streams.append(out.read_bytes())
+    assert streams[0] == streams[1] == streams[2]
+    back = tmp_path / "back.bin"
+    subprocess.run([str(cpu_bin), "-df", str(tmp_path / "out4.x3"), str(back)], check=True, stderr=subprocess.DEVNULL)
+    assert back.read_bytes() == data
+
+
 @pytest.mark.skipif(not REF_BIN.exists(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("case", ["C1:60000:", "C5:40000:-n 3 -t 7", "C4:30000:-x"])
 def test_reference_decodes_our_stream(cpu_bin, corpus, case, tmp_path):

@@ -9,6 +9,7 @@
 
 #include <math.h>
 #include <pthread.h>
+#include <unistd.h>
 #include <sched.h>
 #include <stdatomic.h>
 #include <stdlib.h>
@@ -424,6 +425,243 @@ static void *coder_thread(void *arg)
 	return NULL;
 }
 
+/*
+ * Four stages.  The coding of a tag event (x3.c:132-223) reads two context sets that never see
+ * each other: ctx0 (addressed through the tag-pair map) and ctx1.  Both are updated by every tag
+ * event whatever mode is chosen (x3.c:197-209), so each can be run ahead by a thread of its own
+ * that only needs the step records:
+ *
+ *   parse  ->  ctx0 stage: pair map + ctx0: (found, freq, total, cum) of the tag, then the update
+ *          ->  ctx1 stage: the same for ctx1 (and ctx1's growth with the dictionary, x3.c:414-415)
+ *          ->  coder: event / index / match models, the mode decision on the float products of
+ *              x3.c:152-172 (same operands, same order), arithmetic coder, statistics
+ *
+ * The cumulative frequency is taken eagerly (the reference takes it only for the chosen mode; its
+ * value is the same).  Every structure has exactly one owner thread.
+ */
+struct ctx_out {
+	uint64_t total, cum;
+	uint32_t freq, found;
+};
+
+struct ring4 {
+	struct step_rec *rec;
+	struct ctx_out *o0, *o1;
+	_Atomic uint64_t head;       /* records published by the parser */
+	_Atomic uint64_t t0, t1, t2; /* records consumed by the ctx0 stage, the ctx1 stage, the coder */
+	_Atomic int done;
+	struct coder_state *cs;
+};
+
+static inline uint32_t r4_context1(const struct ring4 *rg, uint64_t j)
+{
+	if (j == 0) {
+		return 0;
+	}
+	const struct step_rec *pr = &rg->rec[(j - 1) & (RING_SIZE - 1)];
+	return (pr->b & REC_HIT) ? pr->a : 0u;
+}
+
+/* waits for the parser; returns 0 when everything has been consumed */
+static inline int r4_wait(struct ring4 *rg, uint64_t tail, uint64_t *head)
+{
+	for (;;) {
+		*head = atomic_load_explicit(&rg->head, memory_order_acquire);
+		if (*head != tail) {
+			return 1;
+		}
+		if (atomic_load_explicit(&rg->done, memory_order_acquire)) {
+			*head = atomic_load_explicit(&rg->head, memory_order_acquire);
+			return *head != tail;
+		}
+		sched_yield();
+	}
+}
+
+static void *ctx0_thread(void *arg)
+{
+	struct ring4 *rg = arg;
+	struct x3_codec *c = rg->cs->c;
+	uint32_t prev_context1 = 0, context1 = 0;
+	uint64_t tail = 0, head;
+	while (r4_wait(rg, tail, &head)) {
+		for (; tail < head; ++tail) {
+			if (tail + 2 * LOOK < head) {
+				const struct step_rec *f = &rg->rec[(tail + 2 * LOOK) & (RING_SIZE - 1)];
+				if (f->b & REC_HIT) {
+					x3_pairmap_prefetch(c->pairs, r4_context1(rg, tail + 2 * LOOK), f->a);
+				}
+			}
+			if (tail + LOOK < head) {
+				const struct step_rec *f = &rg->rec[(tail + LOOK) & (RING_SIZE - 1)];
+				if (f->b & REC_HIT) {
+					/* the pair this event registers is the NEXT tag event's ctx0 id */
+					const int64_t id = x3_pairmap_query(c->pairs, r4_context1(rg, tail + LOOK), f->a);
+					if (id >= 0) {
+						x3_ctx_prefetch(c->ctx0, (uint32_t)id, 0, 0);
+					}
+				}
+			}
+			const struct step_rec *r = &rg->rec[tail & (RING_SIZE - 1)];
+			if (r->b & REC_HIT) {
+				const uint32_t tag = r->a;
+				const uint32_t id = ctx0_lookup(c, prev_context1, context1);
+				register_pair(c, context1, tag);
+				const int64_t item = x3_ctx_find(c->ctx0, id, tag);
+				struct ctx_out *o = &rg->o0[tail & (RING_SIZE - 1)];
+				o->found = item >= 0;
+				if (item >= 0) {
+					const struct x3_ctx *cx = x3_ctxset_get(c->ctx0, id);
+					o->freq = x3_ctx_freqs(cx)[item];
+					o->total = cx->total;
+					o->cum = x3_ctx_cum(cx, (uint32_t)item);
+					x3_ctx_inc(c->ctx0, id, (uint32_t)item);
+				} else {
+					x3_ctx_add(c->ctx0, id, tag);
+				}
+				prev_context1 = context1;
+				context1 = tag;
+			} else {
+				prev_context1 = 0;
+				context1 = 0;
+			}
+		}
+		atomic_store_explicit(&rg->t0, tail, memory_order_release);
+	}
+	return NULL;
+}
+
+static void *ctx1_thread(void *arg)
+{
+	struct ring4 *rg = arg;
+	struct x3_codec *c = rg->cs->c;
+	uint32_t context1 = 0;
+	uint32_t dict_elems = rg->cs->dict_elems;
+	uint64_t tail = 0, head;
+	while (r4_wait(rg, tail, &head)) {
+		for (; tail < head; ++tail) {
+			if (tail + 2 * LOOK < head) {
+				const struct step_rec *f = &rg->rec[(tail + 2 * LOOK) & (RING_SIZE - 1)];
+				if (f->b & REC_HIT) {
+					x3_ctx_prefetch(c->ctx1, r4_context1(rg, tail + 2 * LOOK), f->a, 0);
+				}
+			}
+			if (tail + LOOK < head) {
+				const struct step_rec *f = &rg->rec[(tail + LOOK) & (RING_SIZE - 1)];
+				if (f->b & REC_HIT) {
+					x3_ctx_prefetch(c->ctx1, r4_context1(rg, tail + LOOK), f->a, 1);
+				}
+			}
+			const struct step_rec *r = &rg->rec[tail & (RING_SIZE - 1)];
+			if (r->b & REC_HIT) {
+				const uint32_t tag = r->a;
+				const int64_t item = x3_ctx_find(c->ctx1, context1, tag);
+				struct ctx_out *o = &rg->o1[tail & (RING_SIZE - 1)];
+				o->found = item >= 0;
+				if (item >= 0) {
+					const struct x3_ctx *cx = x3_ctxset_get(c->ctx1, context1);
+					o->freq = x3_ctx_freqs(cx)[item];
+					o->total = cx->total;
+					o->cum = x3_ctx_cum(cx, (uint32_t)item);
+					x3_ctx_inc(c->ctx1, context1, (uint32_t)item);
+				} else {
+					x3_ctx_add(c->ctx1, context1, tag);
+				}
+				context1 = tag;
+			} else {
+				if (r->b) {
+					(void)x3_ctxset_get(c->ctx1, dict_elems); /* enlarge_ctx1, x3.c:414-415 */
+					dict_elems++;
+				}
+				context1 = 0;
+			}
+		}
+		atomic_store_explicit(&rg->t1, tail, memory_order_release);
+	}
+	return NULL;
+}
+
+/* the rest of encode_tag (x3.c:152-195) on the two stages' answers */
+static void code_tag4(struct x3_codec *c, struct x3_bitw *w, const struct ctx_out *a0, const struct ctx_out *a1,
+                      uint32_t index)
+{
+	float prob_ctx0 = 0;
+	if (a0->found) {
+		prob_ctx0 = x3_model_prob(&c->events, X3_E_CTX0) * ((float)a0->freq / (float)a0->total);
+	}
+	float prob_ctx1 = 0;
+	if (a1->found) {
+		prob_ctx1 = x3_model_prob(&c->events, X3_E_CTX1) * ((float)a1->freq / (float)a1->total);
+	}
+	const float prob_idx1 = x3_model_prob(&c->events, X3_E_IDX1) * x3_model_prob(&c->index1, index);
+
+	int mode = X3_E_IDX1;
+	float prob = prob_idx1;
+	if (prob_ctx0 > prob) {
+		mode = X3_E_CTX0;
+		prob = prob_ctx0;
+	}
+	if (prob_ctx1 > prob) {
+		mode = X3_E_CTX1;
+		prob = prob_ctx1;
+	}
+
+	enc_symbol(c, w, &c->events, (uint32_t)mode);
+	x3_model_inc(&c->events, (uint32_t)mode);
+
+	switch (mode) {
+		case X3_E_CTX0:
+			x3_ac_encode(&c->ac, w, a0->cum, a0->cum + a0->freq, a0->total);
+			break;
+		case X3_E_CTX1:
+			x3_ac_encode(&c->ac, w, a1->cum, a1->cum + a1->freq, a1->total);
+			break;
+		default:
+			enc_symbol(c, w, &c->index1, index);
+			x3_model_inc(&c->index1, index);
+			break;
+	}
+	c->st.events[mode]++;
+	c->st.sizes[mode] += prob_to_bits(prob);
+}
+
+static void *coder4_thread(void *arg)
+{
+	struct ring4 *rg = arg;
+	struct coder_state *cs = rg->cs;
+	struct x3_codec *c = cs->c;
+	uint64_t tail = 0;
+	for (;;) {
+		/* a record can be coded once both context stages are through with it */
+		uint64_t lim = atomic_load_explicit(&rg->t0, memory_order_acquire);
+		const uint64_t l1 = atomic_load_explicit(&rg->t1, memory_order_acquire);
+		if (l1 < lim) {
+			lim = l1;
+		}
+		if (lim == tail) {
+			if (atomic_load_explicit(&rg->done, memory_order_acquire) &&
+			    atomic_load_explicit(&rg->head, memory_order_acquire) == tail) {
+				break;
+			}
+			sched_yield();
+			continue;
+		}
+		for (; tail < lim; ++tail) {
+			const struct step_rec *r = &rg->rec[tail & (RING_SIZE - 1)];
+			if (r->b & REC_HIT) {
+				code_tag4(c, cs->w, &rg->o0[tail & (RING_SIZE - 1)], &rg->o1[tail & (RING_SIZE - 1)], r->b & ~REC_HIT);
+			} else {
+				encode_match(c, cs->w, cs->base + r->off, r->a);
+				if (r->b) {
+					x3_model_append(&c->index1); /* x3.c:419 */
+				}
+			}
+		}
+		atomic_store_explicit(&rg->t2, tail, memory_order_release);
+	}
+	return NULL;
+}
+
 void *x3_compress(struct x3_codec *c, char *base, size_t isize, x3_fbm_fn fbm, size_t *out_bytes)
 {
 	struct x3_bitw w;
@@ -436,7 +674,8 @@ void *x3_compress(struct x3_codec *c, char *base, size_t isize, x3_fbm_fn fbm, s
 	struct coder_state cs = {c, &w, ptr, 0, 0, x3_dict_elems(c->dict)};
 
 	const char *env = getenv("X3_THREADS");
-	const int threads = env != NULL ? atoi(env) : 2;
+	/* 1: one thread; 2: parse | code; 4 (default where 4 cores are online): parse | ctx0 | ctx1 | code */
+	const int threads = env != NULL ? atoi(env) : (sysconf(_SC_NPROCESSORS_ONLN) >= 4 ? 4 : 2);
 	if (threads == -1) {
 		/* stage timing aid: parse everything, then code everything */
 		struct step_rec *all = malloc(sizeof(struct step_rec) * (isize + 1));
@@ -466,12 +705,54 @@ void *x3_compress(struct x3_codec *c, char *base, size_t isize, x3_fbm_fn fbm, s
 		        (t1.tv_sec - t0.tv_sec) + (t1.tv_nsec - t0.tv_nsec) * 1e-9,
 		        (t2.tv_sec - t1.tv_sec) + (t2.tv_nsec - t1.tv_nsec) * 1e-9, nrec);
 		free(all);
-	} else if (threads <= 1 || isize < 65536) {
+	} else if (threads <= 1 || (env == NULL && isize < 65536)) { /* small inputs: not worth the threads, unless asked for */
 		struct step_rec r;
 		for (uint8_t *p = ptr; p < end;) {
 			p += parse_step(c, p, ptr, end, fbm, &r);
 			code_step(&cs, &r);
 		}
+	} else if (threads >= 4) {
+		struct ring4 rg;
+		rg.rec = malloc(sizeof(struct step_rec) * RING_SIZE);
+		rg.o0 = malloc(sizeof(struct ctx_out) * RING_SIZE);
+		rg.o1 = malloc(sizeof(struct ctx_out) * RING_SIZE);
+		if (rg.rec == NULL || rg.o0 == NULL || rg.o1 == NULL) {
+			abort();
+		}
+		atomic_init(&rg.head, 0);
+		atomic_init(&rg.t0, 0);
+		atomic_init(&rg.t1, 0);
+		atomic_init(&rg.t2, 0);
+		atomic_init(&rg.done, 0);
+		rg.cs = &cs;
+		pthread_t th[3];
+		if (pthread_create(&th[0], NULL, ctx0_thread, &rg) != 0 || pthread_create(&th[1], NULL, ctx1_thread, &rg) != 0 ||
+		    pthread_create(&th[2], NULL, coder4_thread, &rg) != 0) {
+			abort();
+		}
+		uint64_t head = 0, published = 0, tail_seen = 0;
+		for (uint8_t *p = ptr; p < end;) {
+			while (head - tail_seen >= RING_SIZE) { /* ring full: wait for the coder (the last stage) */
+				tail_seen = atomic_load_explicit(&rg.t2, memory_order_acquire);
+				if (head - tail_seen >= RING_SIZE) {
+					sched_yield();
+				}
+			}
+			p += parse_step(c, p, ptr, end, fbm, &rg.rec[head & (RING_SIZE - 1)]);
+			++head;
+			if (head - published >= RING_BATCH) {
+				atomic_store_explicit(&rg.head, head, memory_order_release);
+				published = head;
+			}
+		}
+		atomic_store_explicit(&rg.head, head, memory_order_release);
+		atomic_store_explicit(&rg.done, 1, memory_order_release);
+		for (int i = 0; i < 3; ++i) {
+			pthread_join(th[i], NULL);
+		}
+		free(rg.rec);
+		free(rg.o0);
+		free(rg.o1);
 	} else {
 		struct ring rg;
 		rg.rec = malloc(sizeof(struct step_rec) * RING_SIZE);
