@@ -16,9 +16,15 @@
 #include <string.h>
 #include <time.h>
 
+#define CTX0_SHARDS 2
+#define C0SET(c, id) ((c)->ctx0[(id) % CTX0_SHARDS])
+#define C0ID(id) ((id) / CTX0_SHARDS)
+
 struct x3_codec {
 	struct x3_dict *dict;
-	struct x3_ctxset *ctx0; /* previous two tags (via the tag-pair map), x3.c:19 */
+	/* previous two tags (via the tag-pair map), x3.c:19; context id i lives in shard i % CTX0_SHARDS
+	 * as its context i / CTX0_SHARDS, so that the pipeline can give every shard a thread of its own */
+	struct x3_ctxset *ctx0[CTX0_SHARDS];
 	struct x3_ctxset *ctx1; /* previous tag, x3.c:20 */
 	struct x3_pairmap *pairs;
 	struct x3_model events, match_size, chars, index1; /* x3.c:47-50 */
@@ -45,7 +51,9 @@ struct x3_codec *x3_codec_create(void)
 		abort();
 	}
 	c->dict = x3_dict_create();
-	c->ctx0 = x3_ctxset_create();
+	for (int i = 0; i < CTX0_SHARDS; ++i) {
+		c->ctx0[i] = x3_ctxset_create();
+	}
 	c->ctx1 = x3_ctxset_create();
 	c->pairs = x3_pairmap_create();
 	x3_model_create(&c->events, X3_E_LAST);
@@ -69,7 +77,9 @@ void x3_codec_destroy(struct x3_codec *c)
 	c->st.ctx0_entries = x3_pairmap_elems(c->pairs);
 	c->st.ctx1_entries = x3_dict_elems(c->dict);
 	x3_dict_destroy(c->dict);
-	x3_ctxset_destroy(c->ctx0);
+	for (int i = 0; i < CTX0_SHARDS; ++i) {
+		x3_ctxset_destroy(c->ctx0[i]);
+	}
 	x3_ctxset_destroy(c->ctx1);
 	x3_pairmap_destroy(c->pairs);
 	x3_model_destroy(&c->events);
@@ -151,7 +161,7 @@ static void register_pair(struct x3_codec *c, uint32_t context1, uint32_t tag)
 	if (id < 0) {
 		id = x3_pairmap_add(c->pairs, context1, tag);
 	}
-	const struct x3_ctx *nx = x3_ctxset_get(c->ctx0, (uint32_t)id); /* enlarge_ctx0 */
+	const struct x3_ctx *nx = x3_ctxset_get(C0SET(c, (uint32_t)id), C0ID((uint32_t)id)); /* enlarge_ctx0 */
 	__builtin_prefetch(nx, 1, 1);
 	c->carry_valid = 1;
 	c->carry_t0 = context1;
@@ -164,9 +174,9 @@ static void update_contexts(struct x3_codec *c, uint32_t ctx0_id, uint32_t conte
                             int64_t item1)
 {
 	if (item0 < 0) {
-		x3_ctx_add(c->ctx0, ctx0_id, tag);
+		x3_ctx_add(C0SET(c, ctx0_id), C0ID(ctx0_id), tag);
 	} else {
-		x3_ctx_inc(c->ctx0, ctx0_id, (uint32_t)item0);
+		x3_ctx_inc(C0SET(c, ctx0_id), C0ID(ctx0_id), (uint32_t)item0);
 	}
 	if (item1 < 0) {
 		x3_ctx_add(c->ctx1, context1, tag);
@@ -183,9 +193,9 @@ static void encode_tag(struct x3_codec *c, struct x3_bitw *w, uint32_t prev_cont
 	const uint32_t ctx0_id = ctx0_lookup(c, prev_context1, context1);
 	register_pair(c, context1, tag);
 
-	const int64_t item0 = x3_ctx_find(c->ctx0, ctx0_id, tag);
+	const int64_t item0 = x3_ctx_find(C0SET(c, ctx0_id), C0ID(ctx0_id), tag);
 	const int64_t item1 = x3_ctx_find(c->ctx1, context1, tag);
-	const struct x3_ctx *c0 = x3_ctxset_get(c->ctx0, ctx0_id);
+	const struct x3_ctx *c0 = x3_ctxset_get(C0SET(c, ctx0_id), C0ID(ctx0_id));
 	const struct x3_ctx *c1 = x3_ctxset_get(c->ctx1, context1);
 
 	/* x3.c:152-160: float products, in this order */
@@ -389,7 +399,7 @@ static inline void look_near(const struct ring *rg, uint64_t j)
 		/* the pair this event registers is the NEXT tag event's ctx0 id */
 		const int64_t id = x3_pairmap_query(c->pairs, context1, r->a);
 		if (id >= 0) {
-			x3_ctx_prefetch(c->ctx0, (uint32_t)id, 0, 0);
+			x3_ctx_prefetch(C0SET(c, (uint32_t)id), C0ID((uint32_t)id), 0, 0);
 		}
 	}
 }
@@ -426,12 +436,13 @@ static void *coder_thread(void *arg)
 }
 
 /*
- * Four stages.  The coding of a tag event (x3.c:132-223) reads two context sets that never see
+ * Five stages.  The coding of a tag event (x3.c:132-223) reads two context sets that never see
  * each other: ctx0 (addressed through the tag-pair map) and ctx1.  Both are updated by every tag
  * event whatever mode is chosen (x3.c:197-209), so each can be run ahead by a thread of its own
  * that only needs the step records:
  *
- *   parse  ->  ctx0 stage: pair map + ctx0: (found, freq, total, cum) of the tag, then the update
+ *   parse  ->  pair stage: the tag-pair map: the ctx0 id of every tag event
+ *          ->  ctx0 stage: ctx0: (found, freq, total, cum) of the tag, then the update
  *          ->  ctx1 stage: the same for ctx1 (and ctx1's growth with the dictionary, x3.c:414-415)
  *          ->  coder: event / index / match models, the mode decision on the float products of
  *              x3.c:152-172 (same operands, same order), arithmetic coder, statistics
@@ -447,8 +458,11 @@ struct ctx_out {
 struct ring4 {
 	struct step_rec *rec;
 	struct ctx_out *o0, *o1;
+	uint32_t *pid;               /* ctx0 id of every tag event, from the pair stage */
+	uint64_t mask;               /* RING_SIZE - 1, or all ones when the arrays hold every record (stage timing aid) */
 	_Atomic uint64_t head;       /* records published by the parser */
-	_Atomic uint64_t t0, t1, t2; /* records consumed by the ctx0 stage, the ctx1 stage, the coder */
+	_Atomic uint64_t tp;         /* records consumed by the pair stage */
+	_Atomic uint64_t t0[CTX0_SHARDS], t1, t2; /* records consumed by the ctx0 shards, the ctx1 stage, the coder */
 	_Atomic int done;
 	struct coder_state *cs;
 };
@@ -458,67 +472,55 @@ static inline uint32_t r4_context1(const struct ring4 *rg, uint64_t j)
 	if (j == 0) {
 		return 0;
 	}
-	const struct step_rec *pr = &rg->rec[(j - 1) & (RING_SIZE - 1)];
+	const struct step_rec *pr = &rg->rec[(j - 1) & rg->mask];
 	return (pr->b & REC_HIT) ? pr->a : 0u;
 }
 
-/* waits for the parser; returns 0 when everything has been consumed */
-static inline int r4_wait(struct ring4 *rg, uint64_t tail, uint64_t *head)
+/* waits until the stage in front (`up`: the parser's head or another stage's tail) is past `tail`;
+ * returns 0 when everything has been consumed */
+static inline int r4_wait(struct ring4 *rg, _Atomic uint64_t *up, uint64_t tail, uint64_t *lim)
 {
 	for (;;) {
-		*head = atomic_load_explicit(&rg->head, memory_order_acquire);
-		if (*head != tail) {
+		*lim = atomic_load_explicit(up, memory_order_acquire);
+		if (*lim != tail) {
 			return 1;
 		}
-		if (atomic_load_explicit(&rg->done, memory_order_acquire)) {
-			*head = atomic_load_explicit(&rg->head, memory_order_acquire);
-			return *head != tail;
+		if (atomic_load_explicit(&rg->done, memory_order_acquire) &&
+		    atomic_load_explicit(&rg->head, memory_order_acquire) == tail) {
+			return 0;
 		}
 		sched_yield();
 	}
 }
 
-static void *ctx0_thread(void *arg)
+/* pair stage: the tag-pair map (x3.c:138-145, 211-222): which ctx0 context every tag event uses */
+static void *pair_thread(void *arg)
 {
 	struct ring4 *rg = arg;
 	struct x3_codec *c = rg->cs->c;
 	uint32_t prev_context1 = 0, context1 = 0;
 	uint64_t tail = 0, head;
-	while (r4_wait(rg, tail, &head)) {
+	while (r4_wait(rg, &rg->head, tail, &head)) {
 		for (; tail < head; ++tail) {
 			if (tail + 2 * LOOK < head) {
-				const struct step_rec *f = &rg->rec[(tail + 2 * LOOK) & (RING_SIZE - 1)];
+				const struct step_rec *f = &rg->rec[(tail + 2 * LOOK) & rg->mask];
 				if (f->b & REC_HIT) {
 					x3_pairmap_prefetch(c->pairs, r4_context1(rg, tail + 2 * LOOK), f->a);
 				}
 			}
-			if (tail + LOOK < head) {
-				const struct step_rec *f = &rg->rec[(tail + LOOK) & (RING_SIZE - 1)];
-				if (f->b & REC_HIT) {
-					/* the pair this event registers is the NEXT tag event's ctx0 id */
-					const int64_t id = x3_pairmap_query(c->pairs, r4_context1(rg, tail + LOOK), f->a);
-					if (id >= 0) {
-						x3_ctx_prefetch(c->ctx0, (uint32_t)id, 0, 0);
-					}
-				}
-			}
-			const struct step_rec *r = &rg->rec[tail & (RING_SIZE - 1)];
+			const struct step_rec *r = &rg->rec[tail & rg->mask];
 			if (r->b & REC_HIT) {
 				const uint32_t tag = r->a;
-				const uint32_t id = ctx0_lookup(c, prev_context1, context1);
-				register_pair(c, context1, tag);
-				const int64_t item = x3_ctx_find(c->ctx0, id, tag);
-				struct ctx_out *o = &rg->o0[tail & (RING_SIZE - 1)];
-				o->found = item >= 0;
-				if (item >= 0) {
-					const struct x3_ctx *cx = x3_ctxset_get(c->ctx0, id);
-					o->freq = x3_ctx_freqs(cx)[item];
-					o->total = cx->total;
-					o->cum = x3_ctx_cum(cx, (uint32_t)item);
-					x3_ctx_inc(c->ctx0, id, (uint32_t)item);
-				} else {
-					x3_ctx_add(c->ctx0, id, tag);
+				rg->pid[tail & rg->mask] = ctx0_lookup(c, prev_context1, context1);
+				/* register (context1, tag): its id is the next tag event's ctx0 id */
+				int64_t id = x3_pairmap_query(c->pairs, context1, tag);
+				if (id < 0) {
+					id = x3_pairmap_add(c->pairs, context1, tag);
 				}
+				c->carry_valid = 1;
+				c->carry_t0 = context1;
+				c->carry_t1 = tag;
+				c->carry_id = (uint32_t)id;
 				prev_context1 = context1;
 				context1 = tag;
 			} else {
@@ -526,7 +528,58 @@ static void *ctx0_thread(void *arg)
 				context1 = 0;
 			}
 		}
-		atomic_store_explicit(&rg->t0, tail, memory_order_release);
+		atomic_store_explicit(&rg->tp, tail, memory_order_release);
+	}
+	return NULL;
+}
+
+struct ctx0_arg {
+	struct ring4 *rg;
+	uint32_t shard;
+};
+
+/* ctx0 stage, one thread per shard: the tag events whose ctx0 id falls into the shard */
+static void *ctx0_thread(void *arg)
+{
+	const struct ctx0_arg *ca = arg;
+	struct ring4 *rg = ca->rg;
+	struct x3_codec *c = rg->cs->c;
+	struct x3_ctxset *set = c->ctx0[ca->shard];
+	uint64_t tail = 0, lim;
+	while (r4_wait(rg, &rg->tp, tail, &lim)) {
+		for (; tail < lim; ++tail) {
+			/* the pair stage is ahead: the contexts of the events to come are known exactly */
+			if (tail + 2 * LOOK < lim) {
+				const uint64_t f = (tail + 2 * LOOK) & rg->mask;
+				if ((rg->rec[f].b & REC_HIT) && rg->pid[f] % CTX0_SHARDS == ca->shard) {
+					x3_ctx_prefetch(set, C0ID(rg->pid[f]), 0, 0);
+				}
+			}
+			if (tail + LOOK < lim) {
+				const uint64_t f = (tail + LOOK) & rg->mask;
+				if ((rg->rec[f].b & REC_HIT) && rg->pid[f] % CTX0_SHARDS == ca->shard) {
+					x3_ctx_prefetch(set, C0ID(rg->pid[f]), rg->rec[f].a, 1);
+				}
+			}
+			const struct step_rec *r = &rg->rec[tail & rg->mask];
+			if ((r->b & REC_HIT) && rg->pid[tail & rg->mask] % CTX0_SHARDS == ca->shard) {
+				const uint32_t tag = r->a;
+				const uint32_t id = C0ID(rg->pid[tail & rg->mask]);
+				const int64_t item = x3_ctx_find(set, id, tag); /* grows the shard on demand (enlarge_ctx0) */
+				struct ctx_out *o = &rg->o0[tail & rg->mask];
+				o->found = item >= 0;
+				if (item >= 0) {
+					const struct x3_ctx *cx = x3_ctxset_get(set, id);
+					o->freq = x3_ctx_freqs(cx)[item];
+					o->total = cx->total;
+					o->cum = x3_ctx_cum(cx, (uint32_t)item);
+					x3_ctx_inc(set, id, (uint32_t)item);
+				} else {
+					x3_ctx_add(set, id, tag);
+				}
+			}
+		}
+		atomic_store_explicit(&rg->t0[ca->shard], tail, memory_order_release);
 	}
 	return NULL;
 }
@@ -538,25 +591,25 @@ static void *ctx1_thread(void *arg)
 	uint32_t context1 = 0;
 	uint32_t dict_elems = rg->cs->dict_elems;
 	uint64_t tail = 0, head;
-	while (r4_wait(rg, tail, &head)) {
+	while (r4_wait(rg, &rg->head, tail, &head)) {
 		for (; tail < head; ++tail) {
 			if (tail + 2 * LOOK < head) {
-				const struct step_rec *f = &rg->rec[(tail + 2 * LOOK) & (RING_SIZE - 1)];
+				const struct step_rec *f = &rg->rec[(tail + 2 * LOOK) & rg->mask];
 				if (f->b & REC_HIT) {
 					x3_ctx_prefetch(c->ctx1, r4_context1(rg, tail + 2 * LOOK), f->a, 0);
 				}
 			}
 			if (tail + LOOK < head) {
-				const struct step_rec *f = &rg->rec[(tail + LOOK) & (RING_SIZE - 1)];
+				const struct step_rec *f = &rg->rec[(tail + LOOK) & rg->mask];
 				if (f->b & REC_HIT) {
 					x3_ctx_prefetch(c->ctx1, r4_context1(rg, tail + LOOK), f->a, 1);
 				}
 			}
-			const struct step_rec *r = &rg->rec[tail & (RING_SIZE - 1)];
+			const struct step_rec *r = &rg->rec[tail & rg->mask];
 			if (r->b & REC_HIT) {
 				const uint32_t tag = r->a;
 				const int64_t item = x3_ctx_find(c->ctx1, context1, tag);
-				struct ctx_out *o = &rg->o1[tail & (RING_SIZE - 1)];
+				struct ctx_out *o = &rg->o1[tail & rg->mask];
 				o->found = item >= 0;
 				if (item >= 0) {
 					const struct x3_ctx *cx = x3_ctxset_get(c->ctx1, context1);
@@ -633,10 +686,12 @@ static void *coder4_thread(void *arg)
 	uint64_t tail = 0;
 	for (;;) {
 		/* a record can be coded once both context stages are through with it */
-		uint64_t lim = atomic_load_explicit(&rg->t0, memory_order_acquire);
-		const uint64_t l1 = atomic_load_explicit(&rg->t1, memory_order_acquire);
-		if (l1 < lim) {
-			lim = l1;
+		uint64_t lim = atomic_load_explicit(&rg->t1, memory_order_acquire);
+		for (int i = 0; i < CTX0_SHARDS; ++i) {
+			const uint64_t l0 = atomic_load_explicit(&rg->t0[i], memory_order_acquire);
+			if (l0 < lim) {
+				lim = l0;
+			}
 		}
 		if (lim == tail) {
 			if (atomic_load_explicit(&rg->done, memory_order_acquire) &&
@@ -647,9 +702,9 @@ static void *coder4_thread(void *arg)
 			continue;
 		}
 		for (; tail < lim; ++tail) {
-			const struct step_rec *r = &rg->rec[tail & (RING_SIZE - 1)];
+			const struct step_rec *r = &rg->rec[tail & rg->mask];
 			if (r->b & REC_HIT) {
-				code_tag4(c, cs->w, &rg->o0[tail & (RING_SIZE - 1)], &rg->o1[tail & (RING_SIZE - 1)], r->b & ~REC_HIT);
+				code_tag4(c, cs->w, &rg->o0[tail & rg->mask], &rg->o1[tail & rg->mask], r->b & ~REC_HIT);
 			} else {
 				encode_match(c, cs->w, cs->base + r->off, r->a);
 				if (r->b) {
@@ -676,7 +731,54 @@ void *x3_compress(struct x3_codec *c, char *base, size_t isize, x3_fbm_fn fbm, s
 	const char *env = getenv("X3_THREADS");
 	/* 1: one thread; 2: parse | code; 4 (default where 4 cores are online): parse | ctx0 | ctx1 | code */
 	const int threads = env != NULL ? atoi(env) : (sysconf(_SC_NPROCESSORS_ONLN) >= 4 ? 4 : 2);
-	if (threads == -1) {
+	if (threads == -4) {
+		/* stage timing aid for the four-stage shape: every stage alone, one after the other */
+		struct ring4 lin;
+		lin.rec = malloc(sizeof(struct step_rec) * (isize + 1));
+		lin.o0 = malloc(sizeof(struct ctx_out) * (isize + 1));
+		lin.o1 = malloc(sizeof(struct ctx_out) * (isize + 1));
+		lin.pid = malloc(sizeof(uint32_t) * (isize + 1));
+		lin.mask = ~(uint64_t)0;
+		lin.cs = &cs;
+		atomic_init(&lin.head, 0);
+		atomic_init(&lin.tp, 0);
+		for (int i = 0; i < CTX0_SHARDS; ++i) {
+			atomic_init(&lin.t0[i], 0);
+		}
+		atomic_init(&lin.t1, 0);
+		atomic_init(&lin.t2, 0);
+		atomic_init(&lin.done, 0);
+		size_t nrec = 0;
+		struct timespec t[6];
+		clock_gettime(CLOCK_MONOTONIC, &t[0]);
+		for (uint8_t *p = ptr; p < end;) {
+			p += parse_step(c, p, ptr, end, fbm, &lin.rec[nrec++]);
+		}
+		atomic_store(&lin.head, nrec);
+		atomic_store(&lin.done, 1);
+		clock_gettime(CLOCK_MONOTONIC, &t[1]);
+		pair_thread(&lin);
+		clock_gettime(CLOCK_MONOTONIC, &t[2]);
+		for (uint32_t i = 0; i < CTX0_SHARDS; ++i) {
+			struct ctx0_arg one = {&lin, i};
+			ctx0_thread(&one);
+		}
+		clock_gettime(CLOCK_MONOTONIC, &t[3]);
+		ctx1_thread(&lin);
+		clock_gettime(CLOCK_MONOTONIC, &t[4]);
+		coder4_thread(&lin);
+		clock_gettime(CLOCK_MONOTONIC, &t[5]);
+		double d[5];
+		for (int i = 0; i < 5; ++i) {
+			d[i] = (t[i + 1].tv_sec - t[i].tv_sec) + (t[i + 1].tv_nsec - t[i].tv_nsec) * 1e-9;
+		}
+		fprintf(stderr, "x3_compress stages: parse %.3f s, pairs %.3f s, ctx0 (all shards, one after the other) %.3f s, ctx1 %.3f s, code %.3f s, %zu steps\n",
+		        d[0], d[1], d[2], d[3], d[4], nrec);
+		free(lin.rec);
+		free(lin.o0);
+		free(lin.o1);
+		free(lin.pid);
+	} else if (threads == -1) {
 		/* stage timing aid: parse everything, then code everything */
 		struct step_rec *all = malloc(sizeof(struct step_rec) * (isize + 1));
 		size_t nrec = 0;
@@ -716,18 +818,32 @@ void *x3_compress(struct x3_codec *c, char *base, size_t isize, x3_fbm_fn fbm, s
 		rg.rec = malloc(sizeof(struct step_rec) * RING_SIZE);
 		rg.o0 = malloc(sizeof(struct ctx_out) * RING_SIZE);
 		rg.o1 = malloc(sizeof(struct ctx_out) * RING_SIZE);
-		if (rg.rec == NULL || rg.o0 == NULL || rg.o1 == NULL) {
+		rg.pid = malloc(sizeof(uint32_t) * RING_SIZE);
+		if (rg.rec == NULL || rg.o0 == NULL || rg.o1 == NULL || rg.pid == NULL) {
 			abort();
 		}
+		rg.mask = RING_SIZE - 1;
 		atomic_init(&rg.head, 0);
-		atomic_init(&rg.t0, 0);
+		atomic_init(&rg.tp, 0);
+		for (int i = 0; i < CTX0_SHARDS; ++i) {
+			atomic_init(&rg.t0[i], 0);
+		}
 		atomic_init(&rg.t1, 0);
 		atomic_init(&rg.t2, 0);
 		atomic_init(&rg.done, 0);
 		rg.cs = &cs;
-		pthread_t th[3];
-		if (pthread_create(&th[0], NULL, ctx0_thread, &rg) != 0 || pthread_create(&th[1], NULL, ctx1_thread, &rg) != 0 ||
-		    pthread_create(&th[2], NULL, coder4_thread, &rg) != 0) {
+		pthread_t th[3 + CTX0_SHARDS];
+		struct ctx0_arg ca[CTX0_SHARDS];
+		int nth = 0;
+		int bad = pthread_create(&th[nth++], NULL, pair_thread, &rg) != 0;
+		for (int i = 0; i < CTX0_SHARDS; ++i) {
+			ca[i].rg = &rg;
+			ca[i].shard = (uint32_t)i;
+			bad |= pthread_create(&th[nth++], NULL, ctx0_thread, &ca[i]) != 0;
+		}
+		bad |= pthread_create(&th[nth++], NULL, ctx1_thread, &rg) != 0;
+		bad |= pthread_create(&th[nth++], NULL, coder4_thread, &rg) != 0;
+		if (bad) {
 			abort();
 		}
 		uint64_t head = 0, published = 0, tail_seen = 0;
@@ -747,12 +863,13 @@ void *x3_compress(struct x3_codec *c, char *base, size_t isize, x3_fbm_fn fbm, s
 		}
 		atomic_store_explicit(&rg.head, head, memory_order_release);
 		atomic_store_explicit(&rg.done, 1, memory_order_release);
-		for (int i = 0; i < 3; ++i) {
+		for (int i = 0; i < nth; ++i) {
 			pthread_join(th[i], NULL);
 		}
 		free(rg.rec);
 		free(rg.o0);
 		free(rg.o1);
+		free(rg.pid);
 	} else {
 		struct ring rg;
 		rg.rec = malloc(sizeof(struct step_rec) * RING_SIZE);
@@ -803,7 +920,7 @@ static uint32_t decode_tag(struct x3_codec *c, struct x3_bitr *r, uint32_t decis
                            uint32_t context1)
 {
 	const uint32_t ctx0_id = ctx0_lookup(c, prev_context1, context1);
-	const struct x3_ctx *c0 = x3_ctxset_get(c->ctx0, ctx0_id);
+	const struct x3_ctx *c0 = x3_ctxset_get(C0SET(c, ctx0_id), C0ID(ctx0_id));
 	const struct x3_ctx *c1 = x3_ctxset_get(c->ctx1, context1);
 
 	uint32_t tag;
@@ -839,7 +956,7 @@ static uint32_t decode_tag(struct x3_codec *c, struct x3_bitr *r, uint32_t decis
 	c->st.events[decision]++;
 	c->st.sizes[decision] += size;
 
-	const int64_t item0 = x3_ctx_find(c->ctx0, ctx0_id, tag);
+	const int64_t item0 = x3_ctx_find(C0SET(c, ctx0_id), C0ID(ctx0_id), tag);
 	const int64_t item1 = x3_ctx_find(c->ctx1, context1, tag);
 	update_contexts(c, ctx0_id, context1, tag, item0, item1);
 	register_pair(c, context1, tag);
