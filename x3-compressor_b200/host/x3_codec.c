@@ -274,8 +274,9 @@ static void encode_match(struct x3_codec *c, struct x3_bitw *w, const uint8_t *p
  *          arithmetic coder, statistics.  Never feeds back into the parse.
  *
  * So the stages run as a two-thread pipeline over a single-producer/single-consumer ring of
- * step records; with X3_THREADS=1 the same two functions run in one thread.  The stream does not
- * depend on the mode (tests compare both with the reference).
+ * step records; with X3_THREADS=1 the same two functions run in one thread.  The code stage is
+ * split further below (X3_THREADS=4, the default).  The stream does not depend on the shape
+ * (tests/test_host_x3.py runs every shape against the reference's streams).
  */
 struct step_rec {
 	uint32_t a;   /* hit: the element's tag;            miss: fragment length */
