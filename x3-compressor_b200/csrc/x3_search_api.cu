@@ -75,7 +75,6 @@ int ensure_kernel_init(int device)
 		return fail(X3S_ERR_ARG, "device index %d out of range", device);
 	}
 	if (!g_kernel_inited[device]) {
-		CU_TRY(x3k_init_device());
 		Scratch &sc = g_scratch[device];
 		CU_TRY(cudaMalloc((void **)&sc.counter, 256));
 		CU_TRY(cudaEventCreateWithFlags(&sc.last, cudaEventDisableTiming));
@@ -89,6 +88,9 @@ int ensure_stream_scratch(int device)
 {
 	Scratch &sc = g_scratch[device];
 	if (sc.deep == nullptr) {
+		/* opt-in shared memory sizes of the brute-force kernels (this also loads their modules, which
+		 * a search that only runs the rank kernels never needs) */
+		CU_TRY(x3k_init_device());
 		CU_TRY(cudaMalloc((void **)&sc.deep, (size_t)x3k_stream_max_grid() * X3K_DEEP_BYTES_PER_CTA));
 		CU_TRY(cudaMemset(sc.deep, 0, (size_t)x3k_stream_max_grid() * X3K_DEEP_BYTES_PER_CTA));
 	}
@@ -101,7 +103,7 @@ int launch_on(int device, int variant, X3SearchParams &prm, cudaStream_t stream,
 	Scratch &sc = g_scratch[device];
 	const bool rank = variant == X3S_KERNEL_RANK ||
 	                  (variant == X3S_KERNEL_DEFAULT && prm.H == nullptr && prm.D <= x3k_rank_max_distances());
-	if (!rank && variant != X3S_KERNEL_NAIVE && variant != X3S_KERNEL_BITSLICED) {
+	if (!rank && variant != X3S_KERNEL_NAIVE) {
 		const int rc = ensure_stream_scratch(device);
 		if (rc != X3S_OK) {
 			return rc;
