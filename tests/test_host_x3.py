@@ -147,6 +147,28 @@ def test_report_matches_reference(cpu_bin, corpus, tmp_path):
     assert pick(a) == pick(b)
 
 
+def test_ratio_beyond_64_round_trips(cpu_bin, tmp_path):
+    """300 KB of zeros compress 765:1.  The reference decoder allocates 64 x the stream size
+    (x3.c:621) and cannot restore this; the product decoder grows its output on demand.  The stream
+    itself is still the reference encoder's, byte for byte."""
+    data = bytes(300_000)
+    src = tmp_path / "z.bin"
+    src.write_bytes(data)
+    out = tmp_path / "z.x3"
+    r = subprocess.run([str(cpu_bin), "-zf", str(src), str(out)], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-400:]
+    s = out.read_bytes()
+    assert len(data) / len(s) > 64
+    if REF_BIN.exists():
+        ref = tmp_path / "z.ref.x3"
+        subprocess.run([str(REF_BIN), "-zf", str(src), str(ref)], check=True, stderr=subprocess.DEVNULL)
+        assert ref.read_bytes() == s
+    back = tmp_path / "z.back"
+    r = subprocess.run([str(cpu_bin), "-df", str(out), str(back)], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-400:]
+    assert back.read_bytes() == data
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", SMALL[::3] + BIG)
 def test_product_binary_emits_reference_stream_gpu(corpus, case, tmp_path):
