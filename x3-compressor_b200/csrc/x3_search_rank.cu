@@ -1141,6 +1141,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) x3_rank_tail_kernel(RankArgs a,
 	}
 }
 
+#undef TL_K
+#undef TL_P
+
 /* kernel launch behind another kernel of the same stream with programmatic dependent launch */
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, bool pdl,
@@ -1384,6 +1387,9 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 				 * queued since were the last ones */
 				volatile uint32_t *rep = s.h_back + 4 * (L - lag);
 				for (unsigned spins = 0; rep[2] != a.seq; ++spins) {
+#if defined(__x86_64__) || defined(__i386__)
+					__builtin_ia32_pause(); /* the report is a few microseconds away: spin politely */
+#endif
 					if ((spins & 0xfffffu) == 0xfffffu) {
 						/* a kernel that died would never report: do not spin on a failed stream */
 						const cudaError_t q = cudaStreamQuery(stream);
