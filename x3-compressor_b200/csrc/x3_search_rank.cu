@@ -66,8 +66,11 @@ constexpr int LV_ITEMS = 8;
 constexpr int LV_TILE = LV_THREADS * LV_ITEMS;
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 16;
+constexpr int RS_ITEMS = 16;                    /* elements per thread of a radix tile: large arrays */
+constexpr int RS_ITEMS_SMALL = 8;               /* ... arrays that would not fill the GPU with large tiles */
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int RS_TILE_SMALL = RS_THREADS * RS_ITEMS_SMALL;
+constexpr uint32_t RS_SMALL_BELOW = 3u << 20;   /* elements: below this a pass uses the small tile */
 constexpr uint32_t RANK_MAX_M = (1u << 24) - 1u;
 constexpr uint32_t PMASK = 0x00ffffffu; /* position bits of a position word */
 constexpr uint32_t PFLAG = 0x80000000u; /* "passed the previous level" */
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(256) x3_rank_bytehist_kernel(RankArgs a)
  * 0 .. M-1 themselves, the key is made of the 4 bytes x[p..p+3], the digit is b1 = x[p+1].
  * A tile is ranked with warp-level digit matching, put in digit order in shared memory while
  * the chained per-digit prefix of the tiles in front resolves, then copied out in runs. */
-template <bool INIT>
+template <bool INIT, int ITEMS>
 __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a, int level, int pass, int ticket,
                                                                        uint32_t epoch)
 {
@@ -265,7 +268,8 @@ __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a
 	__shared__ uint32_t wcnt[RS_WARPS][256];
 	__shared__ uint32_t lbase[256];
 	__shared__ uint32_t tbase[256];
-	__shared__ uint32_t skey[RS_TILE], spos[RS_TILE];
+	constexpr int TILE = RS_THREADS * ITEMS;
+	__shared__ uint32_t skey[TILE], spos[TILE];
 	__shared__ uint32_t s_tile;
 	__shared__ uint32_t wsum[RS_WARPS + 1];
 
@@ -281,7 +285,7 @@ __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a
 	const uint32_t *__restrict__ posIn = src ? a.pos1 : a.pos0;
 	uint32_t *__restrict__ keyOut = src ? a.key0 : a.key1;
 	uint32_t *__restrict__ posOut = src ? a.pos0 : a.pos1;
-	const uint32_t ntiles = (m + RS_TILE - 1) / RS_TILE;
+	const uint32_t ntiles = (m + TILE - 1) / TILE;
 	const int shift = 8 * pass;
 	const uint32_t lt = (1u << lane) - 1u;
 
@@ -321,10 +325,10 @@ __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a
 		if (tile >= ntiles) {
 			break;
 		}
-		const uint32_t base = tile * RS_TILE + warp * (32 * RS_ITEMS);
-		uint32_t key[RS_ITEMS], off[RS_ITEMS];
+		const uint32_t base = tile * TILE + warp * (32 * ITEMS);
+		uint32_t key[ITEMS], off[ITEMS];
 #pragma unroll
-		for (int k = 0; k < RS_ITEMS; ++k) {
+		for (int k = 0; k < ITEMS; ++k) {
 			const uint32_t i = base + 32 * k + lane;
 			const bool valid = i < m;
 			if (INIT) {
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a
 			}
 		}
 #pragma unroll
-		for (int k = 0; k < RS_ITEMS; ++k) {
+		for (int k = 0; k < ITEMS; ++k) {
 			const bool valid = base + 32 * k + lane < m;
 			const uint32_t d = valid ? ((key[k] >> shift) & 255u) : 256u;
 			const uint32_t peers = __match_any_sync(FULL_MASK, d);
@@ -388,7 +392,7 @@ __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a
 		__syncthreads();
 		/* the tile in digit order */
 #pragma unroll
-		for (int k = 0; k < RS_ITEMS; ++k) {
+		for (int k = 0; k < ITEMS; ++k) {
 			if (off[k] != 0xffffffffu) {
 				const uint32_t d = off[k] >> 16;
 				const uint32_t idx = lbase[d] + wcnt[warp][d] + (off[k] & 0xffffu);
@@ -417,7 +421,7 @@ __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a
 			tbase[tid] = gbase[tid] + excl - lbase[tid];
 		}
 		__syncthreads();
-		const uint32_t cnt = m - tile * RS_TILE < RS_TILE ? m - tile * RS_TILE : RS_TILE;
+		const uint32_t cnt = m - tile * TILE < TILE ? m - tile * TILE : TILE;
 		for (uint32_t j = tid; j < cnt; j += RS_THREADS) {
 			const uint32_t kk = skey[j];
 			const uint32_t dst = tbase[(kk >> shift) & 255u] + j;
@@ -1214,7 +1218,7 @@ cudaError_t rank_ensure(int dev, uint32_t M)
 		if ((e = cudaMalloc((void **)&s.pos[j], cap * 4 + 64)) != cudaSuccess) return e;
 	}
 	if ((e = cudaMalloc((void **)&s.st_level, (cap / LV_TILE + 1) * 8)) != cudaSuccess) return e;
-	if ((e = cudaMalloc((void **)&s.st_radix, (cap / RS_TILE + 1) * 256 * 8)) != cudaSuccess) return e;
+	if ((e = cudaMalloc((void **)&s.st_radix, (cap / RS_TILE_SMALL + 1) * 256 * 8)) != cudaSuccess) return e;
 	s.cap = (uint32_t)cap;
 	return cudaSuccess;
 }
@@ -1286,6 +1290,7 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 	const bool trace = getenv("X3_TRACE") != nullptr;
 	const bool profile = getenv("X3_RANK_PROFILE") != nullptr;
 	const bool no_tail = getenv("X3_RANK_NO_TAIL") != nullptr; /* testing knob: never changes results */
+	const uint32_t small_below = RS_SMALL_BELOW;
 	/* programmatic dependent launch between the kernels of a chunk; the profile mode's events would
 	 * sit between the kernels, so it keeps plain launches */
 	const bool pdl = getenv("X3_RANK_NO_PDL") == nullptr && !profile;
@@ -1336,10 +1341,10 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 		}
 		s.seq = s.seq + 1u == 0u ? 1u : s.seq + 1u;
 		a.seq = s.seq;
-		const uint32_t lv_tiles = (a.M + LV_TILE - 1) / LV_TILE, rs_tiles = (a.M + RS_TILE - 1) / RS_TILE;
+		const uint32_t lv_tiles = (a.M + LV_TILE - 1) / LV_TILE, rs_tiles = (a.M + RS_TILE - 1) / RS_TILE, rs_tiles_small = (a.M + RS_TILE_SMALL - 1) / RS_TILE_SMALL;
 		if ((e = cudaMemsetAsync(s.ctrl, 0, sizeof(RankCtrl), stream)) != cudaSuccess) return e;
 		if ((e = cudaMemsetAsync(s.st_level, 0, (size_t)lv_tiles * 8, stream)) != cudaSuccess) return e;
-		if ((e = cudaMemsetAsync(s.st_radix, 0, (size_t)rs_tiles * 256 * 8, stream)) != cudaSuccess) return e;
+		if ((e = cudaMemsetAsync(s.st_radix, 0, (size_t)rs_tiles_small * 256 * 8, stream)) != cudaSuccess) return e;
 		int ticket = 0;
 		const int maxgrid = s.sms * 8;
 		auto grid_for = [&](uint32_t tiles) { return (int)(tiles < (uint32_t)maxgrid ? (tiles > 0 ? tiles : 1) : maxgrid); };
@@ -1363,14 +1368,27 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 		 * of the positions p + 1, tested (and, where the byte is rare, settled) by the first kernel --
 		 * then digit b0 back into buffer 0 */
 		mark(0, 2, 0);
-		if ((e = launch_pdl(x3_rank_radix_kernel<true>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 2, 0, ticket,
-		                    (uint32_t)ticket + 1u)) != cudaSuccess) return e;
+		const bool small_in = a.M < small_below;
+		if (small_in) {
+			e = launch_pdl(x3_rank_radix_kernel<true, RS_ITEMS_SMALL>, grid_for(rs_tiles_small), RS_THREADS, 0, stream, pdl, a, 2,
+			               0, ticket, (uint32_t)ticket + 1u);
+		} else {
+			e = launch_pdl(x3_rank_radix_kernel<true, RS_ITEMS>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 2, 0, ticket,
+			               (uint32_t)ticket + 1u);
+		}
+		if (e != cudaSuccess) return e;
 		++ticket;
 		mark(1, 2, 0);
 		if ((e = launch_pdl(x3_rank_first_kernel, grid_for(lv_tiles), LV_THREADS, 0, stream, pdl, a)) != cudaSuccess) return e;
 		mark(0, 2, 1);
-		if ((e = launch_pdl(x3_rank_radix_kernel<false>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 2, 1, ticket,
-		                    (uint32_t)ticket + 1u)) != cudaSuccess) return e;
+		if (small_in) {
+			e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS_SMALL>, grid_for(rs_tiles_small), RS_THREADS, 0, stream, pdl, a, 2,
+			               1, ticket, (uint32_t)ticket + 1u);
+		} else {
+			e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 2, 1, ticket,
+			               (uint32_t)ticket + 1u);
+		}
+		if (e != cudaSuccess) return e;
 		++ticket;
 		nl += 4;
 		uint32_t known = a.M; /* upper bound of the size of the level about to be queued */
@@ -1435,8 +1453,15 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 			const int np = radix_passes(rbound);
 			for (int pass = 0; pass < np; ++pass) {
 				mark(0, L + 1, pass);
-				if ((e = launch_pdl(x3_rank_radix_kernel<false>, grid_for((known + RS_TILE - 1) / RS_TILE), RS_THREADS, 0, stream,
-				                    pdl, a, L + 1, pass, ticket, (uint32_t)ticket + 1u)) != cudaSuccess) return e;
+				/* the tile size only has to be the same within one pass */
+				if (known < small_below) {
+					e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS_SMALL>, grid_for((known + RS_TILE_SMALL - 1) / RS_TILE_SMALL),
+					               RS_THREADS, 0, stream, pdl, a, L + 1, pass, ticket, (uint32_t)ticket + 1u);
+				} else {
+					e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS>, grid_for((known + RS_TILE - 1) / RS_TILE), RS_THREADS, 0,
+					               stream, pdl, a, L + 1, pass, ticket, (uint32_t)ticket + 1u);
+				}
+				if (e != cudaSuccess) return e;
 				++ticket;
 				++nl;
 			}
