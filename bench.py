@@ -473,15 +473,20 @@ def compress_leg(corpus):
             return {"unavailable": "bin/x3 failed: " + r.stderr[-200:]}
         el = _elapsed(r.stderr)
         srch = _elapsed(r.stderr, "of which match search")
+        start = _elapsed(r.stderr, "of which CUDA start-up") or 0.0
         stream = (td / "c2.x3").read_bytes()
         rd = subprocess.run([str(x3), "-df", str(td / "c2.x3"), str(td / "c2.back")], stderr=subprocess.PIPE, text=True)
         ok = rd.returncode == 0 and (td / "c2.back").read_bytes() == data
         out.update({"value": len(data) / el / 1e6, "unit": "MB/s", "bytes": len(data), "elapsed_s": el,
-                    "search_s": srch, "process_wall_s": wall, "stream_bytes": len(stream),
+                    "search_s": srch, "cuda_startup_s": start,
+                    "value_excluding_cuda_startup": len(data) / max(el - start, 1e-9) / 1e6,
+                    "host_pass_s": el - srch, "process_wall_s": wall, "stream_bytes": len(stream),
                     "ratio": len(data) / len(stream), "round_trip_ok": ok,
                     "decompress_MB_per_s": len(data) / _elapsed(rd.stderr) / 1e6 if ok else None,
                     "what": "bin/x3 -z on the whole C2 file: GPU search (incl. transfers) + sequential host pass, "
-                            "the program's own 'elapsed time' (brackets prepare + compress, cf. x3.c:597-601)"})
+                            "the program's own 'elapsed time' (brackets prepare + compress, cf. x3.c:597-601); "
+                            "cuda_startup_s is the process's one-off driver load + context creation inside it "
+                            "(0.2 s to several seconds depending on the box, unrelated to the search)"})
         if ref.exists():
             n = 1_000_000
             (td / "pre").write_bytes(data[:n])

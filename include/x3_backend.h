@@ -76,6 +76,10 @@ void x3_search_table(const uint8_t **H, const uint8_t **Lstar, size_t *n);
  * so a host can add it to the reference's "elapsed time" (x3.c:597-601). */
 double x3_search_prepare_ms(void);
 
+/* NEW.  The part of that which was the process's one-off CUDA start-up (driver load and first
+ * context; 0 when a previous call had already paid it). */
+double x3_search_startup_ms(void);
+
 /*
  * NEW.  Dictionary callbacks for hosts that cannot export dict_find_match /
  * dict_get_len_by_index as dynamic symbols (e.g. FFI hosts).  Passing NULLs

@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
     L.x3_search_prepare.restype = None
     L.x3_search_release.restype = None
     L.x3_search_prepare_ms.restype = C.c_double
+    L.x3_search_startup_ms.restype = C.c_double
     L.x3_search_table.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.x3_backend_set_dict.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L

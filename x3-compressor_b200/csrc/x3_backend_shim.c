@@ -54,6 +54,7 @@ static size_t g_isize = 0;
 static uint8_t *g_lstar = NULL;
 static uint8_t *g_table = NULL;
 static double g_prepare_ms = 0.0;
+static double g_startup_ms = 0.0; /* one-off CUDA start-up (driver + first context) inside the last prepare */
 
 static void die(const char *what)
 {
@@ -102,6 +103,19 @@ void x3_search_prepare(const char *base, size_t isize)
 		}
 	}
 
+	g_startup_ms = 0.0;
+	if (isize > 0) {
+		/* The first CUDA call of a process loads the driver and creates the context: between 0.2 s and
+		 * several seconds depending on the machine, and nothing to do with the search.  Take it here,
+		 * separately timed, so that a host can report it apart from the search proper. */
+		struct timespec s0, s1;
+		clock_gettime(CLOCK_MONOTONIC, &s0);
+		if (x3s_device_count() > 0) {
+			x3s_host_free(x3s_host_alloc(64));
+		}
+		clock_gettime(CLOCK_MONOTONIC, &s1);
+		g_startup_ms = (s1.tv_sec - s0.tv_sec) * 1e3 + (s1.tv_nsec - s0.tv_nsec) * 1e-6;
+	}
 	if (isize > 0) {
 		/* backend.c:76: the selection loop never runs for t <= 0 */
 		int t = g_max_match_count;
@@ -124,6 +138,11 @@ void x3_search_prepare(const char *base, size_t isize)
 double x3_search_prepare_ms(void)
 {
 	return g_prepare_ms;
+}
+
+double x3_search_startup_ms(void)
+{
+	return g_startup_ms;
 }
 
 void x3_search_table(const uint8_t **H, const uint8_t **Lstar, size_t *n)

@@ -163,6 +163,8 @@ int main(int argc, char *argv[])
 		const double t2 = now_s();
 		fprintf(stderr, "elapsed time: %f\n", (float)(t2 - t0));
 		fprintf(stderr, "of which match search (GPU, incl. transfers): %f\n", (float)(t1 - t0));
+		fprintf(stderr, "of which CUDA start-up (driver + first context, once per process): %f\n",
+		        (float)(x3_search_startup_ms() * 1e-3));
 		x3_search_release();
 
 		size = isize;
