@@ -119,6 +119,17 @@ def test_rank_search_without_tail_kernel(pkg, corpus, monkeypatch, kind, n, W, t
     _assert_rank_same(pkg, data, W, t)
 
 
+@pytest.mark.parametrize("knob,value", [("X3_RANK_NO_PDL", "1"), ("X3_RANK_LAG", "1"), ("X3_RANK_LAG", "4"),
+                                        ("X3_RANK_PROFILE", "1")])
+def test_rank_search_launch_knobs_do_not_change_results(pkg, corpus, monkeypatch, knob, value):
+    """Plain launches instead of programmatic dependent launch, other host lags, event-bracketed
+    launches: only the queueing changes, never the table."""
+    monkeypatch.setenv(knob, value)
+    _assert_rank_same(pkg, _inputs(corpus, "text", 300_000), 8192, 15)
+    _assert_rank_same(pkg, _inputs(corpus, "binary", 120_000), 4096, 40)
+    _assert_rank_same(pkg, _inputs(corpus, "zeros", 30_000), 1024, 3)
+
+
 def test_rank_search_rejects_table_request(pkg):
     with pytest.raises(pkg.X3SearchError):
         pkg.search_host(np.zeros(100, dtype=np.uint8), W=8192, t=15, variant=pkg.KERNEL_RANK, want_table=True)
