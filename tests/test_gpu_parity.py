@@ -78,9 +78,9 @@ def test_table_equals_oracle_threshold_sweep(pkg, corpus, t):
         _assert_same(pkg, _inputs(corpus, "zeros", 3000), 1024, t, variant)
 
 
-def _assert_rank_same(pkg, data, W, t):
+def _assert_rank_same(pkg, data, W, t, pinned=False):
     """The rank search (variant 5, Lstar only) against the oracle."""
-    lstar, _, _ = pkg.search_host(data, W=W, t=t, ngpus=1, variant=pkg.KERNEL_RANK)
+    lstar, _, _ = pkg.search_host(data, W=W, t=t, ngpus=1, variant=pkg.KERNEL_RANK, pinned=pinned)
     _, ls_ref = ol.table(data, W, t)
     assert np.array_equal(lstar, ls_ref), (f"rank search: Lstar differs first at p={int(np.argmax(lstar != ls_ref))} "
                                            f"(n={len(data)} W={W} t={t})")
@@ -128,6 +128,68 @@ def test_rank_search_launch_knobs_do_not_change_results(pkg, corpus, monkeypatch
     _assert_rank_same(pkg, _inputs(corpus, "text", 300_000), 8192, 15)
     _assert_rank_same(pkg, _inputs(corpus, "binary", 120_000), 4096, 40)
     _assert_rank_same(pkg, _inputs(corpus, "zeros", 30_000), 1024, 3)
+
+
+@pytest.mark.parametrize("lanes,pieces", [(2, None), (3, None), (4, None), (2, "1"), (4, "1")])
+def test_rank_search_lanes_do_not_change_results(pkg, corpus, monkeypatch, lanes, pieces):
+    """The position range cut into lanes that are searched concurrently (own stream, own scratch, one
+    host thread feeding all of them).  pieces=None: the host call is pipelined piece by piece (upload,
+    search, copy back per piece); pieces='1': one upload, the device-level search forks into lanes and
+    joins back.  Seams between lanes are invisible, also when a lane's window reaches over more than
+    one neighbour (W = 64 KB against 75 000-position lanes)."""
+    monkeypatch.setenv("X3_RANK_LANES", str(lanes))
+    if pieces is not None:
+        monkeypatch.setenv("X3_HOST_PIECES", pieces)
+    pin = pieces is None  # the library pipelines a shard only between page-locked host buffers
+    _assert_rank_same(pkg, _inputs(corpus, "text", 300_000), 8192, 15, pin)
+    _assert_rank_same(pkg, _inputs(corpus, "binary", 280_000), 4096, 40, pin)
+    _assert_rank_same(pkg, _inputs(corpus, "zeros", 270_000), 1024, 3, pin)
+    _assert_rank_same(pkg, _inputs(corpus, "text", 300_000), 65536, 20, pin)
+    _assert_rank_same(pkg, _inputs(corpus, "mix", 270_000), 300, 0, pin)   # t = 0: memset per lane
+    _assert_rank_same(pkg, _inputs(corpus, "mix", 270_000), 33, 5, pin)    # empty window
+
+
+def test_rank_search_pageable_buffers_are_not_pipelined(pkg, corpus, monkeypatch):
+    """Pageable host buffers (what the backend.h shim gets from the reference's main) take the plain
+    upload - search - copy back sequence whatever the knobs say; the table is the same."""
+    monkeypatch.setenv("X3_RANK_LANES", "3")
+    data = _inputs(corpus, "text", 300_000)
+    a, _, tma = pkg.search_host(data, W=8192, t=15, variant=pkg.KERNEL_RANK, pinned=False)
+    b, _, tmb = pkg.search_host(data, W=8192, t=15, variant=pkg.KERNEL_RANK, pinned=True)
+    assert np.array_equal(a, b) and tma.launches == tmb.launches
+
+
+def test_rank_search_lanes_default_one_per_chunk(pkg, corpus):
+    """Without knobs an input of two chunks runs as two lanes (twice the set-up launches of one
+    chunk, same table as the brute-force kernel)."""
+    data = np.frombuffer(corpus.generate("C3", 17_400_000), dtype=np.uint8)
+    ls_rank, _, tm = pkg.search_host(data, W=8192, t=15, variant=pkg.KERNEL_RANK)
+    ls_bf, _, _ = pkg.search_host(data, W=8192, t=15, variant=pkg.KERNEL_STREAM)
+    assert np.array_equal(ls_rank, ls_bf), f"first difference at p={int(np.argmax(ls_rank != ls_bf))}"
+    assert tm.launches >= 8
+
+
+def test_rank_search_device_api_lanes(pkg, corpus, monkeypatch):
+    """x3s_search_device on a caller's stream: the lanes fork from it and join back into it, so work
+    queued on the stream behind the call sees the complete table."""
+    import torch
+    data = _inputs(corpus, "text", 400_000)
+    W, t = 8192, 15
+    _, ls_ref = ol.table(data, W, t)
+    dev = torch.device("cuda:0")
+    need = pkg.required_bytes(len(data), W)
+    stream = torch.cuda.Stream(device=dev)
+    for lanes in ("1", "3"):
+        monkeypatch.setenv("X3_RANK_LANES", lanes)
+        with torch.cuda.stream(stream):
+            d_x = torch.zeros(need, dtype=torch.uint8, device=dev)
+            d_x[: len(data)] = torch.from_numpy(np.array(data, copy=True)).to(dev, non_blocking=False)
+            d_l = torch.full((len(data),), 99, dtype=torch.uint8, device=dev)
+            pkg.search_device(0, d_x.data_ptr(), len(data), W, t, d_l.data_ptr(), None, stream.cuda_stream,
+                              pkg.KERNEL_RANK)
+            got = d_l.clone()  # queued on the same stream right behind the search
+        stream.synchronize()
+        assert np.array_equal(got.cpu().numpy(), ls_ref), f"lanes={lanes}"
 
 
 def test_rank_search_rejects_table_request(pkg):

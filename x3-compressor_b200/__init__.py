@@ -137,16 +137,36 @@ def padded(data, W: int) -> np.ndarray:
 
 
 def search_host(data, W: int = 8192, t: int = 15, ngpus: int = 1, variant: int = KERNEL_DEFAULT,
-                want_table: bool = False):
+                want_table: bool = False, pinned: bool = False):
     """One call of the hot path over a host buffer through the C ABI.
+
+    pinned=True stages the input and Lstar in page-locked memory (x3s_host_alloc), which is what lets
+    the library pipeline a shard piece by piece (upload | search | copy back).
 
     Returns (lstar[n] u8, H[n,32] u8 or None, Timing)."""
     a = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
     n = len(a)
-    x = padded(a, W)
-    lstar = np.empty(n, dtype=np.uint8)
     H = np.empty((n, MAX_MATCH_LEN), dtype=np.uint8) if want_table else None
     tm = Timing()
+    if pinned and n > 0:
+        L = lib()
+        hx, hl = L.x3s_host_alloc(n + W), L.x3s_host_alloc(n)
+        if not hx or not hl:
+            raise X3SearchError(X3S_ERR_CUDA, L.x3s_last_error().decode(errors="replace"))
+        try:
+            xv = np.ctypeslib.as_array(C.cast(hx, C.POINTER(C.c_uint8)), shape=(n + W,))
+            xv[:n] = a
+            xv[n:] = 0
+            rc = L.x3s_search_host(hx, n, W, t, ngpus, variant, hl, H.ctypes.data if H is not None else None,
+                                   C.byref(tm))
+            _check(rc)
+            lstar = np.ctypeslib.as_array(C.cast(hl, C.POINTER(C.c_uint8)), shape=(n,)).copy()
+        finally:
+            L.x3s_host_free(hx)
+            L.x3s_host_free(hl)
+        return lstar, H, tm
+    x = padded(a, W)
+    lstar = np.empty(n, dtype=np.uint8)
     rc = lib().x3s_search_host(x.ctypes.data, n, W, t, ngpus, variant, lstar.ctypes.data,
                                H.ctypes.data if H is not None else None, C.byref(tm))
     _check(rc)

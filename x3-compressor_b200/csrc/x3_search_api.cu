@@ -22,6 +22,8 @@
 
 namespace {
 
+constexpr int X3S_MAX_PIECES = 4;
+
 thread_local char g_err[512] = "";
 
 int fail(int code, const char *fmt, ...)
@@ -52,7 +54,32 @@ struct DevState {
 	size_t cap_l = 0;
 	uint8_t *d_h = nullptr;
 	size_t cap_h = 0;
+	/* pipelined shard (rank search in pieces): a stream per piece and, per piece, the events
+	 * "upload done", "search done", "Lstar back" */
+	cudaStream_t ps[X3S_MAX_PIECES] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t pev[X3S_MAX_PIECES][3] = {};
+	bool pinited = false;
+	int pieces = 1;  /* pieces of the last search on this device */
+	int pfirst = 0;  /* piece whose upload lets the first search start */
 };
+
+/* what the rank search's "last kernel of this job is queued" callback needs to bring the piece back */
+struct PieceCtx {
+	DevState *ds;
+	uint8_t *h_lstar;       /* host destination of the shard */
+	size_t lo[X3S_MAX_PIECES + 1]; /* piece p = shard positions [lo[p], lo[p+1]) */
+};
+
+cudaError_t piece_queued(void *vctx, int p)
+{
+	PieceCtx *c = (PieceCtx *)vctx;
+	DevState &ds = *c->ds;
+	cudaError_t e;
+	if ((e = cudaEventRecord(ds.pev[p][1], ds.ps[p])) != cudaSuccess) return e;
+	if ((e = cudaMemcpyAsync(c->h_lstar + c->lo[p], ds.d_l + c->lo[p], c->lo[p + 1] - c->lo[p], cudaMemcpyDeviceToHost,
+	                         ds.ps[p])) != cudaSuccess) return e;
+	return cudaEventRecord(ds.pev[p][2], ds.ps[p]);
+}
 
 /* Per-device scratch of the stream kernel (tile counter + deep histogram rows).
  * One search is in flight per device at a time: launches on other streams are
@@ -146,6 +173,18 @@ int check_params(size_t W, int t)
 		return fail(X3S_ERR_UNSUPP, "forward window %zu exceeds 2^31", W);
 	}
 	return X3S_OK;
+}
+
+/* page-locked (cudaHostAlloc / cudaHostRegister) host memory?  Async copies of pageable memory
+ * hold the calling thread until they are done, which would stall the thread that feeds the lanes. */
+bool host_pinned(const void *p)
+{
+	cudaPointerAttributes at;
+	if (p == nullptr || cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+		(void)cudaGetLastError();
+		return false;
+	}
+	return at.type == cudaMemoryTypeHost;
 }
 
 uint32_t distances(size_t W)
@@ -257,6 +296,9 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 	}
 
 	const size_t total = n + W; /* bytes the caller guarantees behind x */
+	/* a shard is pipelined piece by piece only between page-locked buffers (pageable ones take the plain
+	 * upload - search - copy back sequence; the search itself still runs its lanes concurrently) */
+	const bool pinned_io = n > 0 && host_pinned(x) && host_pinned(lstar);
 	std::vector<int> shard_launches(G, 0);
 	std::vector<int> shard_rc(G, X3S_OK);
 	std::vector<std::string> shard_err(G);
@@ -295,6 +337,80 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 		if (a[g] + have > total) {
 			have = total - a[g];
 		}
+		const uint32_t D = distances(W);
+		const bool rank = H == nullptr && (variant == X3S_KERNEL_RANK || (variant == X3S_KERNEL_DEFAULT && D <= x3k_rank_max_distances()));
+		int P = 1;
+		if (rank && getenv("X3_RANK_PROFILE") == nullptr && pinned_io) {
+			const char *hp = getenv("X3_HOST_PIECES"); /* tuning/testing knob; never changes results */
+			P = hp != nullptr && atoi(hp) >= 1 ? atoi(hp) : x3k_rank_default_lanes(np, D);
+			if (P > X3S_MAX_PIECES) P = X3S_MAX_PIECES;
+			if (P > x3k_rank_max_lanes()) P = x3k_rank_max_lanes();
+			while (P > 1 && np / (size_t)P < 65536) --P;
+		}
+		ds.pieces = P;
+		if (P > 1) {
+			/* Pipelined shard: the upload goes piece by piece on ds.stream, piece p is searched on its own
+			 * stream as soon as the bytes it reads (its positions and the window behind them) have
+			 * arrived, and its Lstar goes back while the pieces behind it are still being searched. */
+			if (!ds.pinited) {
+				for (int p = 0; p < X3S_MAX_PIECES; ++p) {
+					CU_TRY(cudaStreamCreateWithFlags(&ds.ps[p], cudaStreamNonBlocking));
+					for (int k = 0; k < 3; ++k) {
+						CU_TRY(cudaEventCreate(&ds.pev[p][k]));
+					}
+				}
+				ds.pinited = true;
+			}
+			PieceCtx ctx;
+			ctx.ds = &ds;
+			ctx.h_lstar = (uint8_t *)lstar + a[g];
+			for (int p = 0; p <= P; ++p) {
+				ctx.lo[p] = p == P ? np : ((size_t)((unsigned __int128)np * p / P) & ~(size_t)4095);
+			}
+			Scratch &sc = g_scratch[dev];
+			CU_TRY(cudaStreamWaitEvent(ds.stream, sc.last, 0));
+			CU_TRY(cudaEventRecord(ds.ev[0], ds.stream));
+			for (int p = 0; p < P; ++p) {
+				/* bytes [lo[p], lo[p+1]) of the shard; the last piece brings the halo and the zeroed slack */
+				const size_t b0 = ctx.lo[p], b1 = p + 1 == P ? have : ctx.lo[p + 1];
+				CU_TRY(cudaMemcpyAsync(ds.d_x + b0, (const uint8_t *)x + a[g] + b0, b1 - b0, cudaMemcpyHostToDevice, ds.stream));
+				if (p + 1 == P && need > have) {
+					CU_TRY(cudaMemsetAsync(ds.d_x + have, 0, need - have, ds.stream));
+				}
+				CU_TRY(cudaEventRecord(ds.pev[p][0], ds.stream));
+			}
+			CU_TRY(cudaEventRecord(ds.ev[1], ds.stream));
+			X3RankJob jobs[X3S_MAX_PIECES];
+			for (int p = 0; p < P; ++p) {
+				jobs[p].x = ds.d_x + ctx.lo[p];
+				jobs[p].lstar = ds.d_l + ctx.lo[p];
+				jobs[p].n = ctx.lo[p + 1] - ctx.lo[p];
+				jobs[p].stream = ds.ps[p];
+				jobs[p].queued = piece_queued;
+				jobs[p].ctx = &ctx;
+				/* the piece reads x3k_required_bytes() behind its start: wait for the upload that brings the last of them */
+				const size_t last = ctx.lo[p] + x3k_required_bytes(jobs[p].n, W) - 1;
+				int q = p;
+				while (q + 1 < P && ctx.lo[q + 1] <= last) {
+					++q;
+				}
+				if (p == 0) {
+					ds.pfirst = q;
+				}
+				CU_TRY(cudaStreamWaitEvent(ds.ps[p], ds.pev[q][0], 0));
+			}
+			const cudaError_t je = x3k_launch_rank_jobs(jobs, P, D, t, &shard_launches[g]);
+			for (int p = 0; p < P; ++p) {
+				/* ds.stream (and with it the device's next search) continues behind every piece */
+				if (je == cudaSuccess) {
+					CU_TRY(cudaStreamWaitEvent(ds.stream, ds.pev[p][2], 0));
+				}
+			}
+			CU_TRY(je);
+			CU_TRY(cudaEventRecord(ds.ev[3], ds.stream));
+			CU_TRY(cudaEventRecord(sc.last, ds.stream));
+			return X3S_OK;
+		}
 		CU_TRY(cudaEventRecord(ds.ev[0], ds.stream));
 		CU_TRY(cudaMemcpyAsync(ds.d_x, (const uint8_t *)x + a[g], have, cudaMemcpyHostToDevice, ds.stream));
 		if (need > have) {
@@ -304,7 +420,7 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 		X3SearchParams prm;
 		prm.x = ds.d_x;
 		prm.n = np;
-		prm.D = distances(W);
+		prm.D = D;
 		prm.t = t;
 		prm.lstar = ds.d_l;
 		prm.H = H != nullptr ? ds.d_h : nullptr;
@@ -366,6 +482,21 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 		CU_TRY(cudaSetDevice(dev));
 		CU_TRY(cudaStreamSynchronize(ds.stream));
 		float ms = 0.f;
+		if (ds.pieces > 1) {
+			/* pipelined shard: the three figures split the critical path -- upload until the first search
+			 * can start, from there to the end of the last search, from there to the last byte back */
+			float up = 0.f, all = 0.f, kend = 0.f;
+			CU_TRY(cudaEventElapsedTime(&up, ds.ev[0], ds.pev[ds.pfirst][0]));
+			CU_TRY(cudaEventElapsedTime(&all, ds.ev[0], ds.ev[3]));
+			for (int p = 0; p < ds.pieces; ++p) {
+				CU_TRY(cudaEventElapsedTime(&ms, ds.ev[0], ds.pev[p][1]));
+				if (ms > kend) kend = ms;
+			}
+			if (up > tm.h2d_ms) tm.h2d_ms = up;
+			if (kend - up > tm.kernel_ms) tm.kernel_ms = kend - up;
+			if (all - kend > tm.d2h_ms) tm.d2h_ms = all - kend;
+			continue;
+		}
 		CU_TRY(cudaEventElapsedTime(&ms, ds.ev[0], ds.ev[1]));
 		if (ms > tm.h2d_ms) tm.h2d_ms = ms;
 		CU_TRY(cudaEventElapsedTime(&ms, ds.ev[1], ds.ev[2]));
@@ -444,6 +575,14 @@ void x3s_release(void)
 				cudaEventDestroy(ds.ev[i]);
 			}
 			cudaStreamDestroy(ds.stream);
+		}
+		if (ds.pinited) {
+			for (int p = 0; p < X3S_MAX_PIECES; ++p) {
+				cudaStreamDestroy(ds.ps[p]);
+				for (int k = 0; k < 3; ++k) {
+					cudaEventDestroy(ds.pev[p][k]);
+				}
+			}
 		}
 		ds = DevState();
 		if (g < 64 && g_kernel_inited[g]) {

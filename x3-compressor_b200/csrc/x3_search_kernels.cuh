@@ -38,9 +38,26 @@ size_t x3k_required_bytes(size_t n, size_t W);
 cudaError_t x3k_launch(int variant, const X3SearchParams &prm, cudaStream_t stream, int *launches);
 
 /* Rank search (x3_search_rank.cu): Lstar only, any t <= 254, D <= x3k_rank_max_distances().
- * Issues its launches on `stream` but returns only after the last level has reported its
- * size (one small read-back per level).  cudaErrorNotSupported when H is requested. */
+ * Issues its launches on `stream` (and on lane streams forked from and joined back into it) but
+ * returns only after the last level has reported its size (one small zero-copy report per level).
+ * cudaErrorNotSupported when H is requested. */
 cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int *launches);
+
+/* The same for up to x3k_rank_max_lanes() independent position ranges of the current device at
+ * once, each on a stream of the caller's (no fork/join): one host thread keeps all of them fed.
+ * `queued` is called as soon as the job's last kernel is queued on its stream (the API layer
+ * queues the job's D2H copy there, while the other jobs are still being queued). */
+struct X3RankJob {
+	const uint8_t *x;      /* device, 16-byte aligned, x3k_required_bytes(n, W) readable */
+	uint8_t *lstar;        /* n bytes */
+	unsigned long long n;
+	cudaStream_t stream;
+	cudaError_t (*queued)(void *ctx, int job);
+	void *ctx;
+};
+cudaError_t x3k_launch_rank_jobs(const X3RankJob *jobs, int njobs, uint32_t D, int t, int *launches);
+int x3k_rank_max_lanes(void);
+int x3k_rank_default_lanes(unsigned long long n, uint32_t D); /* X3_RANK_LANES, else one per chunk */
 uint32_t x3k_rank_max_distances(void);
 void x3k_rank_release(int device);
 int x3k_rank_profile(int device, int kind, double *ms, double *elements, int *launches);

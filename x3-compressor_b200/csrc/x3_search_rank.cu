@@ -62,7 +62,11 @@
 namespace {
 
 constexpr int LV_THREADS = 256;
-constexpr int LV_ITEMS = 8;
+#ifndef X3_LV_ITEMS
+#define X3_LV_ITEMS 8
+#endif
+constexpr int LV_ITEMS = X3_LV_ITEMS;           /* elements per thread of a level tile */
+constexpr int LV_CTAS = LV_ITEMS <= 8 ? 6 : 4;  /* resident CTAs per SM the level kernel is built for */
 constexpr int LV_TILE = LV_THREADS * LV_ITEMS;
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
@@ -484,10 +488,11 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_first_kernel(RankArgs a
 		const uint32_t base = tile * LV_TILE;
 		const uint32_t i0 = base + tid * LV_ITEMS;
 		if (i0 + LV_ITEMS <= m) {
-			*reinterpret_cast<uint4 *>(sk + tid * LV_ITEMS) = *reinterpret_cast<const uint4 *>(keyIn + i0);
-			*reinterpret_cast<uint4 *>(sk + tid * LV_ITEMS + 4) = *reinterpret_cast<const uint4 *>(keyIn + i0 + 4);
-			*reinterpret_cast<uint4 *>(sp + tid * LV_ITEMS) = *reinterpret_cast<const uint4 *>(posIn + i0);
-			*reinterpret_cast<uint4 *>(sp + tid * LV_ITEMS + 4) = *reinterpret_cast<const uint4 *>(posIn + i0 + 4);
+#pragma unroll
+			for (int v = 0; v < LV_ITEMS; v += 4) {
+				*reinterpret_cast<uint4 *>(sk + tid * LV_ITEMS + v) = *reinterpret_cast<const uint4 *>(keyIn + i0 + v);
+				*reinterpret_cast<uint4 *>(sp + tid * LV_ITEMS + v) = *reinterpret_cast<const uint4 *>(posIn + i0 + v);
+			}
 		} else {
 #pragma unroll
 			for (int e = 0; e < LV_ITEMS; ++e) {
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_first_kernel(RankArgs a
  * once per position, at the level where it stops passing (or by the level-1 rare path, the
  * flush after the last level, or level 32). */
 template <int LK>
-__global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a, int L, int ticket)
+__global__ void __launch_bounds__(LV_THREADS, LV_CTAS) x3_rank_level_kernel(RankArgs a, int L, int ticket)
 {
 	/* LK = min(L, 4), L >= 2.  Keys of levels 2 and 3 carry the bytes behind the gram in their upper
 	 * bits (level 2: b3 b2 | b0 b1; level 3: b3 | rank16 b2), put there by the position-ordered passes
@@ -628,13 +633,16 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 		}
 		const uint32_t base = tile * LV_TILE;
 		const uint32_t i0 = base + tid * LV_ITEMS;
-		/* my 8 consecutive elements stay in registers; the tile and its look-ahead go to shared memory */
+		/* my LV_ITEMS consecutive elements stay in registers; the tile and its look-ahead go to shared memory */
 		uint32_t k[LV_ITEMS], p[LV_ITEMS];
 		if (i0 + LV_ITEMS <= m) {
-			const uint4 k0 = *reinterpret_cast<const uint4 *>(keyIn + i0), k1 = *reinterpret_cast<const uint4 *>(keyIn + i0 + 4);
-			const uint4 p0 = *reinterpret_cast<const uint4 *>(posIn + i0), p1 = *reinterpret_cast<const uint4 *>(posIn + i0 + 4);
-			k[0] = k0.x; k[1] = k0.y; k[2] = k0.z; k[3] = k0.w; k[4] = k1.x; k[5] = k1.y; k[6] = k1.z; k[7] = k1.w;
-			p[0] = p0.x; p[1] = p0.y; p[2] = p0.z; p[3] = p0.w; p[4] = p1.x; p[5] = p1.y; p[6] = p1.z; p[7] = p1.w;
+#pragma unroll
+			for (int v = 0; v < LV_ITEMS; v += 4) {
+				const uint4 kv = *reinterpret_cast<const uint4 *>(keyIn + i0 + v);
+				const uint4 pv = *reinterpret_cast<const uint4 *>(posIn + i0 + v);
+				k[v] = kv.x; k[v + 1] = kv.y; k[v + 2] = kv.z; k[v + 3] = kv.w;
+				p[v] = pv.x; p[v + 1] = pv.y; p[v + 2] = pv.z; p[v + 3] = pv.w;
+			}
 		} else {
 #pragma unroll
 			for (int e = 0; e < LV_ITEMS; ++e) {
@@ -643,10 +651,11 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 				p[e] = v ? posIn[i0 + e] : 0u;
 			}
 		}
-		*reinterpret_cast<uint4 *>(sk + tid * LV_ITEMS) = make_uint4(k[0], k[1], k[2], k[3]);
-		*reinterpret_cast<uint4 *>(sk + tid * LV_ITEMS + 4) = make_uint4(k[4], k[5], k[6], k[7]);
-		*reinterpret_cast<uint4 *>(sp + tid * LV_ITEMS) = make_uint4(p[0], p[1], p[2], p[3]);
-		*reinterpret_cast<uint4 *>(sp + tid * LV_ITEMS + 4) = make_uint4(p[4], p[5], p[6], p[7]);
+#pragma unroll
+		for (int v = 0; v < LV_ITEMS; v += 4) {
+			*reinterpret_cast<uint4 *>(sk + tid * LV_ITEMS + v) = make_uint4(k[v], k[v + 1], k[v + 2], k[v + 3]);
+			*reinterpret_cast<uint4 *>(sp + tid * LV_ITEMS + v) = make_uint4(p[v], p[v + 1], p[v + 2], p[v + 3]);
+		}
 		if ((uint32_t)tid < la) {
 			const uint32_t i = base + LV_TILE + tid;
 			sk[LV_TILE + tid] = i < m ? keyIn[i] : KEY_NONE;
@@ -682,7 +691,7 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 			continue;
 		}
 		__syncthreads();
-		const uint32_t actm = (actbits[tid >> 2] >> ((tid & 3) * 8)) & 0xffu;
+		const uint32_t actm = (actbits[(tid * LV_ITEMS) >> 5] >> ((tid * LV_ITEMS) & 31)) & ((1u << LV_ITEMS) - 1u);
 		const int mylast = actm != 0 ? (int)i0 + (31 - __clz((int)actm)) : -1;
 		/* last passed element in front of mine; in front of the tile: pretend its neighbour passed
 		 * (a superset of the exact rule, at most t+1 extra elements per tile) */
@@ -725,7 +734,7 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_level_kernel(RankArgs a
 		}
 		/* the byte that extends each kept gram (one gather per element; level 1 has it in the key),
 		 * fetched before the scans so that its latency overlaps them */
-		uint32_t nb[2] = {0u, 0u};
+		uint32_t nb[LV_ITEMS / 4] = {0u};
 #pragma unroll
 		for (int e = 0; e < LV_ITEMS; ++e) {
 			if ((partm >> e) & 1u) {
@@ -1083,8 +1092,21 @@ __global__ void __launch_bounds__(TL_THREADS, 1) x3_rank_tail_kernel(RankArgs a,
 		if (m < la + 1u) {
 			continue; /* the next iteration writes the survivors out and stops */
 		}
-		/* stable LSD radix sort of the survivors by (rank, byte), 8 bits per pass, all in shared memory */
-		const int np = radix_passes(groups);
+		/* stable LSD radix sort of the survivors by (rank, byte), 8 bits per pass, all in shared memory --
+		 * unless they are in that order already (a long run of one byte keeps thousands of elements alive
+		 * through all 32 levels, every one of them followed by the same byte: nothing to sort) */
+		int np = radix_passes(groups);
+		{
+			const uint32_t smask = np >= 4 ? 0xffffffffu : (1u << (8 * np)) - 1u;
+			const uint32_t *NK = TL_K(cur);
+			int unsorted = 0;
+			for (uint32_t i = tid; i + 1 < m; i += TL_THREADS) {
+				unsorted |= (NK[i] & smask) > (NK[i + 1] & smask);
+			}
+			if (__syncthreads_or(unsorted) == 0) {
+				np = 0;
+			}
+		}
 		for (int pass = 0; pass < np; ++pass) {
 			uint32_t *SK = TL_K(cur), *SP = TL_P(cur), *DK = TL_K(cur ^ 1), *DP = TL_P(cur ^ 1);
 			const int shift = 8 * pass;
@@ -1167,6 +1189,8 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t sme
 }
 
 /* ---- per-device scratch ------------------------------------------------------------------ */
+constexpr int RANK_MAX_LANES = 4; /* searches (chunks) of one device that may be in flight at once */
+
 struct RankScratch {
 	uint32_t cap = 0; /* elements */
 	uint32_t *key[2] = {nullptr, nullptr};
@@ -1187,11 +1211,21 @@ struct RankScratch {
 	double prof_elems[4] = {0, 0, 0, 0};  /* elements those launches processed */
 	int prof_launches[4] = {0, 0, 0, 0};
 };
-RankScratch g_rank[64];
+RankScratch g_rank[64][RANK_MAX_LANES];
 
-cudaError_t rank_ensure(int dev, uint32_t M)
+/* streams the lanes of a device-level search (x3k_launch_rank) run on, forked from and joined
+ * back into the caller's stream */
+struct RankLanes {
+	cudaStream_t st[RANK_MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t fork = nullptr;
+	cudaEvent_t join[RANK_MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+	bool made = false;
+};
+RankLanes g_lanes[64];
+
+cudaError_t rank_ensure(int dev, int lane, uint32_t M)
 {
-	RankScratch &s = g_rank[dev];
+	RankScratch &s = g_rank[dev][lane];
 	cudaError_t e;
 	if (s.ctrl == nullptr) {
 		if ((e = cudaMalloc((void **)&s.ctrl, sizeof(RankCtrl))) != cudaSuccess) return e;
@@ -1223,6 +1257,249 @@ cudaError_t rank_ensure(int dev, uint32_t M)
 	return cudaSuccess;
 }
 
+/* what every chunk of one call shares */
+struct RankCfg {
+	uint32_t D;
+	int t;
+	uint32_t lim;     /* fewer elements than this: nobody can pass */
+	bool trace, profile, no_tail, pdl;
+	int lag;          /* levels of work that stay queued while the host waits for a level size (>= 1) */
+};
+
+/* one lane: a job (a position range on a stream) searched chunk by chunk.  Queueing is a
+ * resumable state machine, so that one host thread can keep several lanes fed: a lane that waits
+ * for a level report hands the turn to the next one. */
+struct RankLane {
+	X3RankJob job;
+	int index = 0;
+	RankScratch *s = nullptr;
+	unsigned long long CH = 0;    /* chunk length (positions) */
+	unsigned long long next = 0;  /* first position of the chunk to start next */
+	bool active = false;          /* a chunk is being queued */
+	bool finished = false;
+	RankArgs a;
+	int L = 0;                    /* level about to be queued */
+	int ticket = 0;
+	uint32_t known = 0;           /* upper bound of the size of that level */
+	unsigned spins = 0;
+	int nl = 0;
+};
+
+int rank_grid_for(const RankScratch &s, uint32_t tiles)
+{
+	const uint32_t maxgrid = (uint32_t)s.sms * 8u;
+	return (int)(tiles < maxgrid ? (tiles > 0 ? tiles : 1) : maxgrid);
+}
+
+void rank_mark(const RankCfg &c, RankLane &ln, int kind, int level, int pass)
+{
+	/* profile mode: an event in front of every launch (and one behind the last) */
+	RankScratch &s = *ln.s;
+	if (c.profile && s.npev < 259) {
+		cudaEventRecord(s.pev[s.npev], ln.job.stream);
+		s.pkind[s.npev] = kind;
+		s.plevel[s.npev] = level;
+		s.ppass[s.npev] = pass;
+		++s.npev;
+	}
+}
+
+/* the set-up launches of the lane's next chunk: byte histogram, the two level-2 passes, level 1 */
+cudaError_t rank_chunk_begin(const RankCfg &c, RankLane &ln)
+{
+	cudaError_t e;
+	RankScratch &s = *ln.s;
+	cudaStream_t stream = ln.job.stream;
+	const unsigned long long a0 = ln.next;
+	RankArgs &a = ln.a;
+	a.x = ln.job.x + a0;
+	a.lstar = ln.job.lstar + a0;
+	a.n_out = (uint32_t)(ln.job.n - a0 < ln.CH ? ln.job.n - a0 : ln.CH);
+	a.M = a.n_out + c.D;
+	a.D = c.D;
+	a.t = c.t;
+	a.ctrl = s.ctrl;
+	a.key0 = s.key[0];
+	a.key1 = s.key[1];
+	a.pos0 = s.pos[0];
+	a.pos1 = s.pos[1];
+	a.st_level = s.st_level;
+	a.st_radix = s.st_radix;
+	{
+		void *dp = nullptr;
+		if ((e = cudaHostGetDevicePointer(&dp, s.h_back, 0)) != cudaSuccess) return e;
+		a.report = (volatile uint32_t *)dp;
+	}
+	s.seq = s.seq + 1u == 0u ? 1u : s.seq + 1u;
+	a.seq = s.seq;
+	ln.next = a0 + a.n_out;
+	const uint32_t lv_tiles = (a.M + LV_TILE - 1) / LV_TILE, rs_tiles = (a.M + RS_TILE - 1) / RS_TILE, rs_tiles_small = (a.M + RS_TILE_SMALL - 1) / RS_TILE_SMALL;
+	if ((e = cudaMemsetAsync(s.ctrl, 0, sizeof(RankCtrl), stream)) != cudaSuccess) return e;
+	if ((e = cudaMemsetAsync(s.st_level, 0, (size_t)lv_tiles * 8, stream)) != cudaSuccess) return e;
+	if ((e = cudaMemsetAsync(s.st_radix, 0, (size_t)rs_tiles_small * 256 * 8, stream)) != cudaSuccess) return e;
+	ln.ticket = 0;
+	s.npev = 0;
+	/* Lstar = 1 wherever level 1 passes and nothing deeper does; the level-1 kernel writes the rest */
+	if ((e = cudaMemsetAsync(a.lstar, 1, a.n_out, stream)) != cudaSuccess) return e;
+	rank_mark(c, ln, 2, 1, 0);
+	x3_rank_bytehist_kernel<<<rank_grid_for(s, (a.M + 65535) / 65536), 256, 0, stream>>>(a);
+	/* level 2 is sorted from x by (b0, b1): digit b1 into buffer 1 -- which is also the level-1 order
+	 * of the positions p + 1, tested (and, where the byte is rare, settled) by the first kernel --
+	 * then digit b0 back into buffer 0 */
+	rank_mark(c, ln, 0, 2, 0);
+	const bool small_in = a.M < RS_SMALL_BELOW;
+	if (small_in) {
+		e = launch_pdl(x3_rank_radix_kernel<true, RS_ITEMS_SMALL>, rank_grid_for(s, rs_tiles_small), RS_THREADS, 0, stream, c.pdl, a,
+		               2, 0, ln.ticket, (uint32_t)ln.ticket + 1u);
+	} else {
+		e = launch_pdl(x3_rank_radix_kernel<true, RS_ITEMS>, rank_grid_for(s, rs_tiles), RS_THREADS, 0, stream, c.pdl, a, 2, 0,
+		               ln.ticket, (uint32_t)ln.ticket + 1u);
+	}
+	if (e != cudaSuccess) return e;
+	++ln.ticket;
+	rank_mark(c, ln, 1, 2, 0);
+	if ((e = launch_pdl(x3_rank_first_kernel, rank_grid_for(s, lv_tiles), LV_THREADS, 0, stream, c.pdl, a)) != cudaSuccess) return e;
+	rank_mark(c, ln, 0, 2, 1);
+	if (small_in) {
+		e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS_SMALL>, rank_grid_for(s, rs_tiles_small), RS_THREADS, 0, stream, c.pdl, a,
+		               2, 1, ln.ticket, (uint32_t)ln.ticket + 1u);
+	} else {
+		e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS>, rank_grid_for(s, rs_tiles), RS_THREADS, 0, stream, c.pdl, a, 2, 1,
+		               ln.ticket, (uint32_t)ln.ticket + 1u);
+	}
+	if (e != cudaSuccess) return e;
+	++ln.ticket;
+	ln.nl += 4;
+	ln.known = a.M;
+	ln.L = 2;
+	ln.spins = 0;
+	ln.active = true;
+	return cudaSuccess;
+}
+
+/* the chunk's last launch is queued */
+cudaError_t rank_chunk_end(const RankCfg &c, RankLane &ln)
+{
+	cudaError_t e;
+	RankScratch &s = *ln.s;
+	ln.active = false;
+	if ((e = cudaGetLastError()) != cudaSuccess) return e;
+	if (c.profile) {
+		rank_mark(c, ln, 3, 0, 0);
+		if ((e = cudaStreamSynchronize(ln.job.stream)) != cudaSuccess) return e;
+		RankCtrl *hc = (RankCtrl *)malloc(sizeof(RankCtrl));
+		if (hc == nullptr) return cudaErrorMemoryAllocation;
+		if ((e = cudaMemcpy(hc, s.ctrl, sizeof(RankCtrl), cudaMemcpyDeviceToHost)) != cudaSuccess) {
+			free(hc);
+			return e;
+		}
+		for (int i = 0; i + 1 < s.npev; ++i) {
+			float ms = 0.f;
+			if (cudaEventElapsedTime(&ms, s.pev[i], s.pev[i + 1]) != cudaSuccess) {
+				continue;
+			}
+			/* elements the launch really processed, from the level sizes the device recorded */
+			const int kind = s.pkind[i], lv = s.plevel[i];
+			double el = hc->lv[lv].m;
+			if (kind == 0 && lv > 1 && (hc->lv[lv].m < c.lim || s.ppass[i] >= radix_passes(hc->lv[lv].groups))) {
+				el = 0; /* a pass that returned at once */
+			}
+			s.prof_ms[kind] += ms;
+			s.prof_elems[kind] += el;
+			s.prof_launches[kind] += el > 0 ? 1 : 0;
+		}
+		free(hc);
+	}
+	return cudaSuccess;
+}
+
+/* Queues as much of the lane's current chunk as can be queued without waiting.  *blocked: the
+ * lane waits for the size report of a level that is still running. */
+cudaError_t rank_chunk_step(const RankCfg &c, RankLane &ln, bool *blocked)
+{
+	cudaError_t e;
+	RankScratch &s = *ln.s;
+	RankArgs &a = ln.a;
+	cudaStream_t stream = ln.job.stream;
+	*blocked = false;
+	for (;;) {
+		const int L = ln.L;
+		if (L == 2 && ln.known <= (uint32_t)TL_CAP && !c.no_tail) {
+			/* a small input: every level from 2 on in one launch */
+			rank_mark(c, ln, 1, L, 0);
+			if ((e = launch_pdl(x3_rank_tail_kernel, 1, TL_THREADS, TL_SMEM, stream, c.pdl, a, L)) != cudaSuccess) return e;
+			++ln.nl;
+			return rank_chunk_end(c, ln);
+		}
+		if (L >= 2 + c.lag) {
+			/* lv[L-lag+1] as level L-lag left it: its size bounds level L, and tells whether the levels
+			 * queued since were the last ones */
+			volatile uint32_t *rep = s.h_back + 4 * (L - c.lag);
+			if (rep[2] != a.seq) {
+				if ((++ln.spins & 0xfffffu) == 0u) {
+					/* a kernel that died would never report: do not wait on a failed stream */
+					const cudaError_t q = cudaStreamQuery(stream);
+					if (q != cudaErrorNotReady && rep[2] != a.seq) {
+						return q == cudaSuccess ? cudaErrorUnknown : q;
+					}
+				}
+				*blocked = true;
+				return cudaSuccess;
+			}
+			ln.known = rep[0];
+			if (c.trace) {
+				fprintf(stderr, "x3k_launch_rank: lane %d chunk at %llu level %d: %u elements, %u groups\n", ln.index,
+				        ln.next - a.n_out, L - c.lag + 1, ln.known, s.h_back[4 * (L - c.lag) + 1]);
+			}
+			if (ln.known < c.lim) {
+				return rank_chunk_end(c, ln);
+			}
+			if (ln.known <= (uint32_t)TL_CAP && !c.no_tail) {
+				/* small enough for one CTA: every remaining level in one launch */
+				rank_mark(c, ln, 1, L, 0);
+				if ((e = launch_pdl(x3_rank_tail_kernel, 1, TL_THREADS, TL_SMEM, stream, c.pdl, a, L)) != cudaSuccess) return e;
+				++ln.nl;
+				return rank_chunk_end(c, ln);
+			}
+		}
+		const uint32_t known = ln.known;
+		rank_mark(c, ln, 1, L, 0);
+		const int lgrid = rank_grid_for(s, (known + LV_TILE - 1) / LV_TILE);
+		if (L == 2) {
+			e = launch_pdl(x3_rank_level_kernel<2>, lgrid, LV_THREADS, 0, stream, c.pdl, a, L, ln.ticket);
+		} else if (L == 3) {
+			e = launch_pdl(x3_rank_level_kernel<3>, lgrid, LV_THREADS, 0, stream, c.pdl, a, L, ln.ticket);
+		} else {
+			e = launch_pdl(x3_rank_level_kernel<4>, lgrid, LV_THREADS, 0, stream, c.pdl, a, L, ln.ticket);
+		}
+		if (e != cudaSuccess) return e;
+		++ln.ticket;
+		++ln.nl;
+		if (L == 32) {
+			return rank_chunk_end(c, ln);
+		}
+		/* the level-(L+1) keys have at most min(256^L, known) ranks: queue that many passes; a pass
+		 * the real rank range does not need returns at once */
+		const uint32_t rbound = L == 2 ? (known < 65536u ? known : 65536u) : known;
+		const int np = radix_passes(rbound);
+		for (int pass = 0; pass < np; ++pass) {
+			rank_mark(c, ln, 0, L + 1, pass);
+			/* the tile size only has to be the same within one pass */
+			if (known < RS_SMALL_BELOW) {
+				e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS_SMALL>, rank_grid_for(s, (known + RS_TILE_SMALL - 1) / RS_TILE_SMALL),
+				               RS_THREADS, 0, stream, c.pdl, a, L + 1, pass, ln.ticket, (uint32_t)ln.ticket + 1u);
+			} else {
+				e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS>, rank_grid_for(s, (known + RS_TILE - 1) / RS_TILE), RS_THREADS, 0,
+				               stream, c.pdl, a, L + 1, pass, ln.ticket, (uint32_t)ln.ticket + 1u);
+			}
+			if (e != cudaSuccess) return e;
+			++ln.ticket;
+			++ln.nl;
+		}
+		ln.L = L + 1;
+	}
+}
+
 } /* namespace */
 
 /* largest number of distances the rank search takes (chunks must keep room for positions) */
@@ -1231,23 +1508,39 @@ uint32_t x3k_rank_max_distances(void)
 	return 1u << 23;
 }
 
+int x3k_rank_max_lanes(void)
+{
+	return RANK_MAX_LANES;
+}
+
 void x3k_rank_release(int dev)
 {
-	RankScratch &s = g_rank[dev];
-	for (int j = 0; j < 2; ++j) {
-		cudaFree(s.key[j]);
-		cudaFree(s.pos[j]);
-	}
-	cudaFree(s.st_level);
-	cudaFree(s.st_radix);
-	cudaFree(s.ctrl);
-	cudaFreeHost(s.h_back);
-	if (s.pev_made) {
-		for (int i = 0; i < 520; ++i) {
-			cudaEventDestroy(s.pev[i]);
+	for (int lane = 0; lane < RANK_MAX_LANES; ++lane) {
+		RankScratch &s = g_rank[dev][lane];
+		for (int j = 0; j < 2; ++j) {
+			cudaFree(s.key[j]);
+			cudaFree(s.pos[j]);
 		}
+		cudaFree(s.st_level);
+		cudaFree(s.st_radix);
+		cudaFree(s.ctrl);
+		cudaFreeHost(s.h_back);
+		if (s.pev_made) {
+			for (int i = 0; i < 520; ++i) {
+				cudaEventDestroy(s.pev[i]);
+			}
+		}
+		s = RankScratch();
 	}
-	s = RankScratch();
+	RankLanes &ls = g_lanes[dev];
+	if (ls.made) {
+		for (int j = 0; j < RANK_MAX_LANES; ++j) {
+			cudaStreamDestroy(ls.st[j]);
+			cudaEventDestroy(ls.join[j]);
+		}
+		cudaEventDestroy(ls.fork);
+	}
+	ls = RankLanes();
 }
 
 /* Device time of the last profiled search on `dev` (X3_RANK_PROFILE=1): kind 0 = radix passes,
@@ -1258,7 +1551,7 @@ int x3k_rank_profile(int dev, int kind, double *ms, double *elements, int *launc
 	if (dev < 0 || dev >= 64 || kind < 0 || kind >= 4) {
 		return -1;
 	}
-	const RankScratch &s = g_rank[dev];
+	const RankScratch &s = g_rank[dev][0];
 	*ms = s.prof_ms[kind];
 	*elements = s.prof_elems[kind];
 	*launches = s.prof_launches[kind];
@@ -1266,11 +1559,159 @@ int x3k_rank_profile(int dev, int kind, double *ms, double *elements, int *launc
 }
 
 /*
- * Lstar for positions [0, prm.n) by the rank method.  Everything the levels need to know about
- * each other (sizes, buffers, whether the search is over) lives in device memory, so the launches
- * are simply queued on `stream`; the host only reads the size of level L-1 back before it queues
- * level L (two levels of work stay queued behind that wait), to size the grids and to stop
- * queueing once the search has ended.
+ * Lstar by the rank method for up to RANK_MAX_LANES jobs of the current device at once, job j on
+ * its own stream with its own scratch (lane j).  Everything the levels of a chunk need to know
+ * about each other (sizes, buffers, whether the search is over) lives in device memory, so the
+ * launches are simply queued; the host only reads the size of level L-lag back before it queues
+ * level L (`lag` levels of work stay queued behind that wait), to size the grids and to stop
+ * queueing once the search has ended.  While one lane waits for such a report the others are fed:
+ * the mid-size levels of a chunk are one wave of tiles each, latency and not throughput, and two
+ * chunks in flight fill each other's gaps (and one job's copies overlap another's kernels).
+ */
+cudaError_t x3k_launch_rank_jobs(const X3RankJob *jobs, int njobs, uint32_t D, int t, int *launches)
+{
+	cudaError_t e;
+	if (njobs < 1 || njobs > RANK_MAX_LANES || D > x3k_rank_max_distances() || t > 254) {
+		return cudaErrorNotSupported;
+	}
+	int dev = 0;
+	if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+	if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+	RankCfg c;
+	c.D = D;
+	c.t = t;
+	c.lim = (uint32_t)t + 2u;
+	c.trace = getenv("X3_TRACE") != nullptr;
+	/* the profile mode's events sit between the kernels of one stream: one job only */
+	c.profile = getenv("X3_RANK_PROFILE") != nullptr && njobs == 1;
+	c.no_tail = getenv("X3_RANK_NO_TAIL") != nullptr; /* testing knob: never changes results */
+	/* programmatic dependent launch between the kernels of a chunk; the profile mode keeps plain launches */
+	c.pdl = getenv("X3_RANK_NO_PDL") == nullptr && !c.profile;
+	c.lag = getenv("X3_RANK_LAG") != nullptr && atoi(getenv("X3_RANK_LAG")) >= 1 ? atoi(getenv("X3_RANK_LAG")) : 2;
+	const auto wall0 = std::chrono::steady_clock::now();
+	const unsigned long long CHMAX = (unsigned long long)((RANK_MAX_M - D) & ~4095u);
+
+	RankLane lanes[RANK_MAX_LANES];
+	int open = 0;
+	for (int j = 0; j < njobs; ++j) {
+		RankLane &ln = lanes[j];
+		ln.job = jobs[j];
+		ln.index = j;
+		ln.s = &g_rank[dev][j];
+		if (ln.job.n == 0) {
+			ln.finished = true;
+			continue;
+		}
+		if (t <= 0 || D == 0) {
+			/* backend.c:76 never enters the selection / the window holds no distance: return 1 everywhere */
+			if ((e = cudaMemsetAsync(ln.job.lstar, 0, ln.job.n, ln.job.stream)) != cudaSuccess) return e;
+			ln.finished = true;
+			continue;
+		}
+		/* chunks of equal length, so that ranks and chunk-relative positions fit 24 bits */
+		const unsigned long long nch = (ln.job.n + CHMAX - 1) / CHMAX;
+		ln.CH = (((ln.job.n + nch - 1) / nch) + 4095ull) & ~4095ull;
+		const unsigned long long first = ln.job.n < ln.CH ? ln.job.n : ln.CH;
+		if ((e = rank_ensure(dev, j, (uint32_t)(first + D))) != cudaSuccess) return e;
+		RankScratch &s = *ln.s;
+		if (c.profile && !s.pev_made) {
+			for (int i = 0; i < 520; ++i) {
+				if ((e = cudaEventCreate(&s.pev[i])) != cudaSuccess) return e;
+			}
+			s.pev_made = true;
+		}
+		for (int k = 0; k < 4; ++k) {
+			s.prof_ms[k] = s.prof_elems[k] = 0;
+			s.prof_launches[k] = 0;
+		}
+		++open;
+	}
+	if (c.trace) {
+		fprintf(stderr, "x3k_launch_rank: scratch of %d lane(s) ready after %.3f ms\n", njobs,
+		        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
+	}
+	/* lanes whose job needs no kernels are done already */
+	for (int j = 0; j < njobs; ++j) {
+		if (lanes[j].finished && lanes[j].job.queued != nullptr) {
+			if ((e = lanes[j].job.queued(lanes[j].job.ctx, j)) != cudaSuccess) return e;
+		}
+	}
+	while (open > 0) {
+		bool progress = false;
+		for (int j = 0; j < njobs; ++j) {
+			RankLane &ln = lanes[j];
+			if (ln.finished) {
+				continue;
+			}
+			if (!ln.active) {
+				if (ln.next >= ln.job.n) {
+					ln.finished = true;
+					--open;
+					progress = true;
+					if (ln.job.queued != nullptr && (e = ln.job.queued(ln.job.ctx, j)) != cudaSuccess) return e;
+					continue;
+				}
+				if ((e = rank_chunk_begin(c, ln)) != cudaSuccess) return e;
+				progress = true;
+			}
+			bool blocked = false;
+			if ((e = rank_chunk_step(c, ln, &blocked)) != cudaSuccess) return e;
+			if (!blocked) {
+				progress = true;
+			}
+		}
+		if (!progress) {
+#if defined(__x86_64__) || defined(__i386__)
+			__builtin_ia32_pause(); /* the reports are a few microseconds away: spin politely */
+#endif
+		}
+	}
+	int nl = 0;
+	for (int j = 0; j < njobs; ++j) {
+		nl += lanes[j].nl;
+	}
+	if (launches != nullptr) {
+		*launches += nl;
+	}
+	if (c.trace) {
+		fprintf(stderr, "x3k_launch_rank: %d launches queued after %.3f ms\n", nl,
+		        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
+	}
+	return cudaGetLastError();
+}
+
+/* Lanes a search over n positions is split into when the caller does not say (X3_RANK_LANES
+ * overrides): one per chunk the input needs anyway, at most RANK_MAX_LANES.  Measured on B200
+ * (tests/gpu_lanes_ab.py): the chain of ~40 launches of ONE chunk does not get shorter when the chunk
+ * is halved (C2: 1.00 -> 0.98 ms with twice the launches), but the chains of different chunks overlap
+ * well (60 MB of C5: 12.2 -> 9.0 ms with 4 lanes). */
+int x3k_rank_default_lanes(unsigned long long n, uint32_t D)
+{
+	const char *v = getenv("X3_RANK_LANES");
+	unsigned long long lanes;
+	if (v != nullptr && atoi(v) >= 1) {
+		lanes = (unsigned long long)atoi(v);
+	} else {
+		const unsigned long long chmax = (unsigned long long)((RANK_MAX_M - (D < (1u << 23) ? D : (1u << 23))) & ~4095u);
+		lanes = (n + chmax - 1) / chmax;
+	}
+	if (getenv("X3_RANK_PROFILE") != nullptr) {
+		lanes = 1; /* the profile mode's events bracket the launches of one stream */
+	}
+	if (lanes > (unsigned long long)RANK_MAX_LANES) {
+		lanes = RANK_MAX_LANES;
+	}
+	/* lanes start at multiples of 4096 positions; tiny inputs are not split */
+	while (lanes > 1 && n / lanes < 65536ull) {
+		--lanes;
+	}
+	return lanes < 1 ? 1 : (int)lanes;
+}
+
+/*
+ * Lstar for positions [0, prm.n) of a device-resident buffer, ordered behind `stream` and
+ * complete when `stream` reaches the point where this returns: the position range is cut into
+ * lanes that run on streams of their own, forked from and joined back into `stream`.
  */
 cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int *launches)
 {
@@ -1281,225 +1722,47 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 	if (prm.n == 0) {
 		return cudaSuccess;
 	}
-	if (prm.t <= 0 || prm.D == 0) {
-		/* backend.c:76 never enters the selection / the window holds no distance: return 1 everywhere */
-		return cudaMemsetAsync(prm.lstar, 0, prm.n, stream);
+	const int lanes = x3k_rank_default_lanes(prm.n, prm.D);
+	X3RankJob jobs[RANK_MAX_LANES];
+	if (lanes == 1) {
+		jobs[0].x = prm.x;
+		jobs[0].lstar = prm.lstar;
+		jobs[0].n = prm.n;
+		jobs[0].stream = stream;
+		jobs[0].queued = nullptr;
+		jobs[0].ctx = nullptr;
+		return x3k_launch_rank_jobs(jobs, 1, prm.D, prm.t, launches);
 	}
 	int dev = 0;
 	if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
-	const bool trace = getenv("X3_TRACE") != nullptr;
-	const bool profile = getenv("X3_RANK_PROFILE") != nullptr;
-	const bool no_tail = getenv("X3_RANK_NO_TAIL") != nullptr; /* testing knob: never changes results */
-	const uint32_t small_below = RS_SMALL_BELOW;
-	/* programmatic dependent launch between the kernels of a chunk; the profile mode's events would
-	 * sit between the kernels, so it keeps plain launches */
-	const bool pdl = getenv("X3_RANK_NO_PDL") == nullptr && !profile;
-	/* levels of work that stay queued while the host waits for a level size (>= 1) */
-	const int lag = getenv("X3_RANK_LAG") != nullptr && atoi(getenv("X3_RANK_LAG")) >= 1 ? atoi(getenv("X3_RANK_LAG")) : 2;
-	const uint32_t D = prm.D;
-	const unsigned long long CH = (unsigned long long)((RANK_MAX_M - D) & ~4095u);
-	const unsigned long long first = prm.n < CH ? prm.n : CH;
-	const auto wall0 = std::chrono::steady_clock::now();
-	if ((e = rank_ensure(dev, (uint32_t)(first + D))) != cudaSuccess) return e;
-	RankScratch &s = g_rank[dev];
-	if (trace) {
-		fprintf(stderr, "x3k_launch_rank: scratch for %llu elements ready after %.3f ms\n", first + D,
-		        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
+	if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+	RankLanes &ls = g_lanes[dev];
+	if (!ls.made) {
+		if ((e = cudaEventCreateWithFlags(&ls.fork, cudaEventDisableTiming)) != cudaSuccess) return e;
+		for (int j = 0; j < RANK_MAX_LANES; ++j) {
+			if ((e = cudaStreamCreateWithFlags(&ls.st[j], cudaStreamNonBlocking)) != cudaSuccess) return e;
+			if ((e = cudaEventCreateWithFlags(&ls.join[j], cudaEventDisableTiming)) != cudaSuccess) return e;
+		}
+		ls.made = true;
 	}
-	if (profile && !s.pev_made) {
-		for (int i = 0; i < 520; ++i) {
-			if ((e = cudaEventCreate(&s.pev[i])) != cudaSuccess) return e;
-		}
-		s.pev_made = true;
+	if ((e = cudaEventRecord(ls.fork, stream)) != cudaSuccess) return e;
+	for (int j = 0; j < lanes; ++j) {
+		unsigned long long lo = (unsigned long long)((unsigned __int128)prm.n * j / lanes) & ~4095ull;
+		unsigned long long hi = j + 1 == lanes ? prm.n : (unsigned long long)((unsigned __int128)prm.n * (j + 1) / lanes) & ~4095ull;
+		jobs[j].x = prm.x + lo;
+		jobs[j].lstar = prm.lstar + lo;
+		jobs[j].n = hi - lo;
+		jobs[j].stream = ls.st[j];
+		jobs[j].queued = nullptr;
+		jobs[j].ctx = nullptr;
+		if ((e = cudaStreamWaitEvent(ls.st[j], ls.fork, 0)) != cudaSuccess) return e;
 	}
-	for (int k = 0; k < 4; ++k) {
-		s.prof_ms[k] = s.prof_elems[k] = 0;
-		s.prof_launches[k] = 0;
-	}
-	int nl = 0;
-	const uint32_t lim = (uint32_t)prm.t + 2u; /* fewer elements than this: nobody can pass */
-
-	for (unsigned long long a0 = 0; a0 < prm.n; a0 += CH) {
-		RankArgs a;
-		a.x = prm.x + a0;
-		a.lstar = prm.lstar + a0;
-		a.n_out = (uint32_t)(prm.n - a0 < CH ? prm.n - a0 : CH);
-		a.M = a.n_out + D;
-		a.D = D;
-		a.t = prm.t;
-		a.ctrl = s.ctrl;
-		a.key0 = s.key[0];
-		a.key1 = s.key[1];
-		a.pos0 = s.pos[0];
-		a.pos1 = s.pos[1];
-		a.st_level = s.st_level;
-		a.st_radix = s.st_radix;
-		{
-			void *dp = nullptr;
-			if ((e = cudaHostGetDevicePointer(&dp, s.h_back, 0)) != cudaSuccess) return e;
-			a.report = (volatile uint32_t *)dp;
-		}
-		s.seq = s.seq + 1u == 0u ? 1u : s.seq + 1u;
-		a.seq = s.seq;
-		const uint32_t lv_tiles = (a.M + LV_TILE - 1) / LV_TILE, rs_tiles = (a.M + RS_TILE - 1) / RS_TILE, rs_tiles_small = (a.M + RS_TILE_SMALL - 1) / RS_TILE_SMALL;
-		if ((e = cudaMemsetAsync(s.ctrl, 0, sizeof(RankCtrl), stream)) != cudaSuccess) return e;
-		if ((e = cudaMemsetAsync(s.st_level, 0, (size_t)lv_tiles * 8, stream)) != cudaSuccess) return e;
-		if ((e = cudaMemsetAsync(s.st_radix, 0, (size_t)rs_tiles_small * 256 * 8, stream)) != cudaSuccess) return e;
-		int ticket = 0;
-		const int maxgrid = s.sms * 8;
-		auto grid_for = [&](uint32_t tiles) { return (int)(tiles < (uint32_t)maxgrid ? (tiles > 0 ? tiles : 1) : maxgrid); };
-		s.npev = 0;
-		auto mark = [&](int kind, int level, int pass) {
-			/* profile mode: an event in front of every launch (and one behind the last) */
-			if (profile && s.npev < 259) {
-				cudaEventRecord(s.pev[s.npev], stream);
-				s.pkind[s.npev] = kind;
-				s.plevel[s.npev] = level;
-				s.ppass[s.npev] = pass;
-				++s.npev;
-			}
-		};
-
-		/* Lstar = 1 wherever level 1 passes and nothing deeper does; the level-1 kernel writes the rest */
-		if ((e = cudaMemsetAsync(a.lstar, 1, a.n_out, stream)) != cudaSuccess) return e;
-		mark(2, 1, 0);
-		x3_rank_bytehist_kernel<<<grid_for((a.M + 65535) / 65536), 256, 0, stream>>>(a);
-		/* level 2 is sorted from x by (b0, b1): digit b1 into buffer 1 -- which is also the level-1 order
-		 * of the positions p + 1, tested (and, where the byte is rare, settled) by the first kernel --
-		 * then digit b0 back into buffer 0 */
-		mark(0, 2, 0);
-		const bool small_in = a.M < small_below;
-		if (small_in) {
-			e = launch_pdl(x3_rank_radix_kernel<true, RS_ITEMS_SMALL>, grid_for(rs_tiles_small), RS_THREADS, 0, stream, pdl, a, 2,
-			               0, ticket, (uint32_t)ticket + 1u);
-		} else {
-			e = launch_pdl(x3_rank_radix_kernel<true, RS_ITEMS>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 2, 0, ticket,
-			               (uint32_t)ticket + 1u);
-		}
-		if (e != cudaSuccess) return e;
-		++ticket;
-		mark(1, 2, 0);
-		if ((e = launch_pdl(x3_rank_first_kernel, grid_for(lv_tiles), LV_THREADS, 0, stream, pdl, a)) != cudaSuccess) return e;
-		mark(0, 2, 1);
-		if (small_in) {
-			e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS_SMALL>, grid_for(rs_tiles_small), RS_THREADS, 0, stream, pdl, a, 2,
-			               1, ticket, (uint32_t)ticket + 1u);
-		} else {
-			e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS>, grid_for(rs_tiles), RS_THREADS, 0, stream, pdl, a, 2, 1, ticket,
-			               (uint32_t)ticket + 1u);
-		}
-		if (e != cudaSuccess) return e;
-		++ticket;
-		nl += 4;
-		uint32_t known = a.M; /* upper bound of the size of the level about to be queued */
-		for (int L = 2; L <= 32; ++L) {
-			if (L == 2 && known <= (uint32_t)TL_CAP && !no_tail) {
-				/* a small input: every level from 2 on in one launch */
-				mark(1, L, 0);
-				if ((e = launch_pdl(x3_rank_tail_kernel, 1, TL_THREADS, TL_SMEM, stream, pdl, a, L)) != cudaSuccess) return e;
-				++nl;
-				break;
-			}
-			if (L >= 2 + lag) {
-				/* lv[L-lag+1] as level L-lag left it: its size bounds level L, and tells whether the levels
-				 * queued since were the last ones */
-				volatile uint32_t *rep = s.h_back + 4 * (L - lag);
-				for (unsigned spins = 0; rep[2] != a.seq; ++spins) {
-#if defined(__x86_64__) || defined(__i386__)
-					__builtin_ia32_pause(); /* the report is a few microseconds away: spin politely */
-#endif
-					if ((spins & 0xfffffu) == 0xfffffu) {
-						/* a kernel that died would never report: do not spin on a failed stream */
-						const cudaError_t q = cudaStreamQuery(stream);
-						if (q != cudaErrorNotReady && rep[2] != a.seq) {
-							return q == cudaSuccess ? cudaErrorUnknown : q;
-						}
-					}
-				}
-				known = rep[0];
-				if (trace) {
-					fprintf(stderr, "x3k_launch_rank: chunk %llu level %d: %u elements, %u groups\n", a0 / CH, L - lag + 1,
-					        known, s.h_back[4 * (L - lag) + 1]);
-				}
-				if (known < lim) {
-					break;
-				}
-				if (known <= (uint32_t)TL_CAP && !no_tail) {
-					/* small enough for one CTA: every remaining level in one launch */
-					mark(1, L, 0);
-					if ((e = launch_pdl(x3_rank_tail_kernel, 1, TL_THREADS, TL_SMEM, stream, pdl, a, L)) != cudaSuccess) return e;
-					++nl;
-					break;
-				}
-			}
-			mark(1, L, 0);
-			const int lgrid = grid_for((known + LV_TILE - 1) / LV_TILE);
-			if (L == 2) {
-				e = launch_pdl(x3_rank_level_kernel<2>, lgrid, LV_THREADS, 0, stream, pdl, a, L, ticket);
-			} else if (L == 3) {
-				e = launch_pdl(x3_rank_level_kernel<3>, lgrid, LV_THREADS, 0, stream, pdl, a, L, ticket);
-			} else {
-				e = launch_pdl(x3_rank_level_kernel<4>, lgrid, LV_THREADS, 0, stream, pdl, a, L, ticket);
-			}
-			if (e != cudaSuccess) return e;
-			++ticket;
-			++nl;
-			if (L == 32) {
-				break;
-			}
-			/* the level-(L+1) keys have at most min(256^L, known) ranks: queue that many passes; a pass
-			 * the real rank range does not need returns at once */
-			const uint32_t rbound = L == 1 ? (known < 256u ? known : 256u) : (L == 2 ? (known < 65536u ? known : 65536u) : known);
-			const int np = radix_passes(rbound);
-			for (int pass = 0; pass < np; ++pass) {
-				mark(0, L + 1, pass);
-				/* the tile size only has to be the same within one pass */
-				if (known < small_below) {
-					e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS_SMALL>, grid_for((known + RS_TILE_SMALL - 1) / RS_TILE_SMALL),
-					               RS_THREADS, 0, stream, pdl, a, L + 1, pass, ticket, (uint32_t)ticket + 1u);
-				} else {
-					e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS>, grid_for((known + RS_TILE - 1) / RS_TILE), RS_THREADS, 0,
-					               stream, pdl, a, L + 1, pass, ticket, (uint32_t)ticket + 1u);
-				}
-				if (e != cudaSuccess) return e;
-				++ticket;
-				++nl;
-			}
-		}
-		if ((e = cudaGetLastError()) != cudaSuccess) return e;
-		if (profile) {
-			mark(3, 0, 0);
-			if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
-			RankCtrl *hc = (RankCtrl *)malloc(sizeof(RankCtrl));
-			if (hc == nullptr) return cudaErrorMemoryAllocation;
-			if ((e = cudaMemcpy(hc, s.ctrl, sizeof(RankCtrl), cudaMemcpyDeviceToHost)) != cudaSuccess) {
-				free(hc);
-				return e;
-			}
-			for (int i = 0; i + 1 < s.npev; ++i) {
-				float ms = 0.f;
-				if (cudaEventElapsedTime(&ms, s.pev[i], s.pev[i + 1]) != cudaSuccess) {
-					continue;
-				}
-				/* elements the launch really processed, from the level sizes the device recorded */
-				const int kind = s.pkind[i], lv = s.plevel[i];
-				double el = hc->lv[lv].m;
-				if (kind == 0 && lv > 1 && (hc->lv[lv].m < lim || s.ppass[i] >= radix_passes(hc->lv[lv].groups))) {
-					el = 0; /* a pass that returned at once */
-				}
-				s.prof_ms[kind] += ms;
-				s.prof_elems[kind] += el;
-				s.prof_launches[kind] += el > 0 ? 1 : 0;
-			}
-			free(hc);
+	e = x3k_launch_rank_jobs(jobs, lanes, prm.D, prm.t, launches);
+	/* the caller's stream continues behind every lane, also when queueing failed half way */
+	for (int j = 0; j < lanes; ++j) {
+		if (cudaEventRecord(ls.join[j], ls.st[j]) == cudaSuccess) {
+			cudaStreamWaitEvent(stream, ls.join[j], 0);
 		}
 	}
-	if (launches != nullptr) {
-		*launches += nl;
-	}
-	if (trace) {
-		fprintf(stderr, "x3k_launch_rank: %d launches queued after %.3f ms\n", nl,
-		        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
-	}
-	return cudaGetLastError();
+	return e;
 }
