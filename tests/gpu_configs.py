@@ -22,6 +22,8 @@ pkg = g.load_package()
 corpus = g.load_submodule("corpus")
 CFG = {"C2": (None, 8192, 15), "C3": (50_000_000, 1 << 20, 64), "C4": (None, 8192, 15), "C5": (None, 8192, 15)}
 names = sys.argv[1].split(",") if len(sys.argv) > 1 else ["C2", "C3", "C4", "C5"]
+PREV_FILE = ROOT / "profiles" / "r1_rank_configs.json"
+PREV = json.loads(PREV_FILE.read_text()) if PREV_FILE.exists() else {}
 out = {}
 for name in names:
     size, W, t = CFG[name]
@@ -31,7 +33,7 @@ for name in names:
     gen_s = time.time() - t0
     best = None
     for rep in range(3):
-        ls, _, tm = pkg.search_host(data, W=W, t=t, ngpus=1, variant=pkg.KERNEL_DEFAULT)
+        ls, _, tm = pkg.search_host(data, W=W, t=t, ngpus=1, variant=pkg.KERNEL_DEFAULT, pinned=True)
         if best is None or tm.kernel_ms < best[0]:
             best = (tm.kernel_ms, tm.total_ms, tm.h2d_ms, tm.d2h_ms, tm.launches)
     rec = {"bytes": n, "W": W, "t": t, "kernel_ms": best[0], "total_ms": best[1], "h2d_ms": best[2], "d2h_ms": best[3],
@@ -45,6 +47,9 @@ for name in names:
         _, ref = ol.table(data, W, t, p0=a, p1=a + m)
         ok = ok and bool(np.array_equal(ls[a:a + m], ref))
     rec["oracle_bands_ok"] = ok
+    if name in PREV:
+        # the table recorded by the earlier build of the round (other chunking, no lanes): same bytes
+        rec["same_table_as_recorded"] = PREV[name].get("lstar_sha256") == rec["lstar_sha256"]
     if W <= 65536 and n <= 60_000_000:
         bf, _, tmb = pkg.search_host(data, W=W, t=t, ngpus=1, variant=pkg.KERNEL_STREAM)
         rec["equals_brute_force"] = bool(np.array_equal(bf, ls))

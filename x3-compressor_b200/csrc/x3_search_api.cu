@@ -54,31 +54,51 @@ struct DevState {
 	size_t cap_l = 0;
 	uint8_t *d_h = nullptr;
 	size_t cap_h = 0;
-	/* pipelined shard (rank search in pieces): a stream per piece and, per piece, the events
-	 * "upload done", "search done", "Lstar back" */
+	/* pipelined shard (rank search, page-locked host buffers): the upload goes chunk by chunk on
+	 * `stream` with an event behind every chunk, the chunks are searched on lane streams, and each
+	 * chunk's Lstar goes back on its lane's stream */
 	cudaStream_t ps[X3S_MAX_PIECES] = {nullptr, nullptr, nullptr, nullptr};
-	cudaEvent_t pev[X3S_MAX_PIECES][3] = {};
+	cudaEvent_t pev[X3S_MAX_PIECES][2] = {}; /* per lane: last search queued so far done, its Lstar back */
+	std::vector<cudaEvent_t> upev;           /* per chunk: uploaded */
 	bool pinited = false;
-	int pieces = 1;  /* pieces of the last search on this device */
-	int pfirst = 0;  /* piece whose upload lets the first search start */
+	int pieces = 1;  /* lanes of the last search on this device */
+	int pfirst = 0;  /* chunk whose upload lets the first search start */
 };
 
-/* what the rank search's "last kernel of this job is queued" callback needs to bring the piece back */
+/* what the rank search's per-chunk hooks need */
 struct PieceCtx {
 	DevState *ds;
-	uint8_t *h_lstar;       /* host destination of the shard */
-	size_t lo[X3S_MAX_PIECES + 1]; /* piece p = shard positions [lo[p], lo[p+1]) */
+	uint8_t *h_lstar;        /* host destination of the shard */
+	unsigned long long CH;   /* chunk length */
+	unsigned long long nch;
+	size_t W;
 };
 
-cudaError_t piece_queued(void *vctx, int p)
+/* the lane's stream waits for the upload that brings the last byte the chunk reads */
+cudaError_t piece_before(void *vctx, int lane, unsigned long long a0, unsigned long long len)
+{
+	PieceCtx *c = (PieceCtx *)vctx;
+	DevState &ds = *c->ds;
+	const unsigned long long last = a0 + x3k_required_bytes((size_t)len, c->W) - 1;
+	unsigned long long q = last / c->CH;
+	if (q >= c->nch) {
+		q = c->nch - 1;
+	}
+	if (a0 == 0) {
+		ds.pfirst = (int)q;
+	}
+	return cudaStreamWaitEvent(ds.ps[lane], ds.upev[(size_t)q], 0);
+}
+
+/* the chunk's last kernel is queued: its Lstar goes back behind it */
+cudaError_t piece_after(void *vctx, int lane, unsigned long long a0, unsigned long long len)
 {
 	PieceCtx *c = (PieceCtx *)vctx;
 	DevState &ds = *c->ds;
 	cudaError_t e;
-	if ((e = cudaEventRecord(ds.pev[p][1], ds.ps[p])) != cudaSuccess) return e;
-	if ((e = cudaMemcpyAsync(c->h_lstar + c->lo[p], ds.d_l + c->lo[p], c->lo[p + 1] - c->lo[p], cudaMemcpyDeviceToHost,
-	                         ds.ps[p])) != cudaSuccess) return e;
-	return cudaEventRecord(ds.pev[p][2], ds.ps[p]);
+	if ((e = cudaEventRecord(ds.pev[lane][0], ds.ps[lane])) != cudaSuccess) return e;
+	if ((e = cudaMemcpyAsync(c->h_lstar + a0, ds.d_l + a0, (size_t)len, cudaMemcpyDeviceToHost, ds.ps[lane])) != cudaSuccess) return e;
+	return cudaEventRecord(ds.pev[lane][1], ds.ps[lane]);
 }
 
 /* Per-device scratch of the stream kernel (tile counter + deep histogram rows).
@@ -349,13 +369,13 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 		}
 		ds.pieces = P;
 		if (P > 1) {
-			/* Pipelined shard: the upload goes piece by piece on ds.stream, piece p is searched on its own
-			 * stream as soon as the bytes it reads (its positions and the window behind them) have
-			 * arrived, and its Lstar goes back while the pieces behind it are still being searched. */
+			/* Pipelined shard: the upload goes chunk by chunk on ds.stream, a chunk is searched on the next
+			 * free lane as soon as the bytes it reads (its positions and the window behind them) have
+			 * arrived, and its Lstar goes back while the chunks behind it are still being searched. */
 			if (!ds.pinited) {
 				for (int p = 0; p < X3S_MAX_PIECES; ++p) {
 					CU_TRY(cudaStreamCreateWithFlags(&ds.ps[p], cudaStreamNonBlocking));
-					for (int k = 0; k < 3; ++k) {
+					for (int k = 0; k < 2; ++k) {
 						CU_TRY(cudaEventCreate(&ds.pev[p][k]));
 					}
 				}
@@ -364,49 +384,46 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 			PieceCtx ctx;
 			ctx.ds = &ds;
 			ctx.h_lstar = (uint8_t *)lstar + a[g];
-			for (int p = 0; p <= P; ++p) {
-				ctx.lo[p] = p == P ? np : ((size_t)((unsigned __int128)np * p / P) & ~(size_t)4095);
+			ctx.W = W;
+			x3k_rank_chunking(np, D, P, &ctx.CH, &ctx.nch);
+			while (ds.upev.size() < ctx.nch) {
+				cudaEvent_t ev = nullptr;
+				CU_TRY(cudaEventCreate(&ev));
+				ds.upev.push_back(ev);
 			}
 			Scratch &sc = g_scratch[dev];
 			CU_TRY(cudaStreamWaitEvent(ds.stream, sc.last, 0));
 			CU_TRY(cudaEventRecord(ds.ev[0], ds.stream));
-			for (int p = 0; p < P; ++p) {
-				/* bytes [lo[p], lo[p+1]) of the shard; the last piece brings the halo and the zeroed slack */
-				const size_t b0 = ctx.lo[p], b1 = p + 1 == P ? have : ctx.lo[p + 1];
+			for (unsigned long long q = 0; q < ctx.nch; ++q) {
+				/* bytes of chunk q; the last upload brings the halo and is followed by the zeroed slack */
+				const size_t b0 = (size_t)(q * ctx.CH), b1 = q + 1 == ctx.nch ? have : (size_t)((q + 1) * ctx.CH);
 				CU_TRY(cudaMemcpyAsync(ds.d_x + b0, (const uint8_t *)x + a[g] + b0, b1 - b0, cudaMemcpyHostToDevice, ds.stream));
-				if (p + 1 == P && need > have) {
+				if (q + 1 == ctx.nch && need > have) {
 					CU_TRY(cudaMemsetAsync(ds.d_x + have, 0, need - have, ds.stream));
 				}
-				CU_TRY(cudaEventRecord(ds.pev[p][0], ds.stream));
+				CU_TRY(cudaEventRecord(ds.upev[(size_t)q], ds.stream));
 			}
 			CU_TRY(cudaEventRecord(ds.ev[1], ds.stream));
-			X3RankJob jobs[X3S_MAX_PIECES];
+			X3RankBatch b;
+			b.x = ds.d_x;
+			b.lstar = ds.d_l;
+			b.n = np;
+			b.lanes = P;
 			for (int p = 0; p < P; ++p) {
-				jobs[p].x = ds.d_x + ctx.lo[p];
-				jobs[p].lstar = ds.d_l + ctx.lo[p];
-				jobs[p].n = ctx.lo[p + 1] - ctx.lo[p];
-				jobs[p].stream = ds.ps[p];
-				jobs[p].queued = piece_queued;
-				jobs[p].ctx = &ctx;
-				/* the piece reads x3k_required_bytes() behind its start: wait for the upload that brings the last of them */
-				const size_t last = ctx.lo[p] + x3k_required_bytes(jobs[p].n, W) - 1;
-				int q = p;
-				while (q + 1 < P && ctx.lo[q + 1] <= last) {
-					++q;
-				}
-				if (p == 0) {
-					ds.pfirst = q;
-				}
-				CU_TRY(cudaStreamWaitEvent(ds.ps[p], ds.pev[q][0], 0));
+				b.streams[p] = ds.ps[p];
+				/* lanes that get no chunk (or whose hooks never run) still have recorded events to wait on and time */
+				CU_TRY(cudaStreamWaitEvent(ds.ps[p], ds.ev[0], 0));
+				CU_TRY(cudaEventRecord(ds.pev[p][0], ds.ps[p]));
+				CU_TRY(cudaEventRecord(ds.pev[p][1], ds.ps[p]));
 			}
-			const cudaError_t je = x3k_launch_rank_jobs(jobs, P, D, t, &shard_launches[g]);
+			b.before_chunk = piece_before;
+			b.after_chunk = piece_after;
+			b.ctx = &ctx;
+			CU_TRY(x3k_launch_rank_batch(b, D, t, &shard_launches[g]));
 			for (int p = 0; p < P; ++p) {
-				/* ds.stream (and with it the device's next search) continues behind every piece */
-				if (je == cudaSuccess) {
-					CU_TRY(cudaStreamWaitEvent(ds.stream, ds.pev[p][2], 0));
-				}
+				/* ds.stream (and with it the device's next search) continues behind every lane */
+				CU_TRY(cudaStreamWaitEvent(ds.stream, ds.pev[p][1], 0));
 			}
-			CU_TRY(je);
 			CU_TRY(cudaEventRecord(ds.ev[3], ds.stream));
 			CU_TRY(cudaEventRecord(sc.last, ds.stream));
 			return X3S_OK;
@@ -486,10 +503,10 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 			/* pipelined shard: the three figures split the critical path -- upload until the first search
 			 * can start, from there to the end of the last search, from there to the last byte back */
 			float up = 0.f, all = 0.f, kend = 0.f;
-			CU_TRY(cudaEventElapsedTime(&up, ds.ev[0], ds.pev[ds.pfirst][0]));
+			CU_TRY(cudaEventElapsedTime(&up, ds.ev[0], ds.upev[(size_t)ds.pfirst]));
 			CU_TRY(cudaEventElapsedTime(&all, ds.ev[0], ds.ev[3]));
 			for (int p = 0; p < ds.pieces; ++p) {
-				CU_TRY(cudaEventElapsedTime(&ms, ds.ev[0], ds.pev[p][1]));
+				CU_TRY(cudaEventElapsedTime(&ms, ds.ev[0], ds.pev[p][0]));
 				if (ms > kend) kend = ms;
 			}
 			if (up > tm.h2d_ms) tm.h2d_ms = up;
@@ -579,10 +596,13 @@ void x3s_release(void)
 		if (ds.pinited) {
 			for (int p = 0; p < X3S_MAX_PIECES; ++p) {
 				cudaStreamDestroy(ds.ps[p]);
-				for (int k = 0; k < 3; ++k) {
+				for (int k = 0; k < 2; ++k) {
 					cudaEventDestroy(ds.pev[p][k]);
 				}
 			}
+		}
+		for (cudaEvent_t ev : ds.upev) {
+			cudaEventDestroy(ev);
 		}
 		ds = DevState();
 		if (g < 64 && g_kernel_inited[g]) {

@@ -43,19 +43,24 @@ cudaError_t x3k_launch(int variant, const X3SearchParams &prm, cudaStream_t stre
  * cudaErrorNotSupported when H is requested. */
 cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int *launches);
 
-/* The same for up to x3k_rank_max_lanes() independent position ranges of the current device at
- * once, each on a stream of the caller's (no fork/join): one host thread keeps all of them fed.
- * `queued` is called as soon as the job's last kernel is queued on its stream (the API layer
- * queues the job's D2H copy there, while the other jobs are still being queued). */
-struct X3RankJob {
+/* The same with the lanes spelled out: positions [0, n) are searched chunk by chunk
+ * (x3k_rank_chunking), each chunk on the next free of `lanes` streams of the caller's (no
+ * fork/join), one host thread keeping all of them fed.  before_chunk is called before the first
+ * launch of a chunk is queued on its lane's stream (the API layer makes the stream wait for the
+ * upload of the bytes the chunk reads), after_chunk as soon as its last kernel is queued (the API
+ * layer queues the copy back of the chunk's Lstar there, while other chunks are still searched). */
+struct X3RankBatch {
 	const uint8_t *x;      /* device, 16-byte aligned, x3k_required_bytes(n, W) readable */
 	uint8_t *lstar;        /* n bytes */
 	unsigned long long n;
-	cudaStream_t stream;
-	cudaError_t (*queued)(void *ctx, int job);
+	int lanes;             /* 1 .. x3k_rank_max_lanes() */
+	cudaStream_t streams[4];
+	cudaError_t (*before_chunk)(void *ctx, int lane, unsigned long long a0, unsigned long long len);
+	cudaError_t (*after_chunk)(void *ctx, int lane, unsigned long long a0, unsigned long long len);
 	void *ctx;
 };
-cudaError_t x3k_launch_rank_jobs(const X3RankJob *jobs, int njobs, uint32_t D, int t, int *launches);
+cudaError_t x3k_launch_rank_batch(const X3RankBatch &b, uint32_t D, int t, int *launches);
+void x3k_rank_chunking(unsigned long long n, uint32_t D, int lanes, unsigned long long *chunk, unsigned long long *count);
 int x3k_rank_max_lanes(void);
 int x3k_rank_default_lanes(unsigned long long n, uint32_t D); /* X3_RANK_LANES, else one per chunk */
 uint32_t x3k_rank_max_distances(void);

@@ -1266,15 +1266,15 @@ struct RankCfg {
 	int lag;          /* levels of work that stay queued while the host waits for a level size (>= 1) */
 };
 
-/* one lane: a job (a position range on a stream) searched chunk by chunk.  Queueing is a
- * resumable state machine, so that one host thread can keep several lanes fed: a lane that waits
- * for a level report hands the turn to the next one. */
+/* one lane: a stream with scratch of its own that takes the batch's chunks one after the other.
+ * Queueing is a resumable state machine, so that one host thread can keep several lanes fed: a
+ * lane that waits for a level report hands the turn to the next one. */
 struct RankLane {
-	X3RankJob job;
+	const X3RankBatch *b = nullptr;
+	cudaStream_t stream = nullptr;
 	int index = 0;
 	RankScratch *s = nullptr;
-	unsigned long long CH = 0;    /* chunk length (positions) */
-	unsigned long long next = 0;  /* first position of the chunk to start next */
+	unsigned long long a0 = 0;    /* first position of the chunk being queued */
 	bool active = false;          /* a chunk is being queued */
 	bool finished = false;
 	RankArgs a;
@@ -1296,7 +1296,7 @@ void rank_mark(const RankCfg &c, RankLane &ln, int kind, int level, int pass)
 	/* profile mode: an event in front of every launch (and one behind the last) */
 	RankScratch &s = *ln.s;
 	if (c.profile && s.npev < 259) {
-		cudaEventRecord(s.pev[s.npev], ln.job.stream);
+		cudaEventRecord(s.pev[s.npev], ln.stream);
 		s.pkind[s.npev] = kind;
 		s.plevel[s.npev] = level;
 		s.ppass[s.npev] = pass;
@@ -1304,17 +1304,17 @@ void rank_mark(const RankCfg &c, RankLane &ln, int kind, int level, int pass)
 	}
 }
 
-/* the set-up launches of the lane's next chunk: byte histogram, the two level-2 passes, level 1 */
-cudaError_t rank_chunk_begin(const RankCfg &c, RankLane &ln)
+/* the set-up launches of a chunk [a0, a0 + len): byte histogram, the two level-2 passes, level 1 */
+cudaError_t rank_chunk_begin(const RankCfg &c, RankLane &ln, unsigned long long a0, unsigned long long len)
 {
 	cudaError_t e;
 	RankScratch &s = *ln.s;
-	cudaStream_t stream = ln.job.stream;
-	const unsigned long long a0 = ln.next;
+	cudaStream_t stream = ln.stream;
 	RankArgs &a = ln.a;
-	a.x = ln.job.x + a0;
-	a.lstar = ln.job.lstar + a0;
-	a.n_out = (uint32_t)(ln.job.n - a0 < ln.CH ? ln.job.n - a0 : ln.CH);
+	ln.a0 = a0;
+	a.x = ln.b->x + a0;
+	a.lstar = ln.b->lstar + a0;
+	a.n_out = (uint32_t)len;
 	a.M = a.n_out + c.D;
 	a.D = c.D;
 	a.t = c.t;
@@ -1332,7 +1332,6 @@ cudaError_t rank_chunk_begin(const RankCfg &c, RankLane &ln)
 	}
 	s.seq = s.seq + 1u == 0u ? 1u : s.seq + 1u;
 	a.seq = s.seq;
-	ln.next = a0 + a.n_out;
 	const uint32_t lv_tiles = (a.M + LV_TILE - 1) / LV_TILE, rs_tiles = (a.M + RS_TILE - 1) / RS_TILE, rs_tiles_small = (a.M + RS_TILE_SMALL - 1) / RS_TILE_SMALL;
 	if ((e = cudaMemsetAsync(s.ctrl, 0, sizeof(RankCtrl), stream)) != cudaSuccess) return e;
 	if ((e = cudaMemsetAsync(s.st_level, 0, (size_t)lv_tiles * 8, stream)) != cudaSuccess) return e;
@@ -1386,7 +1385,7 @@ cudaError_t rank_chunk_end(const RankCfg &c, RankLane &ln)
 	if ((e = cudaGetLastError()) != cudaSuccess) return e;
 	if (c.profile) {
 		rank_mark(c, ln, 3, 0, 0);
-		if ((e = cudaStreamSynchronize(ln.job.stream)) != cudaSuccess) return e;
+		if ((e = cudaStreamSynchronize(ln.stream)) != cudaSuccess) return e;
 		RankCtrl *hc = (RankCtrl *)malloc(sizeof(RankCtrl));
 		if (hc == nullptr) return cudaErrorMemoryAllocation;
 		if ((e = cudaMemcpy(hc, s.ctrl, sizeof(RankCtrl), cudaMemcpyDeviceToHost)) != cudaSuccess) {
@@ -1404,6 +1403,10 @@ cudaError_t rank_chunk_end(const RankCfg &c, RankLane &ln)
 			if (kind == 0 && lv > 1 && (hc->lv[lv].m < c.lim || s.ppass[i] >= radix_passes(hc->lv[lv].groups))) {
 				el = 0; /* a pass that returned at once */
 			}
+			if (c.trace) {
+				fprintf(stderr, "x3k_launch_rank: profile %-6s level %2d pass %d: %8.2f us, %9.0f elements\n",
+				        kind == 0 ? "radix" : (kind == 1 ? "level" : "setup"), lv, s.ppass[i], ms * 1e3, el);
+			}
 			s.prof_ms[kind] += ms;
 			s.prof_elems[kind] += el;
 			s.prof_launches[kind] += el > 0 ? 1 : 0;
@@ -1420,7 +1423,7 @@ cudaError_t rank_chunk_step(const RankCfg &c, RankLane &ln, bool *blocked)
 	cudaError_t e;
 	RankScratch &s = *ln.s;
 	RankArgs &a = ln.a;
-	cudaStream_t stream = ln.job.stream;
+	cudaStream_t stream = ln.stream;
 	*blocked = false;
 	for (;;) {
 		const int L = ln.L;
@@ -1449,7 +1452,7 @@ cudaError_t rank_chunk_step(const RankCfg &c, RankLane &ln, bool *blocked)
 			ln.known = rep[0];
 			if (c.trace) {
 				fprintf(stderr, "x3k_launch_rank: lane %d chunk at %llu level %d: %u elements, %u groups\n", ln.index,
-				        ln.next - a.n_out, L - c.lag + 1, ln.known, s.h_back[4 * (L - c.lag) + 1]);
+				        ln.a0, L - c.lag + 1, ln.known, s.h_back[4 * (L - c.lag) + 1]);
 			}
 			if (ln.known < c.lim) {
 				return rank_chunk_end(c, ln);
@@ -1558,21 +1561,45 @@ int x3k_rank_profile(int dev, int kind, double *ms, double *elements, int *launc
 	return 0;
 }
 
+/* chunk length and count of a search over n positions on `lanes` lanes: chunks of equal length
+ * (a multiple of 4096), as few as the 24-bit element format allows but at least one per lane */
+void x3k_rank_chunking(unsigned long long n, uint32_t D, int lanes, unsigned long long *chunk, unsigned long long *count)
+{
+	const unsigned long long CHMAX = (unsigned long long)((RANK_MAX_M - (D < (1u << 23) ? D : (1u << 23))) & ~4095u);
+	unsigned long long nch = (n + CHMAX - 1) / CHMAX;
+	if (nch < (unsigned long long)lanes) {
+		nch = (unsigned long long)lanes;
+	}
+	if (nch < 1) {
+		nch = 1;
+	}
+	unsigned long long CH = (((n + nch - 1) / nch) + 4095ull) & ~4095ull;
+	if (CH == 0) {
+		CH = 4096;
+	}
+	*chunk = CH;
+	*count = (n + CH - 1) / CH;
+}
+
 /*
- * Lstar by the rank method for up to RANK_MAX_LANES jobs of the current device at once, job j on
- * its own stream with its own scratch (lane j).  Everything the levels of a chunk need to know
- * about each other (sizes, buffers, whether the search is over) lives in device memory, so the
- * launches are simply queued; the host only reads the size of level L-lag back before it queues
- * level L (`lag` levels of work stay queued behind that wait), to size the grids and to stop
- * queueing once the search has ended.  While one lane waits for such a report the others are fed:
- * the mid-size levels of a chunk are one wave of tiles each, latency and not throughput, and two
- * chunks in flight fill each other's gaps (and one job's copies overlap another's kernels).
+ * Lstar by the rank method for positions [0, b.n) of the current device, chunk by chunk, on up to
+ * RANK_MAX_LANES lanes at once: a lane is a stream of the caller's with scratch of its own, and
+ * takes the next chunk whenever its last one is queued.  Everything the levels of a chunk need to
+ * know about each other (sizes, buffers, whether the search is over) lives in device memory, so
+ * the launches are simply queued; the host only reads the size of level L-lag back before it
+ * queues level L (`lag` levels of work stay queued behind that wait), to size the grids and to
+ * stop queueing once the search has ended.  While one lane waits for such a report the others are
+ * fed: the mid-size levels of a chunk are one wave of tiles each -- latency, not throughput -- and
+ * chunks in flight together fill each other's gaps (and one chunk's copies overlap another's kernels).
  */
-cudaError_t x3k_launch_rank_jobs(const X3RankJob *jobs, int njobs, uint32_t D, int t, int *launches)
+cudaError_t x3k_launch_rank_batch(const X3RankBatch &b, uint32_t D, int t, int *launches)
 {
 	cudaError_t e;
-	if (njobs < 1 || njobs > RANK_MAX_LANES || D > x3k_rank_max_distances() || t > 254) {
+	if (b.lanes < 1 || b.lanes > RANK_MAX_LANES || D > x3k_rank_max_distances() || t > 254) {
 		return cudaErrorNotSupported;
+	}
+	if (b.n == 0) {
+		return cudaSuccess;
 	}
 	int dev = 0;
 	if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -1582,37 +1609,29 @@ cudaError_t x3k_launch_rank_jobs(const X3RankJob *jobs, int njobs, uint32_t D, i
 	c.t = t;
 	c.lim = (uint32_t)t + 2u;
 	c.trace = getenv("X3_TRACE") != nullptr;
-	/* the profile mode's events sit between the kernels of one stream: one job only */
-	c.profile = getenv("X3_RANK_PROFILE") != nullptr && njobs == 1;
+	/* the profile mode's events sit between the kernels of one stream: one lane only */
+	c.profile = getenv("X3_RANK_PROFILE") != nullptr && b.lanes == 1;
 	c.no_tail = getenv("X3_RANK_NO_TAIL") != nullptr; /* testing knob: never changes results */
 	/* programmatic dependent launch between the kernels of a chunk; the profile mode keeps plain launches */
 	c.pdl = getenv("X3_RANK_NO_PDL") == nullptr && !c.profile;
 	c.lag = getenv("X3_RANK_LAG") != nullptr && atoi(getenv("X3_RANK_LAG")) >= 1 ? atoi(getenv("X3_RANK_LAG")) : 2;
 	const auto wall0 = std::chrono::steady_clock::now();
-	const unsigned long long CHMAX = (unsigned long long)((RANK_MAX_M - D) & ~4095u);
+	unsigned long long CH = 0, nch = 0;
+	x3k_rank_chunking(b.n, D, b.lanes, &CH, &nch);
+	const bool trivial = t <= 0 || D == 0; /* backend.c:76 never enters the selection / the window holds no
+	                                        * distance: return 1 everywhere, a memset per chunk */
 
 	RankLane lanes[RANK_MAX_LANES];
-	int open = 0;
-	for (int j = 0; j < njobs; ++j) {
+	for (int j = 0; j < b.lanes; ++j) {
 		RankLane &ln = lanes[j];
-		ln.job = jobs[j];
+		ln.b = &b;
+		ln.stream = b.streams[j];
 		ln.index = j;
 		ln.s = &g_rank[dev][j];
-		if (ln.job.n == 0) {
-			ln.finished = true;
+		if (trivial || (unsigned long long)j >= nch) {
 			continue;
 		}
-		if (t <= 0 || D == 0) {
-			/* backend.c:76 never enters the selection / the window holds no distance: return 1 everywhere */
-			if ((e = cudaMemsetAsync(ln.job.lstar, 0, ln.job.n, ln.job.stream)) != cudaSuccess) return e;
-			ln.finished = true;
-			continue;
-		}
-		/* chunks of equal length, so that ranks and chunk-relative positions fit 24 bits */
-		const unsigned long long nch = (ln.job.n + CHMAX - 1) / CHMAX;
-		ln.CH = (((ln.job.n + nch - 1) / nch) + 4095ull) & ~4095ull;
-		const unsigned long long first = ln.job.n < ln.CH ? ln.job.n : ln.CH;
-		if ((e = rank_ensure(dev, j, (uint32_t)(first + D))) != cudaSuccess) return e;
+		if ((e = rank_ensure(dev, j, (uint32_t)((b.n < CH ? b.n : CH) + D))) != cudaSuccess) return e;
 		RankScratch &s = *ln.s;
 		if (c.profile && !s.pev_made) {
 			for (int i = 0; i < 520; ++i) {
@@ -1624,40 +1643,47 @@ cudaError_t x3k_launch_rank_jobs(const X3RankJob *jobs, int njobs, uint32_t D, i
 			s.prof_ms[k] = s.prof_elems[k] = 0;
 			s.prof_launches[k] = 0;
 		}
-		++open;
 	}
 	if (c.trace) {
-		fprintf(stderr, "x3k_launch_rank: scratch of %d lane(s) ready after %.3f ms\n", njobs,
-		        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
+		fprintf(stderr, "x3k_launch_rank: %llu chunk(s) of %llu positions on %d lane(s), scratch ready after %.3f ms\n", nch, CH,
+		        b.lanes, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
 	}
-	/* lanes whose job needs no kernels are done already */
-	for (int j = 0; j < njobs; ++j) {
-		if (lanes[j].finished && lanes[j].job.queued != nullptr) {
-			if ((e = lanes[j].job.queued(lanes[j].job.ctx, j)) != cudaSuccess) return e;
-		}
-	}
+	unsigned long long next = 0; /* chunks are handed out in order */
+	int open = b.lanes;
 	while (open > 0) {
 		bool progress = false;
-		for (int j = 0; j < njobs; ++j) {
+		for (int j = 0; j < b.lanes; ++j) {
 			RankLane &ln = lanes[j];
 			if (ln.finished) {
 				continue;
 			}
 			if (!ln.active) {
-				if (ln.next >= ln.job.n) {
+				if (next >= nch) {
 					ln.finished = true;
 					--open;
 					progress = true;
-					if (ln.job.queued != nullptr && (e = ln.job.queued(ln.job.ctx, j)) != cudaSuccess) return e;
 					continue;
 				}
-				if ((e = rank_chunk_begin(c, ln)) != cudaSuccess) return e;
+				const unsigned long long a0 = next * CH, len = b.n - a0 < CH ? b.n - a0 : CH;
+				++next;
 				progress = true;
+				if (b.before_chunk != nullptr && (e = b.before_chunk(b.ctx, j, a0, len)) != cudaSuccess) return e;
+				if (trivial) {
+					if ((e = cudaMemsetAsync(b.lstar + a0, 0, len, ln.stream)) != cudaSuccess) return e;
+					ln.a0 = a0;
+					ln.a.n_out = (uint32_t)len;
+				} else if ((e = rank_chunk_begin(c, ln, a0, len)) != cudaSuccess) {
+					return e;
+				}
 			}
 			bool blocked = false;
-			if ((e = rank_chunk_step(c, ln, &blocked)) != cudaSuccess) return e;
+			if (ln.active && (e = rank_chunk_step(c, ln, &blocked)) != cudaSuccess) return e;
 			if (!blocked) {
 				progress = true;
+			}
+			if (!ln.active && b.after_chunk != nullptr) {
+				/* the chunk's last kernel is queued on the lane's stream */
+				if ((e = b.after_chunk(b.ctx, j, ln.a0, ln.a.n_out)) != cudaSuccess) return e;
 			}
 		}
 		if (!progress) {
@@ -1667,7 +1693,7 @@ cudaError_t x3k_launch_rank_jobs(const X3RankJob *jobs, int njobs, uint32_t D, i
 		}
 	}
 	int nl = 0;
-	for (int j = 0; j < njobs; ++j) {
+	for (int j = 0; j < b.lanes; ++j) {
 		nl += lanes[j].nl;
 	}
 	if (launches != nullptr) {
@@ -1723,15 +1749,17 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 		return cudaSuccess;
 	}
 	const int lanes = x3k_rank_default_lanes(prm.n, prm.D);
-	X3RankJob jobs[RANK_MAX_LANES];
+	X3RankBatch b;
+	b.x = prm.x;
+	b.lstar = prm.lstar;
+	b.n = prm.n;
+	b.lanes = lanes;
+	b.before_chunk = nullptr;
+	b.after_chunk = nullptr;
+	b.ctx = nullptr;
 	if (lanes == 1) {
-		jobs[0].x = prm.x;
-		jobs[0].lstar = prm.lstar;
-		jobs[0].n = prm.n;
-		jobs[0].stream = stream;
-		jobs[0].queued = nullptr;
-		jobs[0].ctx = nullptr;
-		return x3k_launch_rank_jobs(jobs, 1, prm.D, prm.t, launches);
+		b.streams[0] = stream;
+		return x3k_launch_rank_batch(b, prm.D, prm.t, launches);
 	}
 	int dev = 0;
 	if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
@@ -1747,17 +1775,10 @@ cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int 
 	}
 	if ((e = cudaEventRecord(ls.fork, stream)) != cudaSuccess) return e;
 	for (int j = 0; j < lanes; ++j) {
-		unsigned long long lo = (unsigned long long)((unsigned __int128)prm.n * j / lanes) & ~4095ull;
-		unsigned long long hi = j + 1 == lanes ? prm.n : (unsigned long long)((unsigned __int128)prm.n * (j + 1) / lanes) & ~4095ull;
-		jobs[j].x = prm.x + lo;
-		jobs[j].lstar = prm.lstar + lo;
-		jobs[j].n = hi - lo;
-		jobs[j].stream = ls.st[j];
-		jobs[j].queued = nullptr;
-		jobs[j].ctx = nullptr;
+		b.streams[j] = ls.st[j];
 		if ((e = cudaStreamWaitEvent(ls.st[j], ls.fork, 0)) != cudaSuccess) return e;
 	}
-	e = x3k_launch_rank_jobs(jobs, lanes, prm.D, prm.t, launches);
+	e = x3k_launch_rank_batch(b, prm.D, prm.t, launches);
 	/* the caller's stream continues behind every lane, also when queueing failed half way */
 	for (int j = 0; j < lanes; ++j) {
 		if (cudaEventRecord(ls.join[j], ls.st[j]) == cudaSuccess) {
