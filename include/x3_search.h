@@ -49,6 +49,10 @@ typedef struct x3s_timing {
 	double h2d_ms;    /* host -> device copies (max over GPUs) */
 	double kernel_ms; /* search kernels (max over GPUs), CUDA events */
 	double d2h_ms;    /* device -> host copies of Lstar (and H) */
+	                  /* A shard that is pipelined chunk by chunk (see x3s_search_host) overlaps the three;
+	                   * the figures then split its critical path: h2d_ms = until the first search can
+	                   * start, kernel_ms = from there to the end of the last search, d2h_ms = from there
+	                   * to the last byte back. */
 	double total_ms;  /* wall time of the whole call */
 	int    gpus;      /* GPUs actually used */
 	int    launches;  /* kernel launches issued */
@@ -79,9 +83,11 @@ size_t x3s_required_bytes(size_t n_positions, size_t W);
  *            results are ordered behind it; the brute-force kernels return at once, the rank
  *            search returns when its last level has been queued (it reads level sizes back
  *            while queueing, so the call lasts about as long as the search)
- * One search per device at a time: the library keeps one set of scratch buffers per device
+ * One search per device at a time: the library keeps its scratch buffers per device
  * (searches issued from different streams are ordered behind each other; do not call this
- * concurrently from several host threads for the same device).
+ * concurrently from several host threads for the same device).  Inside one search the chunks of a
+ * large input run on lane streams of the library's own, forked from `stream` and joined back into
+ * it before the call returns, so the ordering seen by the caller is that of a single stream.
  */
 int x3s_search_device(int device, const void *d_x, size_t n_positions, size_t W, int t,
                       void *d_lstar, void *d_H, void *stream, int variant);
@@ -92,6 +98,13 @@ int x3s_search_device(int device, const void *d_x, size_t n_positions, size_t W,
  * `ngpus` contiguous ranges, each shipped with its trailing window halo; results
  * land in lstar[n] (and H[n*32] when H != NULL).  ngpus <= 0 means "all visible".
  * Synchronous.  Device and staging buffers are cached between calls.
+ *
+ * A shard larger than one chunk of the rank search (2^24 - W positions) is searched as several
+ * chunks in flight at once (up to 4 by default, X3_RANK_LANES=1..8 overrides; never changes the
+ * result).  When x and lstar are page-locked (x3s_host_alloc, or cudaHostRegister by the caller)
+ * the shard is also pipelined: the upload goes chunk by chunk, a chunk is searched as soon as the
+ * bytes it reads have arrived, and its Lstar is copied back while later chunks are still searched.
+ * Pageable buffers take the plain upload - search - copy back sequence.
  */
 int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int variant,
                     void *lstar, void *H, x3s_timing *timing);

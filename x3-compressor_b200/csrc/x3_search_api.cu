@@ -22,7 +22,7 @@
 
 namespace {
 
-constexpr int X3S_MAX_PIECES = 4;
+constexpr int X3S_MAX_PIECES = 8;
 
 thread_local char g_err[512] = "";
 
@@ -57,7 +57,7 @@ struct DevState {
 	/* pipelined shard (rank search, page-locked host buffers): the upload goes chunk by chunk on
 	 * `stream` with an event behind every chunk, the chunks are searched on lane streams, and each
 	 * chunk's Lstar goes back on its lane's stream */
-	cudaStream_t ps[X3S_MAX_PIECES] = {nullptr, nullptr, nullptr, nullptr};
+	cudaStream_t ps[X3S_MAX_PIECES] = {};
 	cudaEvent_t pev[X3S_MAX_PIECES][2] = {}; /* per lane: last search queued so far done, its Lstar back */
 	std::vector<cudaEvent_t> upev;           /* per chunk: uploaded */
 	bool pinited = false;

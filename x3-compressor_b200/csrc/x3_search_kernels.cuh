@@ -54,7 +54,7 @@ struct X3RankBatch {
 	uint8_t *lstar;        /* n bytes */
 	unsigned long long n;
 	int lanes;             /* 1 .. x3k_rank_max_lanes() */
-	cudaStream_t streams[4];
+	cudaStream_t streams[8];
 	cudaError_t (*before_chunk)(void *ctx, int lane, unsigned long long a0, unsigned long long len);
 	cudaError_t (*after_chunk)(void *ctx, int lane, unsigned long long a0, unsigned long long len);
 	void *ctx;

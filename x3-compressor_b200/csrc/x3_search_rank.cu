@@ -1189,7 +1189,8 @@ cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t sme
 }
 
 /* ---- per-device scratch ------------------------------------------------------------------ */
-constexpr int RANK_MAX_LANES = 4; /* searches (chunks) of one device that may be in flight at once */
+constexpr int RANK_MAX_LANES = 8; /* searches (chunks) of one device that may be in flight at once */
+constexpr int RANK_DEFAULT_LANES = 4; /* ... unless X3_RANK_LANES says otherwise */
 
 struct RankScratch {
 	uint32_t cap = 0; /* elements */
@@ -1216,9 +1217,9 @@ RankScratch g_rank[64][RANK_MAX_LANES];
 /* streams the lanes of a device-level search (x3k_launch_rank) run on, forked from and joined
  * back into the caller's stream */
 struct RankLanes {
-	cudaStream_t st[RANK_MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+	cudaStream_t st[RANK_MAX_LANES] = {};
 	cudaEvent_t fork = nullptr;
-	cudaEvent_t join[RANK_MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+	cudaEvent_t join[RANK_MAX_LANES] = {};
 	bool made = false;
 };
 RankLanes g_lanes[64];
@@ -1720,6 +1721,9 @@ int x3k_rank_default_lanes(unsigned long long n, uint32_t D)
 	} else {
 		const unsigned long long chmax = (unsigned long long)((RANK_MAX_M - (D < (1u << 23) ? D : (1u << 23))) & ~4095u);
 		lanes = (n + chmax - 1) / chmax;
+		if (lanes > (unsigned long long)RANK_DEFAULT_LANES) {
+			lanes = RANK_DEFAULT_LANES;
+		}
 	}
 	if (getenv("X3_RANK_PROFILE") != nullptr) {
 		lanes = 1; /* the profile mode's events bracket the launches of one stream */
