@@ -61,12 +61,18 @@
 
 namespace {
 
-constexpr int LV_THREADS = 256;
+#ifndef X3_LV_THREADS
+#define X3_LV_THREADS 256
+#endif
+constexpr int LV_THREADS = X3_LV_THREADS;      /* threads of a level-kernel CTA */
+constexpr int F1_THREADS = 256;                 /* level-1 kernel: tile geometry of its own */
+constexpr int F1_ITEMS = 8;
+constexpr int F1_TILE = F1_THREADS * F1_ITEMS;
 #ifndef X3_LV_ITEMS
 #define X3_LV_ITEMS 8
 #endif
 constexpr int LV_ITEMS = X3_LV_ITEMS;           /* elements per thread of a level tile */
-constexpr int LV_CTAS = LV_ITEMS <= 8 ? 6 : 4;  /* resident CTAs per SM the level kernel is built for */
+constexpr int LV_CTAS = (LV_ITEMS <= 8 ? 6 : 4) * 256 / LV_THREADS;  /* resident CTAs per SM the level kernel is built for */
 constexpr int LV_TILE = LV_THREADS * LV_ITEMS;
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
@@ -445,15 +451,15 @@ __global__ void __launch_bounds__(RS_THREADS, 5) x3_rank_radix_kernel(RankArgs a
  * so Lstar = #{L : count_L >= c1} = the smallest LCP32 over those followers, 0 when c1 < 2
  * (backend.c:76-78 collapsed) -- settled here by walking them.  Position 0 has no element (p = -1):
  * its followers are the head of its byte's group, found through the digit histogram. */
-__global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_first_kernel(RankArgs a)
+__global__ void __launch_bounds__(F1_THREADS, 6) x3_rank_first_kernel(RankArgs a)
 {
-	__shared__ __align__(16) uint32_t sk[LV_TILE + 256 + 8]; /* + look-ahead (<= 255) + the walk's read-ahead */
-	__shared__ __align__(16) uint32_t sp[LV_TILE + 256 + 8];
+	__shared__ __align__(16) uint32_t sk[F1_TILE + 256 + 8]; /* + look-ahead (<= 255) + the walk's read-ahead */
+	__shared__ __align__(16) uint32_t sp[F1_TILE + 256 + 8];
 	const int tid = threadIdx.x;
 	pdl_wait();
 	pdl_launch_dependents();
 	const uint32_t m = a.M;
-	const uint32_t ntiles = (m + LV_TILE - 1) / LV_TILE;
+	const uint32_t ntiles = (m + F1_TILE - 1) / F1_TILE;
 	const uint32_t D = a.D, n_out = a.n_out;
 	const uint32_t la = (uint32_t)a.t + 1u;
 	const uint32_t *__restrict__ keyIn = a.key1; /* the output of x3_rank_radix_kernel<INIT> */
@@ -485,31 +491,31 @@ __global__ void __launch_bounds__(LV_THREADS, 6) x3_rank_first_kernel(RankArgs a
 		}
 	}
 	for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-		const uint32_t base = tile * LV_TILE;
-		const uint32_t i0 = base + tid * LV_ITEMS;
-		if (i0 + LV_ITEMS <= m) {
+		const uint32_t base = tile * F1_TILE;
+		const uint32_t i0 = base + tid * F1_ITEMS;
+		if (i0 + F1_ITEMS <= m) {
 #pragma unroll
-			for (int v = 0; v < LV_ITEMS; v += 4) {
-				*reinterpret_cast<uint4 *>(sk + tid * LV_ITEMS + v) = *reinterpret_cast<const uint4 *>(keyIn + i0 + v);
-				*reinterpret_cast<uint4 *>(sp + tid * LV_ITEMS + v) = *reinterpret_cast<const uint4 *>(posIn + i0 + v);
+			for (int v = 0; v < F1_ITEMS; v += 4) {
+				*reinterpret_cast<uint4 *>(sk + tid * F1_ITEMS + v) = *reinterpret_cast<const uint4 *>(keyIn + i0 + v);
+				*reinterpret_cast<uint4 *>(sp + tid * F1_ITEMS + v) = *reinterpret_cast<const uint4 *>(posIn + i0 + v);
 			}
 		} else {
 #pragma unroll
-			for (int e = 0; e < LV_ITEMS; ++e) {
+			for (int e = 0; e < F1_ITEMS; ++e) {
 				const bool v = i0 + e < m;
-				sk[tid * LV_ITEMS + e] = v ? keyIn[i0 + e] : 0u;
-				sp[tid * LV_ITEMS + e] = v ? posIn[i0 + e] : 0u;
+				sk[tid * F1_ITEMS + e] = v ? keyIn[i0 + e] : 0u;
+				sp[tid * F1_ITEMS + e] = v ? posIn[i0 + e] : 0u;
 			}
 		}
 		if ((uint32_t)tid < la) {
-			const uint32_t i = base + LV_TILE + tid;
-			sk[LV_TILE + tid] = i < m ? keyIn[i] : 0u;
-			sp[LV_TILE + tid] = i < m ? posIn[i] : 0u;
+			const uint32_t i = base + F1_TILE + tid;
+			sk[F1_TILE + tid] = i < m ? keyIn[i] : 0u;
+			sp[F1_TILE + tid] = i < m ? posIn[i] : 0u;
 		}
 		__syncthreads();
 #pragma unroll 1
-		for (int e = 0; e < LV_ITEMS; ++e) {
-			const uint32_t idx = e * LV_THREADS + tid;
+		for (int e = 0; e < F1_ITEMS; ++e) {
+			const uint32_t idx = e * F1_THREADS + tid;
 			if (base + idx >= m) {
 				break;
 			}
@@ -616,9 +622,11 @@ __global__ void __launch_bounds__(LV_THREADS, LV_CTAS) x3_rank_level_kernel(Rank
 	/* digits of the new keys that can be non-zero: ranks are below the number of L-grams */
 	const uint32_t rbound = L == 1 ? (m < 256u ? m : 256u) : (L == 2 ? (m < 65536u ? m : 65536u) : m);
 	const int ndig = radix_passes(rbound);
+	if (tid < 256) {
 #pragma unroll
-	for (int j = 0; j < 4; ++j) {
-		hist[j][tid] = 0;
+		for (int j = 0; j < 4; ++j) {
+			hist[j][tid] = 0;
+		}
 	}
 	__syncthreads();
 
@@ -854,7 +862,7 @@ __global__ void __launch_bounds__(LV_THREADS, LV_CTAS) x3_rank_level_kernel(Rank
 	if (emit) {
 		__syncthreads();
 		for (int j = 0; j < ndig; ++j) {
-			if (hist[j][tid] != 0) {
+			if (tid < 256 && hist[j][tid] != 0) {
 				atomicAdd(&a.ctrl->hist[L + 1][j][tid], hist[j][tid]);
 			}
 		}
@@ -1286,9 +1294,9 @@ struct RankLane {
 	int nl = 0;
 };
 
-int rank_grid_for(const RankScratch &s, uint32_t tiles)
+int rank_grid_for(const RankScratch &s, uint32_t tiles, int threads = 256)
 {
-	const uint32_t maxgrid = (uint32_t)s.sms * 8u;
+	const uint32_t maxgrid = (uint32_t)s.sms * 8u * 256u / (uint32_t)threads;
 	return (int)(tiles < maxgrid ? (tiles > 0 ? tiles : 1) : maxgrid);
 }
 
@@ -1333,7 +1341,7 @@ cudaError_t rank_chunk_begin(const RankCfg &c, RankLane &ln, unsigned long long 
 	}
 	s.seq = s.seq + 1u == 0u ? 1u : s.seq + 1u;
 	a.seq = s.seq;
-	const uint32_t lv_tiles = (a.M + LV_TILE - 1) / LV_TILE, rs_tiles = (a.M + RS_TILE - 1) / RS_TILE, rs_tiles_small = (a.M + RS_TILE_SMALL - 1) / RS_TILE_SMALL;
+	const uint32_t lv_tiles = (a.M + LV_TILE - 1) / LV_TILE, f1_tiles = (a.M + F1_TILE - 1) / F1_TILE, rs_tiles = (a.M + RS_TILE - 1) / RS_TILE, rs_tiles_small = (a.M + RS_TILE_SMALL - 1) / RS_TILE_SMALL;
 	if ((e = cudaMemsetAsync(s.ctrl, 0, sizeof(RankCtrl), stream)) != cudaSuccess) return e;
 	if ((e = cudaMemsetAsync(s.st_level, 0, (size_t)lv_tiles * 8, stream)) != cudaSuccess) return e;
 	if ((e = cudaMemsetAsync(s.st_radix, 0, (size_t)rs_tiles_small * 256 * 8, stream)) != cudaSuccess) return e;
@@ -1358,7 +1366,7 @@ cudaError_t rank_chunk_begin(const RankCfg &c, RankLane &ln, unsigned long long 
 	if (e != cudaSuccess) return e;
 	++ln.ticket;
 	rank_mark(c, ln, 1, 2, 0);
-	if ((e = launch_pdl(x3_rank_first_kernel, rank_grid_for(s, lv_tiles), LV_THREADS, 0, stream, c.pdl, a)) != cudaSuccess) return e;
+	if ((e = launch_pdl(x3_rank_first_kernel, rank_grid_for(s, f1_tiles), F1_THREADS, 0, stream, c.pdl, a)) != cudaSuccess) return e;
 	rank_mark(c, ln, 0, 2, 1);
 	if (small_in) {
 		e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS_SMALL>, rank_grid_for(s, rs_tiles_small), RS_THREADS, 0, stream, c.pdl, a,
@@ -1468,7 +1476,7 @@ cudaError_t rank_chunk_step(const RankCfg &c, RankLane &ln, bool *blocked)
 		}
 		const uint32_t known = ln.known;
 		rank_mark(c, ln, 1, L, 0);
-		const int lgrid = rank_grid_for(s, (known + LV_TILE - 1) / LV_TILE);
+		const int lgrid = rank_grid_for(s, (known + LV_TILE - 1) / LV_TILE, LV_THREADS);
 		if (L == 2) {
 			e = launch_pdl(x3_rank_level_kernel<2>, lgrid, LV_THREADS, 0, stream, c.pdl, a, L, ln.ticket);
 		} else if (L == 3) {
