@@ -56,11 +56,26 @@ UNIT = "MB/s"
 ALU_OPS_PER_PAIR = None  # filled from x3s_kernel_info when the library reports it
 
 
+_C2 = None
+
+
 def member(corpus, r: int) -> np.ndarray:
-    """Member r of the weak-scaling input: member 0 is exactly config C2."""
+    """Member r of the weak-scaling input: member 0 is exactly config C2; member r > 0 is C2 with its
+    19 248 lines (one paragraph each) in a seeded random order -- other bytes, another table, the same
+    size and the same statistics, so that per-GPU work really is fixed as N grows.  (Freshly generated
+    texts of the same shape differ by up to 12 % in search time with the seed -- measured: 1.00 against
+    1.13 ms -- and the max over ranks then reports the hardest seed, not the scaling.)"""
+    global _C2
+    if _C2 is None:
+        _C2 = corpus.generate("C2")
     if r == 0:
-        return np.frombuffer(corpus.generate("C2"), dtype=np.uint8)
-    return np.frombuffer(corpus.text(MEMBER_BYTES, seed=2 + 1000 * r, vocab=30000, para=True), dtype=np.uint8)
+        return np.frombuffer(_C2, dtype=np.uint8)
+    lines = _C2.split(b"\n")
+    tail = lines.pop()  # bytes behind the last newline stay at the end
+    order = np.random.Generator(np.random.PCG64(1000 * r)).permutation(len(lines))
+    out = b"\n".join(lines[i] for i in order) + b"\n" + tail
+    assert len(out) == MEMBER_BYTES
+    return np.frombuffer(out, dtype=np.uint8)
 
 
 def padded_member(corpus, r: int, world: int) -> np.ndarray:
@@ -226,6 +241,28 @@ def run_reference(args):
     return 0
 
 
+def bind_near_gpu(torch, local):
+    """One rank per GPU: run this rank's host threads on the CPUs NVML names as closest to its GPU.
+    The rank search is fed by a host thread that reads level sizes back while it queues launches; a
+    thread on the far socket pays the inter-socket hop on every one of them.  Returns the CPU set
+    or None when NVML cannot tell."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(local)
+        bus = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        h = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {i for i in range(ncpu) if (words[i // 64] >> (i % 64)) & 1} & os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:  # NVML missing or the query unsupported: leave the scheduler alone
+        pass
+    return None
+
+
 # ----------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------
@@ -246,6 +283,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device visible (the search has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    near = bind_near_gpu(torch, local) if os.environ.get("X3_BENCH_NO_BIND") is None else None
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -347,8 +385,16 @@ def run_b200(args):
     L.x3s_host_free(hx)
     L.x3s_host_free(hl)
 
+    if os.environ.get("X3_BENCH_RANKS") is not None:
+        print(f"rank {rank}: device {dev_ms / args.steps:.4f} ms/step, end to end {e2e_s / args.steps * 1e3:.4f} ms/step, "
+              f"cpus {near if near is None else (near[0], near[-1], len(near))}", file=sys.stderr, flush=True)
     # ---- max over ranks ----------------------------------------------------------------
+    per_rank_ms = [dev_ms / args.steps]
     if dist is not None:
+        mine = torch.tensor([dev_ms / args.steps], dtype=torch.float64, device=dev)
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank_ms = [float(v[0]) for v in every]
         tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dev_ms, e2e_s = float(tt[0]), float(tt[1])
@@ -425,7 +471,10 @@ def run_b200(args):
                                "(BASELINE.json configs[1]); one position = one byte",
                    "window_bytes": W_BYTES, "max_match_count": T_COUNT, "positions_per_gpu": n,
                    "l2": "flushed between timed steps (256 MiB fill, outside the event pairs)",
-                   "sharding": "contiguous position ranges with trailing window halo, no collective"},
+                   "sharding": "contiguous position ranges with trailing window halo, no collective",
+                   "members": "rank 0 searches C2, rank r > 0 C2 with its lines in a seeded random order "
+                              "(same size and statistics, other bytes)",
+                   "per_rank_ms_per_step": per_rank_ms},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(len(x_host)) * world,
                 "d2h_bytes_per_step": int(n) * world, "ms_per_step": e2e_s / args.steps * 1e3,
                 "api": "x3s_search_host (include/x3_search.h), pinned host buffers"},
