@@ -847,12 +847,22 @@ __global__ void __launch_bounds__(LV_THREADS, LV_CTAS) x3_rank_level_kernel(Rank
 					keyOut[dst0 + j] = nk;
 					posOut[dst0 + j] = sp[j];
 				}
-				/* digit histograms of the new keys, one shared-memory add per distinct digit of the warp */
-				for (int dgt = 0; dgt < ndig; ++dgt) {
-					const uint32_t d = on ? (nk >> (8 * dgt)) & 255u : 256u;
-					const uint32_t peers = __match_any_sync(FULL_MASK, d);
+				/* digit histograms of the new keys */
+				/* digit 0 is the byte behind the gram: many distinct values per warp, where MATCH.ANY is at its
+				 * slowest and plain shared-memory adds collide little; the rank digits are (nearly) uniform
+				 * within a warp, where it is the other way round (C2 1.000 -> 0.975 ms) */
+				if (on) {
+					atomicAdd(&hist[0][nk & 255u], 1u);
+				}
+				if (ndig > 1) {
+					/* one match on the whole rank serves all of its digits */
+					const uint32_t r = on ? (nk >> 8) & (0xffffffffu >> (40 - 8 * ndig)) : 0xffffffffu;
+					const uint32_t peers = __match_any_sync(FULL_MASK, r);
 					if (on && lane == __ffs(peers) - 1) {
-						atomicAdd(&hist[dgt][d], (uint32_t)__popc(peers));
+						const uint32_t c = (uint32_t)__popc(peers);
+						for (int dgt = 1; dgt < ndig; ++dgt) {
+							atomicAdd(&hist[dgt][(nk >> (8 * dgt)) & 255u], c);
+						}
 					}
 				}
 			}
