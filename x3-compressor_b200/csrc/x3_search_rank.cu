@@ -1276,6 +1276,19 @@ cudaError_t rank_ensure(int dev, int lane, uint32_t M)
 	return cudaSuccess;
 }
 
+/* tuning knobs (never change results): CTAs per SM a persistent grid is capped at, for the radix / level-1
+ * kernels and for the level kernels; array size below which a radix pass takes the small tile */
+struct RankTune {
+	uint32_t rs_per_sm = 8, lv_per_sm = 8, small_below = RS_SMALL_BELOW;
+	RankTune()
+	{
+		const char *v;
+		if ((v = getenv("X3_RANK_RSGRID")) != nullptr && atoi(v) >= 1) rs_per_sm = (uint32_t)atoi(v);
+		if ((v = getenv("X3_RANK_LVGRID")) != nullptr && atoi(v) >= 1) lv_per_sm = (uint32_t)atoi(v);
+		if ((v = getenv("X3_RANK_SMALL")) != nullptr && atoi(v) >= 0) small_below = (uint32_t)atoi(v);
+	}
+};
+
 /* what every chunk of one call shares */
 struct RankCfg {
 	uint32_t D;
@@ -1283,6 +1296,7 @@ struct RankCfg {
 	uint32_t lim;     /* fewer elements than this: nobody can pass */
 	bool trace, profile, no_tail, pdl;
 	int lag;          /* levels of work that stay queued while the host waits for a level size (>= 1) */
+	RankTune tune;
 };
 
 /* one lane: a stream with scratch of its own that takes the batch's chunks one after the other.
@@ -1304,9 +1318,9 @@ struct RankLane {
 	int nl = 0;
 };
 
-int rank_grid_for(const RankScratch &s, uint32_t tiles, int threads = 256)
+int rank_grid_for(const RankScratch &s, uint32_t tiles, uint32_t per_sm = 8, int threads = 256)
 {
-	const uint32_t maxgrid = (uint32_t)s.sms * 8u * 256u / (uint32_t)threads;
+	const uint32_t maxgrid = (uint32_t)s.sms * per_sm * 256u / (uint32_t)threads;
 	return (int)(tiles < maxgrid ? (tiles > 0 ? tiles : 1) : maxgrid);
 }
 
@@ -1365,24 +1379,24 @@ cudaError_t rank_chunk_begin(const RankCfg &c, RankLane &ln, unsigned long long 
 	 * of the positions p + 1, tested (and, where the byte is rare, settled) by the first kernel --
 	 * then digit b0 back into buffer 0 */
 	rank_mark(c, ln, 0, 2, 0);
-	const bool small_in = a.M < RS_SMALL_BELOW;
+	const bool small_in = a.M < c.tune.small_below;
 	if (small_in) {
-		e = launch_pdl(x3_rank_radix_kernel<true, RS_ITEMS_SMALL>, rank_grid_for(s, rs_tiles_small), RS_THREADS, 0, stream, c.pdl, a,
+		e = launch_pdl(x3_rank_radix_kernel<true, RS_ITEMS_SMALL>, rank_grid_for(s, rs_tiles_small, c.tune.rs_per_sm), RS_THREADS, 0, stream, c.pdl, a,
 		               2, 0, ln.ticket, (uint32_t)ln.ticket + 1u);
 	} else {
-		e = launch_pdl(x3_rank_radix_kernel<true, RS_ITEMS>, rank_grid_for(s, rs_tiles), RS_THREADS, 0, stream, c.pdl, a, 2, 0,
+		e = launch_pdl(x3_rank_radix_kernel<true, RS_ITEMS>, rank_grid_for(s, rs_tiles, c.tune.rs_per_sm), RS_THREADS, 0, stream, c.pdl, a, 2, 0,
 		               ln.ticket, (uint32_t)ln.ticket + 1u);
 	}
 	if (e != cudaSuccess) return e;
 	++ln.ticket;
 	rank_mark(c, ln, 1, 2, 0);
-	if ((e = launch_pdl(x3_rank_first_kernel, rank_grid_for(s, f1_tiles), F1_THREADS, 0, stream, c.pdl, a)) != cudaSuccess) return e;
+	if ((e = launch_pdl(x3_rank_first_kernel, rank_grid_for(s, f1_tiles, c.tune.rs_per_sm), F1_THREADS, 0, stream, c.pdl, a)) != cudaSuccess) return e;
 	rank_mark(c, ln, 0, 2, 1);
 	if (small_in) {
-		e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS_SMALL>, rank_grid_for(s, rs_tiles_small), RS_THREADS, 0, stream, c.pdl, a,
+		e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS_SMALL>, rank_grid_for(s, rs_tiles_small, c.tune.rs_per_sm), RS_THREADS, 0, stream, c.pdl, a,
 		               2, 1, ln.ticket, (uint32_t)ln.ticket + 1u);
 	} else {
-		e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS>, rank_grid_for(s, rs_tiles), RS_THREADS, 0, stream, c.pdl, a, 2, 1,
+		e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS>, rank_grid_for(s, rs_tiles, c.tune.rs_per_sm), RS_THREADS, 0, stream, c.pdl, a, 2, 1,
 		               ln.ticket, (uint32_t)ln.ticket + 1u);
 	}
 	if (e != cudaSuccess) return e;
@@ -1486,7 +1500,7 @@ cudaError_t rank_chunk_step(const RankCfg &c, RankLane &ln, bool *blocked)
 		}
 		const uint32_t known = ln.known;
 		rank_mark(c, ln, 1, L, 0);
-		const int lgrid = rank_grid_for(s, (known + LV_TILE - 1) / LV_TILE, LV_THREADS);
+		const int lgrid = rank_grid_for(s, (known + LV_TILE - 1) / LV_TILE, c.tune.lv_per_sm, LV_THREADS);
 		if (L == 2) {
 			e = launch_pdl(x3_rank_level_kernel<2>, lgrid, LV_THREADS, 0, stream, c.pdl, a, L, ln.ticket);
 		} else if (L == 3) {
@@ -1507,11 +1521,11 @@ cudaError_t rank_chunk_step(const RankCfg &c, RankLane &ln, bool *blocked)
 		for (int pass = 0; pass < np; ++pass) {
 			rank_mark(c, ln, 0, L + 1, pass);
 			/* the tile size only has to be the same within one pass */
-			if (known < RS_SMALL_BELOW) {
-				e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS_SMALL>, rank_grid_for(s, (known + RS_TILE_SMALL - 1) / RS_TILE_SMALL),
+			if (known < c.tune.small_below) {
+				e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS_SMALL>, rank_grid_for(s, (known + RS_TILE_SMALL - 1) / RS_TILE_SMALL, c.tune.rs_per_sm),
 				               RS_THREADS, 0, stream, c.pdl, a, L + 1, pass, ln.ticket, (uint32_t)ln.ticket + 1u);
 			} else {
-				e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS>, rank_grid_for(s, (known + RS_TILE - 1) / RS_TILE), RS_THREADS, 0,
+				e = launch_pdl(x3_rank_radix_kernel<false, RS_ITEMS>, rank_grid_for(s, (known + RS_TILE - 1) / RS_TILE, c.tune.rs_per_sm), RS_THREADS, 0,
 				               stream, c.pdl, a, L + 1, pass, ln.ticket, (uint32_t)ln.ticket + 1u);
 			}
 			if (e != cudaSuccess) return e;
