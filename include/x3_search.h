@@ -130,6 +130,17 @@ void  x3s_host_free(void *p);
  */
 int x3s_rank_profile(int device, int kind, double *ms, double *elements, int *launches);
 
+/*
+ * How a rank search over n_positions with window W is cut up (no device needed): the positions are
+ * searched in `chunks` chunks of `chunk_positions` positions each (a multiple of 4096; the last one
+ * may be shorter; chunk + W - 33 < 2^24, so that ranks and chunk-relative positions fit 24 bits),
+ * `lanes_used` of them in flight at once.  lanes = 0 asks for the library's own choice (one lane per
+ * chunk, at most 4, X3_RANK_LANES overrides), lanes >= 1 for that many (capped at 8).  Each lane owns
+ * 16 B of device scratch per chunk element.  X3S_ERR_UNSUPP when W - 33 > 2^23 (the brute-force
+ * kernels take such windows).
+ */
+int x3s_rank_plan(size_t n_positions, size_t W, int lanes, size_t *chunk_positions, size_t *chunks, int *lanes_used);
+
 /* Frees every cached device/staging buffer. */
 void x3s_release(void);
 

@@ -72,6 +72,9 @@ def lib() -> C.CDLL:
     L.x3s_host_free.argtypes = [C.c_void_p]
     L.x3s_rank_profile.restype = C.c_int
     L.x3s_rank_profile.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
+    L.x3s_rank_plan.restype = C.c_int
+    L.x3s_rank_plan.argtypes = [C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                C.POINTER(C.c_int)]
     L.x3s_release.restype = None
     L.x3s_set_devices.restype = C.c_int
     L.x3s_set_devices.argtypes = [C.POINTER(C.c_int), C.c_int]
@@ -110,6 +113,13 @@ def rank_profile(device: int = 0):
         _check(lib().x3s_rank_profile(device, kind, C.byref(ms), C.byref(el), C.byref(nl)))
         out[name] = (ms.value, el.value, nl.value)
     return out
+
+
+def rank_plan(n: int, W: int, lanes: int = 0):
+    """(chunk_positions, chunks, lanes_used) of a rank search over n positions (x3s_rank_plan)."""
+    ch, cnt, used = C.c_size_t(), C.c_size_t(), C.c_int()
+    _check(lib().x3s_rank_plan(n, W, lanes, C.byref(ch), C.byref(cnt), C.byref(used)))
+    return ch.value, cnt.value, used.value
 
 
 def set_devices(ids):

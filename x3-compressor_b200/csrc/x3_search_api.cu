@@ -555,6 +555,27 @@ int x3s_rank_profile(int device, int kind, double *ms, double *elements, int *la
 	return X3S_OK;
 }
 
+int x3s_rank_plan(size_t n_positions, size_t W, int lanes, size_t *chunk_positions, size_t *chunks, int *lanes_used)
+{
+	if (chunk_positions == nullptr || chunks == nullptr || lanes_used == nullptr || lanes < 0) {
+		return fail(X3S_ERR_ARG, "x3s_rank_plan: null pointer or negative lane count");
+	}
+	const uint32_t D = distances(W);
+	if (W > ((size_t)1 << 31) || D > x3k_rank_max_distances()) {
+		return fail(X3S_ERR_UNSUPP, "forward window %zu is beyond the rank search (W - 33 <= 2^23)", W);
+	}
+	int L = lanes == 0 ? x3k_rank_default_lanes(n_positions, D) : lanes;
+	if (L > x3k_rank_max_lanes()) {
+		L = x3k_rank_max_lanes();
+	}
+	unsigned long long ch = 0, cnt = 0;
+	x3k_rank_chunking(n_positions, D, L, &ch, &cnt);
+	*chunk_positions = (size_t)ch;
+	*chunks = (size_t)cnt;
+	*lanes_used = (unsigned long long)L < cnt ? L : (int)(cnt > 0 ? cnt : 1);
+	return X3S_OK;
+}
+
 void *x3s_host_alloc(size_t bytes)
 {
 	void *p = nullptr;
