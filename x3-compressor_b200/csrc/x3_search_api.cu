@@ -234,7 +234,7 @@ const char *x3s_last_error(void)
 
 const char *x3s_version(void)
 {
-	return "x3-b200 search 0.2 (sm_100a; kernels: stream, bitsliced, naive)";
+	return "x3-b200 search 0.3 (sm_100a; kernels: rank, stream, bitsliced, naive)";
 }
 
 size_t x3s_required_bytes(size_t n_positions, size_t W)
