@@ -94,3 +94,37 @@ def lstar_rank(x: np.ndarray, n: int, W: int, t: int, tile: int | None = None, s
         order = np.argsort(nkey, kind="stable")
         key, pos = nkey[order], pos[order]
     return ls
+
+
+def merge_pass_order(nkey: np.ndarray) -> np.ndarray:
+    """Round-2 design note, stated here so that its exactness is pinned on the CPU: the sort between two
+    levels needs ONE ranked radix pass, not three, when the rank range is small enough for a dense count
+    matrix.
+
+    nkey[i] = rank[i] * 256 + byte[i] in the order the level kernel writes it: sorted by (rank, position),
+    positions increasing inside a rank.  Wanted: the stable order by (rank, byte).
+
+      pass A   stable counting sort by byte alone (the existing 8-bit pass) -> order (byte, rank, position);
+               inside it every (byte, rank) pair is one contiguous run, positions still increasing
+      matrix   cnt[rank][byte], accumulated where the keys are written; base = its exclusive scan in
+               (rank, byte) order, i.e. in key order -- the destination of the first element of each run
+      pass B   "merge pass": element i of the pass-A array goes to base[nkey] + (i - start of its run);
+               whole runs move as blocks: no ranking (no MATCH.ANY), no per-digit chained prefix
+
+    Returns the permutation (indices into nkey) this produces; equal to np.argsort(nkey, kind='stable')."""
+    m = len(nkey)
+    if m == 0:
+        return np.zeros(0, dtype=np.int64)
+    byte = nkey & 255
+    a = np.argsort(byte, kind="stable")                      # pass A
+    ka = nkey[a]
+    groups = int(nkey.max() >> 8) + 1
+    cnt = np.bincount(nkey, minlength=groups * 256)          # the count matrix, flattened in key order
+    base = np.cumsum(cnt) - cnt
+    head = np.ones(m, dtype=bool)
+    head[1:] = ka[1:] != ka[:-1]
+    start = np.maximum.accumulate(np.where(head, np.arange(m), 0))
+    dest = base[ka] + (np.arange(m) - start)                 # pass B
+    out = np.empty(m, dtype=np.int64)
+    out[dest] = a
+    return out

@@ -4,6 +4,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as ol
+import rank_model as rm
 from rank_model import lstar_rank
 
 
@@ -37,3 +38,14 @@ def test_rank_model_equals_oracle(corpus, kind, n, W, t):
     assert np.array_equal(lstar_rank(x, len(a), W, t, tile=64), ref)
     # ... and so does keeping every element for level 2 (the kernels sort level 2 from x)
     assert np.array_equal(lstar_rank(x, len(a), W, t, tile=64, direct_level2=True), ref)
+
+
+@pytest.mark.parametrize("seed,m,groups", [(1, 1, 1), (2, 5000, 1), (3, 5000, 7), (4, 20000, 900), (5, 3000, 3000)])
+def test_merge_pass_equals_stable_sort(seed, m, groups):
+    """The one-ranked-pass sort of DESIGN.md section 11 (byte pass, count matrix, block moves) gives exactly
+    the stable (rank, byte) order the three radix passes give today."""
+    rng = np.random.default_rng(seed)
+    rank = np.sort(rng.integers(0, groups, m))               # the level kernel writes ranks in order
+    byte = rng.choice(np.array([0, 32, 101, 116, 255]), m, p=[.1, .3, .3, .2, .1]) if seed % 2 else rng.integers(0, 256, m)
+    nkey = rank.astype(np.int64) * 256 + byte
+    assert np.array_equal(rm.merge_pass_order(nkey), np.argsort(nkey, kind="stable"))
