@@ -694,11 +694,53 @@ struct x3_dict {
 	int32_t *node_elem; /* tag of the string ending in this node, or -1 */
 	uint32_t nodes, node_cap;
 	struct hmap child; /* (node << 8 | byte) -> node */
-	/* order statistics over stamps */
-	uint64_t *tree;      /* Fenwick: 1 where a stamp is live */
+	/* order statistics over stamps: one bit per stamp (live or not) and a Fenwick tree over the
+	 * population counts of the 64-bit words -- six levels less to walk than a tree over the stamps */
+	uint64_t *bits;      /* stamp_cap / 64 words */
+	uint64_t *tree;      /* Fenwick over popcount(bits[w]) */
 	int32_t *stamp_elem; /* element that holds a stamp, or -1 */
-	uint32_t stamp_cap, next_stamp;
+	uint32_t stamp_cap, next_stamp; /* stamp_cap: a power of two, at least 64 */
 };
+
+static inline void stamp_set(struct x3_dict *d, uint32_t st)
+{
+	d->bits[st >> 6] |= 1ull << (st & 63);
+	fen_add(d->tree, d->stamp_cap >> 6, st >> 6, 1);
+}
+
+static inline void stamp_clear(struct x3_dict *d, uint32_t st)
+{
+	d->bits[st >> 6] &= ~(1ull << (st & 63));
+	fen_add(d->tree, d->stamp_cap >> 6, st >> 6, (uint64_t)-1);
+}
+
+/* live stamps in [0, i) */
+static inline uint64_t stamp_prefix(const struct x3_dict *d, uint32_t i)
+{
+	uint64_t s = fen_prefix(d->tree, i >> 6);
+	if (i & 63) {
+		s += (uint64_t)__builtin_popcountll(d->bits[i >> 6] & ((1ull << (i & 63)) - 1ull));
+	}
+	return s;
+}
+
+/* the live stamp with exactly k live stamps below it (k < number of live stamps) */
+static inline uint32_t stamp_select(const struct x3_dict *d, uint64_t k)
+{
+	uint64_t cum;
+	const uint32_t w = fen_find(d->tree, d->stamp_cap >> 6, k, &cum);
+	if (w >= (d->stamp_cap >> 6)) {
+		abort();
+	}
+	uint64_t word = d->bits[w];
+	for (uint64_t r = k - cum; r > 0; --r) {
+		word &= word - 1; /* drop the lowest live stamp of the word */
+	}
+	if (word == 0) {
+		abort();
+	}
+	return (w << 6) + (uint32_t)__builtin_ctzll(word);
+}
 
 struct x3_dict *x3_dict_create(void)
 {
@@ -713,7 +755,8 @@ struct x3_dict *x3_dict_create(void)
 	d->nodes = 1;
 	hmap_init(&d->child, 4096);
 	d->stamp_cap = 1024;
-	d->tree = xcalloc((size_t)d->stamp_cap + 1, sizeof(uint64_t));
+	d->bits = xcalloc((size_t)d->stamp_cap / 64, sizeof(uint64_t));
+	d->tree = xcalloc((size_t)d->stamp_cap / 64 + 1, sizeof(uint64_t));
 	d->stamp_elem = xmalloc((size_t)d->stamp_cap * sizeof(int32_t));
 	for (uint32_t i = 0; i < d->stamp_cap; ++i) {
 		d->stamp_elem[i] = -1;
@@ -728,6 +771,7 @@ void x3_dict_destroy(struct x3_dict *d)
 	free(d->stamp);
 	free(d->node_elem);
 	hmap_free(&d->child);
+	free(d->bits);
 	free(d->tree);
 	free(d->stamp_elem);
 	free(d);
@@ -787,24 +831,28 @@ static void dict_compact(struct x3_dict *d)
 	}
 	if (ncap != d->stamp_cap) {
 		d->stamp_elem = xrealloc(d->stamp_elem, (size_t)ncap * sizeof(int32_t));
-		d->tree = xrealloc(d->tree, ((size_t)ncap + 1) * sizeof(uint64_t));
+		d->bits = xrealloc(d->bits, ((size_t)ncap / 64) * sizeof(uint64_t));
+		d->tree = xrealloc(d->tree, ((size_t)ncap / 64 + 1) * sizeof(uint64_t));
 		d->stamp_cap = ncap;
 	}
 	for (uint32_t i = 0; i < d->stamp_cap; ++i) {
 		d->stamp_elem[i] = -1;
 	}
-	memset(d->tree, 0, ((size_t)d->stamp_cap + 1) * sizeof(uint64_t));
 	for (uint32_t i = 0; i < k; ++i) {
 		d->stamp_elem[i] = order[i];
 		d->stamp[order[i]] = i;
 	}
-	/* Fenwick over k leading ones */
-	for (uint32_t i = 1; i <= d->stamp_cap; ++i) {
-		if (i <= k) {
-			d->tree[i] += 1;
-		}
+	/* k leading live stamps */
+	const uint32_t words = d->stamp_cap / 64;
+	memset(d->tree, 0, ((size_t)words + 1) * sizeof(uint64_t));
+	for (uint32_t w = 0; w < words; ++w) {
+		const uint32_t lo = w * 64;
+		d->bits[w] = k >= lo + 64 ? ~0ull : (k > lo ? (1ull << (k - lo)) - 1ull : 0ull);
+	}
+	for (uint32_t i = 1; i <= words; ++i) {
+		d->tree[i] += (uint64_t)__builtin_popcountll(d->bits[i - 1]);
 		const uint32_t j = i + (i & (0u - i));
-		if (j <= d->stamp_cap) {
+		if (j <= words) {
 			d->tree[j] += d->tree[i];
 		}
 	}
@@ -817,7 +865,7 @@ static void dict_stamp_front(struct x3_dict *d, uint32_t tag, int had_stamp)
 	if (had_stamp) {
 		const uint32_t old = d->stamp[tag];
 		d->stamp_elem[old] = -1;
-		fen_add(d->tree, d->stamp_cap, old, (uint64_t)-1);
+		stamp_clear(d, old);
 	}
 	if (d->next_stamp == d->stamp_cap) {
 		if (!had_stamp) {
@@ -834,7 +882,7 @@ static void dict_stamp_front(struct x3_dict *d, uint32_t tag, int had_stamp)
 	const uint32_t st = d->next_stamp++;
 	d->stamp[tag] = st;
 	d->stamp_elem[st] = (int32_t)tag;
-	fen_add(d->tree, d->stamp_cap, st, 1);
+	stamp_set(d, st);
 }
 
 uint32_t x3_dict_insert(struct x3_dict *d, const uint8_t *s, uint32_t len)
@@ -890,7 +938,7 @@ const uint8_t *x3_dict_str(const struct x3_dict *d, uint32_t tag)
 uint32_t x3_dict_index_of(const struct x3_dict *d, uint32_t tag)
 {
 	/* number of elements used more recently = position in the cost-sorted array */
-	const uint64_t upto = fen_prefix(d->tree, d->stamp[tag] + 1);
+	const uint64_t upto = stamp_prefix(d, d->stamp[tag] + 1);
 	return (uint32_t)(d->elems - upto);
 }
 
@@ -902,10 +950,8 @@ uint32_t x3_dict_tag_at(const struct x3_dict *d, uint32_t index)
 	/* the element with exactly `index` more recent ones is the (elems - index)-th live
 	 * stamp in ascending order: find the largest pos with prefix(pos) <= k - 1 */
 	const uint64_t k = (uint64_t)d->elems - index;
-	uint64_t cum;
-	const uint32_t pos = fen_find(d->tree, d->stamp_cap, k - 1, &cum);
-	/* pos is the largest position whose prefix is <= k-1: stamps [0,pos) hold k-1 live
-	 * ones and stamp `pos` is live */
+	const uint32_t pos = stamp_select(d, k - 1);
+	/* stamps [0,pos) hold k-1 live ones and stamp `pos` is live */
 	if (pos >= d->stamp_cap || d->stamp_elem[pos] < 0) {
 		abort();
 	}
