@@ -80,6 +80,10 @@ double x3_search_prepare_ms(void);
  * context; 0 when a previous call had already paid it). */
 double x3_search_startup_ms(void);
 
+/* NEW.  The part that page-locked the caller's buffer in place (so that upload, search and copy
+ * back can overlap chunk by chunk); the buffer is unlocked again by x3_search_release(). */
+double x3_search_register_ms(void);
+
 /*
  * NEW.  Dictionary callbacks for hosts that cannot export dict_find_match /
  * dict_get_len_by_index as dynamic symbols (e.g. FFI hosts).  Passing NULLs

@@ -33,7 +33,8 @@ extern "C" {
 #define X3S_ERR_UNSUPP   (-3) /* parameter outside what the kernels implement */
 
 #define X3S_MAX_MATCH_LEN 32  /* reference backend.h:7-10 */
-#define X3S_MAX_T        254  /* u8 cells saturate at 255; lossless while t <= 254 */
+#define X3S_MAX_T        254  /* 32-bin table H and the brute-force kernels: u8 cells saturate at 255, lossless
+                              * while t <= 254.  The Lstar-only rank search takes any t (reference backend.c:21-26) */
 
 /* kernel variants */
 #define X3S_KERNEL_DEFAULT   0 /* production choice: the rank search for Lstar alone, the stream kernel when the
@@ -119,6 +120,15 @@ int x3s_set_devices(const int *ids, int count);
 /* Pinned host memory helpers (so FFI callers can avoid pageable copies). */
 void *x3s_host_alloc(size_t bytes);
 void  x3s_host_free(void *p);
+
+/*
+ * Page-locks memory the caller owns (malloc, mmap, a shared-memory segment ...) where it lies, so
+ * that x3s_search_host() can pipeline a shard between it and the device; the range is rounded out
+ * to whole pages.  x3s_host_unregister() takes the same pointer.  X3S_ERR_CUDA when the driver
+ * refuses (the buffer then still works, as pageable memory).
+ */
+int x3s_host_register(void *p, size_t bytes);
+int x3s_host_unregister(void *p);
 
 /*
  * Measurement hook of the rank search.  With the environment variable X3_RANK_PROFILE=1 the

@@ -17,6 +17,8 @@ const char *x3s_version(void) { return "oracle-backed fake (tests only)"; }
 size_t x3s_required_bytes(size_t n, size_t W) { return n + W; }
 void *x3s_host_alloc(size_t bytes) { return malloc(bytes); }
 void x3s_host_free(void *p) { free(p); }
+int x3s_host_register(void *p, size_t bytes) { (void)p; (void)bytes; return X3S_ERR_CUDA; }
+int x3s_host_unregister(void *p) { (void)p; return X3S_ERR_CUDA; }
 void x3s_release(void) {}
 int x3s_set_devices(const int *ids, int count) { (void)ids; (void)count; return X3S_OK; }
 
@@ -31,7 +33,7 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
                     x3s_timing *timing)
 {
 	(void)ngpus; (void)variant;
-	if (t > X3S_MAX_T) {
+	if (t > X3S_MAX_T && H != NULL) {
 		return X3S_ERR_UNSUPP;
 	}
 	x3o_table_fast((const uint8_t *)x, n + W, 0, n, W, t, (uint8_t *)H, NULL, (uint8_t *)lstar);

@@ -35,7 +35,9 @@ INPUTS = {
 }
 # (W, t, f1, f2)
 PARAMS = [(8192, 15, 4, 0), (1024, 3, 4, 0), (100, 1, 4, 0), (34, 15, 4, 0), (33, 15, 4, 0), (0, 15, 4, 0),
-          (4096, 50, 0, 0), (2048, 7, 1, 1), (8192, 15, 0, 3), (8192, 0, 4, 0), (65536, 64, 4, 0)]
+          (4096, 50, 0, 0), (2048, 7, 1, 1), (8192, 15, 0, 3), (8192, 0, 4, 0), (65536, 64, 4, 0),
+          # t >= 255: the reference takes any int (backend.c:21-26)
+          (8192, 255, 4, 0), (8192, 300, 4, 0), (65536, 1000, 4, 0), (2048, 256, 0, 2)]
 
 
 def fbm_all(R, data: bytes, W, t, f1, f2):
@@ -80,7 +82,8 @@ def main():
     streams = {}
     x3 = ROOT / "oracle" / "_ref" / "x3_ref"
     cases = [("C1", 60000), ("C4", 30000), ("C5", 40000), ("C2", 20000)]
-    flagsets = ["", "-t 1", "-t 3 -w 1", "-t 50 -w 32", "-m 0", "-m 1 -n 1", "-n 3 -t 7", "-x", "-w 0", "-t 0"]
+    flagsets = ["", "-t 1", "-t 3 -w 1", "-t 50 -w 32", "-m 0", "-m 1 -n 1", "-n 3 -t 7", "-x", "-w 0", "-t 0",
+                "-t 255", "-t 300", "-t 1000 -w 64"]
     with tempfile.TemporaryDirectory() as td:
         for name, size in cases:
             data = corpus.generate(name, size)

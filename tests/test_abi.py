@@ -60,10 +60,19 @@ def test_no_cpu_fallback(pkg):
 
 
 def test_unsupported_parameters_are_rejected(pkg):
+    """t >= 255 is refused only where u8 cells count (the 32-bin table, the brute-force variants);
+    the Lstar-only search takes any t, like the reference (backend.c:21-26)."""
     data = np.zeros(1000, dtype=np.uint8)
     with pytest.raises(pkg.X3SearchError) as ei:
-        pkg.search_host(data, W=8192, t=255)
+        pkg.search_host(data, W=8192, t=255, want_table=True)
     assert ei.value.code == pkg.X3S_ERR_UNSUPP
+    with pytest.raises(pkg.X3SearchError) as ei:
+        pkg.search_host(data, W=8192, t=300, variant=pkg.KERNEL_STREAM)
+    assert ei.value.code == pkg.X3S_ERR_UNSUPP
+    if pkg.device_count() == 0:
+        with pytest.raises(pkg.X3SearchError) as ei:
+            pkg.search_host(data, W=8192, t=300)  # accepted as a parameter; fails only for want of a device
+        assert ei.value.code == pkg.X3S_ERR_CUDA
 
 
 def test_shard_ranges_cover_input(pkg):

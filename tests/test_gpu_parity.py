@@ -100,7 +100,7 @@ def test_rank_search_equals_oracle_window_sweep(pkg, corpus, W):
     _assert_rank_same(pkg, _inputs(corpus, "rand2", min(n, 4500)), W, 3)
 
 
-@pytest.mark.parametrize("t", [0, 1, 2, 3, 15, 16, 64, 200, 254])
+@pytest.mark.parametrize("t", [0, 1, 2, 3, 15, 16, 64, 200, 254, 255, 256, 300, 1000, 70000])
 def test_rank_search_equals_oracle_threshold_sweep(pkg, corpus, t):
     _assert_rank_same(pkg, _inputs(corpus, "mix", 9000), 2048, t)
     _assert_rank_same(pkg, _inputs(corpus, "zeros", 3000), 1024, t)
@@ -244,7 +244,7 @@ def test_empty_and_rejected_inputs(pkg):
     ls, H, _ = pkg.search_host(np.zeros(0, dtype=np.uint8), W=8192, t=15, want_table=True)
     assert len(ls) == 0 and H.shape == (0, 32)
     with pytest.raises(pkg.X3SearchError) as ei:
-        pkg.search_host(np.zeros(100, dtype=np.uint8), W=8192, t=255)
+        pkg.search_host(np.zeros(100, dtype=np.uint8), W=8192, t=255, want_table=True)  # u8 cells
     assert ei.value.code == pkg.X3S_ERR_UNSUPP
 
 
@@ -323,11 +323,36 @@ def test_full_size_c2_properties(pkg, corpus):
 
 
 def test_multi_gpu_sharding_equals_single(pkg, corpus):
-    """x3s_search_host with ngpus > 1 (all visible GPUs) returns the single-GPU table."""
+    """x3s_search_host with ngpus > 1 returns the single-GPU table (needs a box with >= 2 GPUs: on one
+    GPU "all visible" is one shard, and the comparison would prove nothing)."""
+    if pkg.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
     data = np.frombuffer(corpus.generate("C5", 3_000_000), dtype=np.uint8)
-    one, _, _ = pkg.search_host(data, W=8192, t=15, ngpus=1)
-    many, _, tm = pkg.search_host(data, W=8192, t=15, ngpus=0)
-    assert np.array_equal(one, many)
+    one, _, tm1 = pkg.search_host(data, W=8192, t=15, ngpus=1)
+    assert tm1.gpus == 1
+    _, ls_ref = ol.table(data, 8192, 15, p0=1_400_000, p1=1_600_000)  # the band around the 2-GPU seam
+    assert np.array_equal(one[1_400_000:1_600_000], ls_ref)
+    for ngpus in sorted({2, min(3, pkg.device_count()), pkg.device_count()}):
+        many, _, tm = pkg.search_host(data, W=8192, t=15, ngpus=ngpus)
+        assert tm.gpus == ngpus >= 2
+        assert np.array_equal(one, many), f"ngpus={ngpus}: first difference at p={int(np.argmax(one != many))}"
+        pinned, _, tm = pkg.search_host(data, W=8192, t=15, ngpus=ngpus, pinned=True)
+        assert tm.gpus == ngpus and np.array_equal(one, pinned)
+
+
+@pytest.mark.parametrize("n,W,t", [(3 * 4096 + 17, 8192, 15), (2 * 4096, 65536, 3), (5 * 4096 + 1, 4096, 7),
+                                   (70_000, 1 << 17, 20)])
+def test_multi_gpu_seams_small_input_large_window(pkg, corpus, n, W, t):
+    """Seam-focused: few positions, cuts at multiples of 4096, windows that reach over one or several
+    neighbouring shards (the trailing halo is clamped at the end of the padded buffer)."""
+    if pkg.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    data = _inputs(corpus, "text", n)
+    _, ls_ref = ol.table(data, W, t)
+    for ngpus in sorted({2, min(3, pkg.device_count()), pkg.device_count()}):
+        got, _, tm = pkg.search_host(data, W=W, t=t, ngpus=ngpus)
+        assert tm.gpus == min(ngpus, n // 4096 + 1)
+        assert np.array_equal(got, ls_ref), f"ngpus={ngpus}: first difference at p={int(np.argmax(got != ls_ref))}"
 
 
 @pytest.mark.skipif(not (REF / "x3_ref_dropin").exists(), reason="oracle/_ref not shipped")

@@ -70,6 +70,10 @@ def lib() -> C.CDLL:
     L.x3s_host_alloc.restype = C.c_void_p
     L.x3s_host_alloc.argtypes = [C.c_size_t]
     L.x3s_host_free.argtypes = [C.c_void_p]
+    L.x3s_host_register.restype = C.c_int
+    L.x3s_host_register.argtypes = [C.c_void_p, C.c_size_t]
+    L.x3s_host_unregister.restype = C.c_int
+    L.x3s_host_unregister.argtypes = [C.c_void_p]
     L.x3s_rank_profile.restype = C.c_int
     L.x3s_rank_profile.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.x3s_rank_plan.restype = C.c_int

@@ -259,21 +259,38 @@ def _member(kind: str, n: int, seed: int) -> bytes:
     raise ValueError(kind)
 
 
-def silesia_mix(n: int = 211938580, seed: int = 5) -> bytes:
-    """Tar-like concatenation with the Silesia size profile, scaled to n bytes."""
+def _member_job(job):
+    kind, body, seed = job
+    return _member(kind, body, seed)
+
+
+def silesia_mix(n: int = 211938580, seed: int = 5, workers: int = 1) -> bytes:
+    """Tar-like concatenation with the Silesia size profile, scaled to n bytes.  workers > 1
+    generates the members in that many processes (same bytes: every member has a seed of its own)."""
     total = sum(s for _, s, _ in _SILESIA)
-    parts = []
+    heads = []
+    jobs = []
     used = 0
     for i, (name, size, kind) in enumerate(_SILESIA):
         share = n - used if i == len(_SILESIA) - 1 else int(size * n / total)
         share = max(share, 0)
         hdr = (name.encode().ljust(100, b"\0") + b"0000644\0" + f"{share:011o}\0".encode()).ljust(512, b"\0")
         body = max(share - 512, 0)
-        parts.append(hdr[: min(512, share)])
-        if body:
-            parts.append(_member(kind, body, seed * 100 + i))
+        heads.append(hdr[: min(512, share)])
+        jobs.append((kind, body, seed * 100 + i))
         used += share
-    out = b"".join(parts)
+    if workers > 1:
+        import multiprocessing as mp
+        # largest members first, so that the pool's wall time is that of the largest one
+        order = sorted(range(len(jobs)), key=lambda j: -jobs[j][1])
+        with mp.get_context("fork").Pool(min(workers, len(jobs))) as pool:
+            res = pool.map(_member_job, [jobs[j] for j in order], chunksize=1)
+        bodies = [b""] * len(jobs)
+        for j, b in zip(order, res):
+            bodies[j] = b
+    else:
+        bodies = [_member(*job) if job[1] else b"" for job in jobs]
+    out = b"".join(h + (b if job[1] else b"") for h, b, job in zip(heads, bodies, jobs))
     assert len(out) == n, (len(out), n)
     return out
 
@@ -306,3 +323,28 @@ def generate(name: str, size: int | None = None) -> bytes:
     if name == "C5":
         return silesia_mix(n, seed=5)
     raise KeyError(name)
+
+
+def generate_cached(name: str, size: int | None = None, workers: int = 8, cache_dir: str = "/dev/shm") -> bytes:
+    """generate() through a file cache in tmpfs (the 212 MB mix takes ~40 s of Python; the bench's
+    two arms and four GPU counts would each pay it).  The cache is only ever a copy of what
+    generate() returns: it is written under a temporary name and renamed, and a file of the wrong
+    length is ignored.  Call it before CUDA is initialised (the workers are forked)."""
+    import os
+    n = CONFIGS[name]["size"] if size is None else size
+    path = os.path.join(cache_dir, f"x3b200_corpus_{name}_{n}.bin")
+    try:
+        if os.path.getsize(path) == n:
+            with open(path, "rb") as f:
+                return f.read()
+    except OSError:
+        pass
+    data = silesia_mix(n, seed=5, workers=workers) if name == "C5" else generate(name, size)
+    try:
+        tmp = f"{path}.{os.getpid()}.tmp"
+        with open(tmp, "wb") as f:
+            f.write(data)
+        os.replace(tmp, path)
+    except OSError:
+        pass
+    return data

@@ -184,10 +184,15 @@ int grow(uint8_t **ptr, size_t *cap, size_t need)
 	return X3S_OK;
 }
 
-int check_params(size_t W, int t)
+int check_params(size_t W, int t, const void *H, int variant)
 {
-	if (t > X3S_MAX_T) {
-		return fail(X3S_ERR_UNSUPP, "max match count %d exceeds %d (u8 table cells)", t, X3S_MAX_T);
+	/* the rank search (Lstar only) takes any t, like the reference (backend.c:21-26); the brute-force
+	 * kernels count in u8 cells that saturate at 255, which is lossless only while t <= 254 */
+	const bool brute = H != nullptr || (variant != X3S_KERNEL_DEFAULT && variant != X3S_KERNEL_RANK) ||
+	                   (W > X3S_MAX_MATCH_LEN + 1 && W - X3S_MAX_MATCH_LEN - 1 > x3k_rank_max_distances());
+	if (t > X3S_MAX_T && brute) {
+		return fail(X3S_ERR_UNSUPP, "max match count %d exceeds %d for the 32-bin table / brute-force kernels (u8 cells)", t,
+		            X3S_MAX_T);
 	}
 	if (W > ((size_t)1 << 31)) {
 		return fail(X3S_ERR_UNSUPP, "forward window %zu exceeds 2^31", W);
@@ -245,7 +250,7 @@ size_t x3s_required_bytes(size_t n_positions, size_t W)
 int x3s_search_device(int device, const void *d_x, size_t n_positions, size_t W, int t, void *d_lstar,
                       void *d_H, void *stream, int variant)
 {
-	int rc = check_params(W, t);
+	int rc = check_params(W, t, d_H, variant);
 	if (rc != X3S_OK) {
 		return rc;
 	}
@@ -277,7 +282,7 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
                     x3s_timing *timing)
 {
 	const auto wall0 = std::chrono::steady_clock::now();
-	int rc = check_params(W, t);
+	int rc = check_params(W, t, H, variant);
 	if (rc != X3S_OK) {
 		return rc;
 	}
@@ -296,13 +301,12 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 	if (nvis <= 0) {
 		return fail(X3S_ERR_CUDA, "no CUDA device visible (the search has no CPU fallback)");
 	}
+	std::lock_guard<std::mutex> lock(g_mu);
 	const int ndev = g_ids.empty() ? nvis : (int)g_ids.size();
 	int G = ngpus <= 0 ? ndev : (ngpus < ndev ? ngpus : ndev);
 	if ((size_t)G > n / 4096 + 1) {
 		G = (int)(n / 4096 + 1); /* do not shard tiny inputs */
 	}
-
-	std::lock_guard<std::mutex> lock(g_mu);
 	if ((int)g_dev.size() < nvis) {
 		g_dev.resize(nvis);
 	}
@@ -594,6 +598,34 @@ void x3s_host_free(void *p)
 	}
 }
 
+int x3s_host_register(void *p, size_t bytes)
+{
+	if (p == nullptr || bytes == 0) {
+		return fail(X3S_ERR_ARG, "x3s_host_register: null pointer or empty range");
+	}
+	/* whole pages: the driver locks pages, and callers hand in slices of larger buffers */
+	const uintptr_t page = 4096, lo = (uintptr_t)p & ~(page - 1), hi = ((uintptr_t)p + bytes + page - 1) & ~(page - 1);
+	const cudaError_t e = cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterPortable);
+	if (e != cudaSuccess) {
+		(void)cudaGetLastError();
+		return fail(X3S_ERR_CUDA, "cudaHostRegister(%zu bytes) failed: %s", (size_t)(hi - lo), cudaGetErrorString(e));
+	}
+	return X3S_OK;
+}
+
+int x3s_host_unregister(void *p)
+{
+	if (p == nullptr) {
+		return fail(X3S_ERR_ARG, "x3s_host_unregister: null pointer");
+	}
+	const cudaError_t e = cudaHostUnregister((void *)((uintptr_t)p & ~(uintptr_t)4095));
+	if (e != cudaSuccess) {
+		(void)cudaGetLastError();
+		return fail(X3S_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e));
+	}
+	return X3S_OK;
+}
+
 void x3s_release(void)
 {
 	std::lock_guard<std::mutex> lock(g_mu);
@@ -626,14 +658,18 @@ void x3s_release(void)
 			cudaEventDestroy(ev);
 		}
 		ds = DevState();
-		if (g < 64 && g_kernel_inited[g]) {
-			cudaFree(g_scratch[g].counter);
-			cudaFree(g_scratch[g].deep);
-			cudaEventDestroy(g_scratch[g].last);
-			x3k_rank_release((int)g);
-			g_scratch[g] = Scratch();
-			g_kernel_inited[g] = false;
+	}
+	/* scratch of every device a search ran on, also those only x3s_search_device() touched */
+	for (int g = 0; g < 64; ++g) {
+		if (!g_kernel_inited[g] || cudaSetDevice(g) != cudaSuccess) {
+			continue;
 		}
+		cudaFree(g_scratch[g].counter);
+		cudaFree(g_scratch[g].deep);
+		cudaEventDestroy(g_scratch[g].last);
+		x3k_rank_release(g);
+		g_scratch[g] = Scratch();
+		g_kernel_inited[g] = false;
 	}
 }
 

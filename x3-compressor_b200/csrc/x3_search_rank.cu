@@ -527,7 +527,10 @@ __global__ void __launch_bounds__(F1_THREADS, 6) x3_rank_first_kernel(RankArgs a
 				sp[tid * F1_ITEMS + e] = v ? posIn[i0 + e] : 0u;
 			}
 		}
-		if ((uint32_t)tid < la) {
+		/* the look-ahead staged behind the tile covers t <= 254; larger t (reference backend.c:21-26
+		 * takes any int) reads the elements further on from global memory */
+		const bool far = la > 256u;
+		if ((uint32_t)tid < (far ? 256u : la)) {
 			const uint32_t i = base + F1_TILE + tid;
 			sk[F1_TILE + tid] = i < m ? keyIn[i] : 0u;
 			sp[F1_TILE + tid] = i < m ? posIn[i] : 0u;
@@ -544,8 +547,12 @@ __global__ void __launch_bounds__(F1_THREADS, 6) x3_rank_first_kernel(RankArgs a
 			if (qq >= n_out) {
 				continue; /* the positions behind the searched range are followers only */
 			}
-			if (base + idx + la < m && ((sk[idx + la] ^ kk) & 255u) == 0u && sp[idx + la] - pp <= D) {
-				continue; /* passes: Lstar >= 1 */
+			if (base + idx + la < m) {
+				const uint32_t kf = far ? keyIn[base + idx + la] : sk[idx + la];
+				const uint32_t pf = far ? posIn[base + idx + la] : sp[idx + la];
+				if (((kf ^ kk) & 255u) == 0u && pf - pp <= D) {
+					continue; /* passes: Lstar >= 1 */
+				}
 			}
 			const uint32_t room = m - 1u - (base + idx);
 			const uint32_t lim = room < (uint32_t)a.t ? room : (uint32_t)a.t;
@@ -556,8 +563,10 @@ __global__ void __launch_bounds__(F1_THREADS, 6) x3_rank_first_kernel(RankArgs a
 				uint32_t kf[4], q[4];
 #pragma unroll
 				for (int u = 0; u < 4; ++u) {
-					kf[u] = sk[idx + j + u];
-					q[u] = sp[idx + j + u];
+					const uint32_t o = idx + j + u;
+					const bool staged = o < (uint32_t)F1_TILE + 256u;
+					kf[u] = staged ? sk[o] : (base + o < m ? keyIn[base + o] : 0u);
+					q[u] = staged ? sp[o] : (base + o < m ? posIn[base + o] : 0u);
 				}
 #pragma unroll
 				for (int u = 0; u < 4; ++u) {
@@ -684,7 +693,10 @@ __global__ void __launch_bounds__(LV_THREADS, LV_CTAS) x3_rank_level_kernel(Rank
 			*reinterpret_cast<uint4 *>(sk + tid * LV_ITEMS + v) = make_uint4(k[v], k[v + 1], k[v + 2], k[v + 3]);
 			*reinterpret_cast<uint4 *>(sp + tid * LV_ITEMS + v) = make_uint4(p[v], p[v + 1], p[v + 2], p[v + 3]);
 		}
-		if ((uint32_t)tid < la) {
+		/* the look-ahead staged behind the tile covers t <= 254; larger t reads the element t+1 places
+		 * further on from global memory */
+		const bool far = la > 256u;
+		if (!far && (uint32_t)tid < la) {
 			const uint32_t i = base + LV_TILE + tid;
 			sk[LV_TILE + tid] = i < m ? keyIn[i] : KEY_NONE;
 			sp[LV_TILE + tid] = i < m ? posIn[i] : 0u;
@@ -701,8 +713,12 @@ __global__ void __launch_bounds__(LV_THREADS, LV_CTAS) x3_rank_level_kernel(Rank
 			const bool out = pp < n_out;
 			bool pass;
 			/* masked compare: no sentinel value exists, so the array bound is checked */
-			pass = valid && out && base + idx + la < m && ((sk[idx + la] ^ kk) & KM) == 0u &&
-			       (sp[idx + la] & PMASK) - pp <= D;
+			pass = valid && out && base + idx + la < m;
+			if (pass) {
+				const uint32_t kf = far ? keyIn[base + idx + la] : sk[idx + la];
+				const uint32_t pf = far ? posIn[base + idx + la] : sp[idx + la];
+				pass = ((kf ^ kk) & KM) == 0u && (pf & PMASK) - pp <= D;
+			}
 			if ((pw & PFLAG) && !pass) {
 				a.lstar[pp] = (uint8_t)(L - 1); /* passed level L-1, stops here */
 			}
@@ -1491,11 +1507,13 @@ cudaError_t rank_chunk_step(const RankCfg &c, RankLane &ln, bool *blocked)
 			/* lv[L-lag+1] as level L-lag left it: its size bounds level L, and tells whether the levels
 			 * queued since were the last ones */
 			volatile uint32_t *rep = s.h_back + 4 * (L - c.lag);
-			if (rep[2] != a.seq) {
+			/* acquire: the size words are read only after the tag (the device orders its stores with
+			 * __threadfence_system; a weakly ordered host CPU must not read them early) */
+			if (__atomic_load_n(&rep[2], __ATOMIC_ACQUIRE) != a.seq) {
 				if ((++ln.spins & 0xfffffu) == 0u) {
 					/* a kernel that died would never report: do not wait on a failed stream */
 					const cudaError_t q = cudaStreamQuery(stream);
-					if (q != cudaErrorNotReady && rep[2] != a.seq) {
+					if (q != cudaErrorNotReady && __atomic_load_n(&rep[2], __ATOMIC_ACQUIRE) != a.seq) {
 						return q == cudaSuccess ? cudaErrorUnknown : q;
 					}
 				}
@@ -1648,7 +1666,7 @@ void x3k_rank_chunking(unsigned long long n, uint32_t D, int lanes, unsigned lon
 cudaError_t x3k_launch_rank_batch(const X3RankBatch &b, uint32_t D, int t, int *launches)
 {
 	cudaError_t e;
-	if (b.lanes < 1 || b.lanes > RANK_MAX_LANES || D > x3k_rank_max_distances() || t > 254) {
+	if (b.lanes < 1 || b.lanes > RANK_MAX_LANES || D > x3k_rank_max_distances()) {
 		return cudaErrorNotSupported;
 	}
 	if (b.n == 0) {
@@ -1798,7 +1816,7 @@ int x3k_rank_default_lanes(unsigned long long n, uint32_t D)
 cudaError_t x3k_launch_rank(const X3SearchParams &prm, cudaStream_t stream, int *launches)
 {
 	cudaError_t e;
-	if (prm.H != nullptr || prm.D > x3k_rank_max_distances() || prm.t > 254) {
+	if (prm.H != nullptr || prm.D > x3k_rank_max_distances()) {
 		return cudaErrorNotSupported;
 	}
 	if (prm.n == 0) {
