@@ -37,14 +37,16 @@ extern "C" {
                               * while t <= 254.  The Lstar-only rank search takes any t (reference backend.c:21-26) */
 
 /* kernel variants */
-#define X3S_KERNEL_DEFAULT   0 /* production choice: the rank search for Lstar alone, the stream kernel when the
-                                * 32-bin table H is requested (or W - 33 > 2^23) */
+#define X3S_KERNEL_DEFAULT   0 /* production choice: for Lstar alone the segment search (W <= 16 KiB, t >= 5) or the
+                                * rank search; the stream kernel when the 32-bin table H is requested (or W - 33 > 2^23) */
 #define X3S_KERNEL_NAIVE     1 /* one thread per position, byte loop; cross-check only */
 #define X3S_KERNEL_BITSLICED 2 /* first bit-sliced version (thread-private u8 histograms); kept for comparison */
 #define X3S_KERNEL_STREAM    3 /* brute-force pair-test kernel (bit-sliced, ALU bound); fast path when t <= 15 and no H */
 #define X3S_KERNEL_STREAM_FULL 4 /* stream kernel, u8 counters forced (what H != NULL or t > 15 selects) */
 #define X3S_KERNEL_RANK      5 /* occurrence-rank search: sorts positions by L-gram level by level; Lstar only
                                 * (d_H must be NULL), cost independent of W and t */
+#define X3S_KERNEL_SEG       6 /* segment search: the rank formulation with a whole segment (positions + window)
+                                * resident in shared memory, one launch; Lstar only, W <= 16 KiB, t >= 5 */
 
 typedef struct x3s_timing {
 	double h2d_ms;    /* host -> device copies (max over GPUs) */

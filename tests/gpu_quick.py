@@ -29,7 +29,7 @@ else:
 ref = None
 for v in variants:
     for rep in range(3):
-        want = check and rep == 0 and v != 5  # the rank search returns Lstar only
+        want = check and rep == 0 and v not in (5, 6)  # the rank and segment searches return Lstar only
         ls, H, tm = pkg.search_host(data, W=W, t=t, variant=v, want_table=want)
         print(f"variant {v} {cfg} n={n} W={W} t={t} rep {rep} table={want}: h2d {tm.h2d_ms:.3f} kernel {tm.kernel_ms:.3f} "
               f"d2h {tm.d2h_ms:.3f} total {tm.total_ms:.3f} ms -> {n / tm.kernel_ms / 1e3:.2f} MB/s, "

@@ -25,7 +25,7 @@ X3S_ERR_CUDA = -1
 X3S_ERR_ARG = -2
 X3S_ERR_UNSUPP = -3
 MAX_MATCH_LEN = 32
-KERNEL_DEFAULT, KERNEL_NAIVE, KERNEL_BITSLICED, KERNEL_STREAM, KERNEL_STREAM_FULL, KERNEL_RANK = 0, 1, 2, 3, 4, 5
+KERNEL_DEFAULT, KERNEL_NAIVE, KERNEL_BITSLICED, KERNEL_STREAM, KERNEL_STREAM_FULL, KERNEL_RANK, KERNEL_SEG = 0, 1, 2, 3, 4, 5, 6
 
 
 class X3SearchError(RuntimeError):

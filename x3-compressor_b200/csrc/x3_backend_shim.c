@@ -124,12 +124,13 @@ void x3_search_prepare(const char *base, size_t isize)
 		clock_gettime(CLOCK_MONOTONIC, &s1);
 		g_startup_ms = (s1.tv_sec - s0.tv_sec) * 1e3 + (s1.tv_nsec - s0.tv_nsec) * 1e-6;
 	}
-	/* The table lives in page-locked memory and the caller's buffer (the reference's malloc'ed iptr,
-	 * x3.c:579) is page-locked where it lies while the tables exist: between page-locked buffers the
-	 * device layer pipelines upload, search and copy back chunk by chunk (x3s_search_host).
-	 * X3_PREPARE_PLAIN=1 keeps both pageable (measurement knob; never changes the table). */
+	/* X3_PREPARE_REGISTER=1 (measurement knob; never changes the table): the table lives in page-locked
+	 * memory and the caller's buffer (the reference's malloc'ed iptr, x3.c:579) is page-locked where it
+	 * lies while the tables exist.  Measured on the B200 box: cudaHostRegister of 212 MB costs 80-130 ms
+	 * and cudaMallocHost of as much 140 ms -- more than the whole search -- so the default leaves both
+	 * pageable and lets the device layer stage them through its own small page-locked ring. */
 	g_register_ms = 0.0;
-	if (isize > 0 && getenv("X3_PREPARE_PLAIN") == NULL && x3s_device_count() > 0) {
+	if (isize > 0 && getenv("X3_PREPARE_REGISTER") != NULL && x3s_device_count() > 0) {
 		struct timespec s0, s1;
 		g_lstar = x3s_host_alloc(isize);
 		g_lstar_pinned = g_lstar != NULL;

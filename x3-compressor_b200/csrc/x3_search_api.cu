@@ -148,9 +148,9 @@ int ensure_stream_scratch(int device)
 int launch_on(int device, int variant, X3SearchParams &prm, cudaStream_t stream, int *launches)
 {
 	Scratch &sc = g_scratch[device];
-	const bool rank = variant == X3S_KERNEL_RANK ||
-	                  (variant == X3S_KERNEL_DEFAULT && prm.H == nullptr && prm.D <= x3k_rank_max_distances());
-	if (!rank && variant != X3S_KERNEL_NAIVE) {
+	const int kind = variant == X3S_KERNEL_DEFAULT ? x3k_default_kind(prm.D, prm.t, prm.H != nullptr)
+	                 : (variant == X3S_KERNEL_RANK ? 1 : (variant == X3S_KERNEL_SEG ? 2 : 0));
+	if (kind == 0 && variant != X3S_KERNEL_NAIVE) {
 		const int rc = ensure_stream_scratch(device);
 		if (rc != X3S_OK) {
 			return rc;
@@ -188,8 +188,13 @@ int check_params(size_t W, int t, const void *H, int variant)
 {
 	/* the rank search (Lstar only) takes any t, like the reference (backend.c:21-26); the brute-force
 	 * kernels count in u8 cells that saturate at 255, which is lossless only while t <= 254 */
-	const bool brute = H != nullptr || (variant != X3S_KERNEL_DEFAULT && variant != X3S_KERNEL_RANK) ||
-	                   (W > X3S_MAX_MATCH_LEN + 1 && W - X3S_MAX_MATCH_LEN - 1 > x3k_rank_max_distances());
+	const size_t Dw = W > X3S_MAX_MATCH_LEN + 1 ? W - X3S_MAX_MATCH_LEN - 1 : 0;
+	const bool brute = H != nullptr || (variant != X3S_KERNEL_DEFAULT && variant != X3S_KERNEL_RANK && variant != X3S_KERNEL_SEG) ||
+	                   Dw > x3k_rank_max_distances();
+	if (variant == X3S_KERNEL_SEG && (H != nullptr || Dw < 1 || Dw > x3k_seg_max_distances() || t < x3k_seg_min_t())) {
+		return fail(X3S_ERR_UNSUPP, "the segment search takes Lstar only, 34 <= W <= %u and t >= %d", x3k_seg_max_distances() + 33u,
+		            x3k_seg_min_t());
+	}
 	if (t > X3S_MAX_T && brute) {
 		return fail(X3S_ERR_UNSUPP, "max match count %d exceeds %d for the 32-bin table / brute-force kernels (u8 cells)", t,
 		            X3S_MAX_T);
@@ -239,7 +244,7 @@ const char *x3s_last_error(void)
 
 const char *x3s_version(void)
 {
-	return "x3-b200 search 0.3 (sm_100a; kernels: rank, stream, bitsliced, naive)";
+	return "x3-b200 search 0.4 (sm_100a; kernels: seg, rank, stream, bitsliced, naive)";
 }
 
 size_t x3s_required_bytes(size_t n_positions, size_t W)
@@ -362,7 +367,83 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 			have = total - a[g];
 		}
 		const uint32_t D = distances(W);
-		const bool rank = H == nullptr && (variant == X3S_KERNEL_RANK || (variant == X3S_KERNEL_DEFAULT && D <= x3k_rank_max_distances()));
+		const int kind = variant == X3S_KERNEL_DEFAULT ? x3k_default_kind(D, t, H != nullptr)
+		                 : (variant == X3S_KERNEL_RANK ? 1 : (variant == X3S_KERNEL_SEG ? 2 : 0));
+		const bool rank = H == nullptr && kind == 1;
+		if (kind == 2 && pinned_io && getenv("X3_HOST_PIECES") == nullptr) {
+			/* Segment search between page-locked buffers, piece by piece: the upload runs ahead on ds.stream,
+			 * a piece (a whole number of segments, 32 MB unless X3_SEG_PIECE_MB says otherwise) is searched on a
+			 * second stream as soon as the bytes it reads -- its own and the window behind them -- have
+			 * arrived, and its Lstar goes back on a third while the next pieces are searched. */
+			const size_t B = x3k_seg_positions(D);
+			const char *pm = getenv("X3_SEG_PIECE_MB");
+			const size_t mb = pm != nullptr && atoi(pm) >= 1 ? (size_t)atoi(pm) : 32;
+			size_t PS = ((mb << 20) / B) * B;
+			if (PS < B) PS = B;
+			const size_t nps = (np + PS - 1) / PS;
+			if (nps >= 2) {
+				if (!ds.pinited) {
+					for (int p = 0; p < X3S_MAX_PIECES; ++p) {
+						CU_TRY(cudaStreamCreateWithFlags(&ds.ps[p], cudaStreamNonBlocking));
+						for (int k = 0; k < 2; ++k) {
+							CU_TRY(cudaEventCreate(&ds.pev[p][k]));
+						}
+					}
+					ds.pinited = true;
+				}
+				while (ds.upev.size() < 2 * nps) {
+					cudaEvent_t ev = nullptr;
+					CU_TRY(cudaEventCreate(&ev));
+					ds.upev.push_back(ev);
+				}
+				cudaStream_t U = ds.stream, K = ds.ps[0], Cc = ds.ps[1];
+				Scratch &sc = g_scratch[dev];
+				CU_TRY(cudaStreamWaitEvent(U, sc.last, 0));
+				CU_TRY(cudaEventRecord(ds.ev[0], U));
+				CU_TRY(cudaStreamWaitEvent(K, ds.ev[0], 0));
+				CU_TRY(cudaStreamWaitEvent(Cc, ds.ev[0], 0));
+				for (size_t q = 0; q < nps; ++q) {
+					const size_t b0 = q * PS, b1 = q + 1 == nps ? have : (q + 1) * PS;
+					CU_TRY(cudaMemcpyAsync(ds.d_x + b0, (const uint8_t *)x + a[g] + b0, b1 - b0, cudaMemcpyHostToDevice, U));
+					if (q + 1 == nps && need > have) {
+						CU_TRY(cudaMemsetAsync(ds.d_x + have, 0, need - have, U));
+					}
+					CU_TRY(cudaEventRecord(ds.upev[q], U));
+				}
+				CU_TRY(cudaEventRecord(ds.ev[1], U));
+				for (size_t q = 0; q < nps; ++q) {
+					const size_t p0 = q * PS, len = np - p0 < PS ? np - p0 : PS;
+					size_t last = (p0 + len + W + 64) / PS; /* the piece that brings the last byte this one reads */
+					if (last >= nps) last = nps - 1;
+					if (q == 0) ds.pfirst = (int)last;
+					CU_TRY(cudaStreamWaitEvent(K, ds.upev[last], 0));
+					X3SearchParams prm;
+					prm.x = ds.d_x + p0;
+					prm.n = len;
+					prm.D = D;
+					prm.t = t;
+					prm.lstar = ds.d_l + p0;
+					prm.H = nullptr;
+					prm.tile_counter = sc.counter;
+					prm.deep = nullptr;
+					prm.ntiles = 0;
+					prm.kd = 0;
+					CU_TRY(x3k_launch_seg(prm, K, &shard_launches[g]));
+					CU_TRY(cudaEventRecord(ds.upev[nps + q], K));
+					CU_TRY(cudaStreamWaitEvent(Cc, ds.upev[nps + q], 0));
+					CU_TRY(cudaMemcpyAsync((uint8_t *)lstar + a[g] + p0, ds.d_l + p0, len, cudaMemcpyDeviceToHost, Cc));
+				}
+				CU_TRY(cudaEventRecord(ds.pev[0][0], K));
+				CU_TRY(cudaEventRecord(ds.pev[1][0], K));
+				CU_TRY(cudaEventRecord(ds.pev[0][1], Cc));
+				CU_TRY(cudaStreamWaitEvent(U, ds.pev[0][0], 0));
+				CU_TRY(cudaStreamWaitEvent(U, ds.pev[0][1], 0));
+				CU_TRY(cudaEventRecord(ds.ev[3], U));
+				CU_TRY(cudaEventRecord(sc.last, U));
+				ds.pieces = 2;
+				return X3S_OK;
+			}
+		}
 		int P = 1;
 		if (rank && getenv("X3_RANK_PROFILE") == nullptr && pinned_io) {
 			const char *hp = getenv("X3_HOST_PIECES"); /* tuning/testing knob; never changes results */

@@ -32,6 +32,8 @@
 #include "x3_search_kernels.cuh"
 #include "x3_search_device.cuh"
 
+#include <cstdlib>
+
 /* ------------------------------------------------------------------------- */
 /* Naive kernel                                                               */
 /* ------------------------------------------------------------------------- */
@@ -470,6 +472,17 @@ cudaError_t x3k_init_device(void)
 }
 
 /* variant: 0/3 stream (production), 1 naive, 2 bitsliced (first version), 4 stream with u8 counters, 5 rank */
+int x3k_default_kind(uint32_t D, int t, bool want_table)
+{
+	if (want_table || D > x3k_rank_max_distances()) {
+		return 0;
+	}
+	if (D >= 1 && D <= x3k_seg_max_distances() && t >= x3k_seg_min_t() && getenv("X3_NO_SEG") == nullptr) {
+		return 2;
+	}
+	return 1;
+}
+
 cudaError_t x3k_launch(int variant, const X3SearchParams &prm, cudaStream_t stream, int *launches)
 {
 	if (prm.n == 0) {
@@ -478,10 +491,15 @@ cudaError_t x3k_launch(int variant, const X3SearchParams &prm, cudaStream_t stre
 	if (launches != nullptr && (variant == 1 || variant == 2)) {
 		*launches += 1;
 	}
-	/* production choice: the rank search whenever only Lstar is wanted (its cost does not grow with
-	 * the window or with t); the brute-force stream kernel for the 32-bin table and for windows
-	 * beyond the rank search's chunking */
-	if (variant == 5 || (variant == 0 && prm.H == nullptr && prm.D <= x3k_rank_max_distances())) {
+	/* production choice when only Lstar is wanted: the segment search while the window fits on chip
+	 * (one launch, HBM traffic = input + result), else the rank search (cost independent of the
+	 * window and of t); the brute-force stream kernel for the 32-bin table and for windows beyond
+	 * the rank search's chunking */
+	const int kind = variant == 0 ? x3k_default_kind(prm.D, prm.t, prm.H != nullptr) : -1;
+	if (variant == 6 || kind == 2) {
+		return x3k_launch_seg(prm, stream, launches);
+	}
+	if (variant == 5 || kind == 1) {
 		return x3k_launch_rank(prm, stream, launches);
 	}
 	if (variant == 1) {

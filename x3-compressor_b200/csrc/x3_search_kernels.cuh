@@ -67,6 +67,17 @@ uint32_t x3k_rank_max_distances(void);
 void x3k_rank_release(int device);
 int x3k_rank_profile(int device, int kind, double *ms, double *elements, int *launches);
 
+/* Segment search (x3_search_seg.cu): Lstar only, windows that fit on chip (1 <= D <=
+ * x3k_seg_max_distances()), t >= x3k_seg_min_t(); one launch, returns at once.  Needs
+ * prm.tile_counter (4 bytes of device memory, zeroed by the launch itself on `stream`). */
+cudaError_t x3k_launch_seg(const X3SearchParams &prm, cudaStream_t stream, int *launches);
+uint32_t x3k_seg_max_distances(void);
+int x3k_seg_min_t(void);
+uint32_t x3k_seg_positions(uint32_t D); /* positions per segment */
+/* what X3S_KERNEL_DEFAULT runs for these parameters: 2 = segment search, 1 = rank search,
+ * 0 = brute-force stream kernel (X3_NO_SEG=1 in the environment takes the segment search out) */
+int x3k_default_kind(uint32_t D, int t, bool want_table);
+
 /* One-time per-device setup (opt-in shared memory size). */
 cudaError_t x3k_init_device(void);
 

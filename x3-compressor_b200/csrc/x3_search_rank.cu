@@ -625,8 +625,10 @@ __global__ void __launch_bounds__(LV_THREADS, LV_CTAS) x3_rank_level_kernel(Rank
 		/* nobody can pass this level (the radix passes did not run either): whoever passed the
 		 * previous one keeps it, and the search is over */
 		if (blockIdx.x == 0) {
+			/* (level 2's input carries no flags -- and was never written when its radix passes returned
+			 * at once: m < t + 2 -- so there is nothing to flush there) */
 			const uint32_t *__restrict__ pu = a.ctrl->lv[L].src0 ? a.pos1 : a.pos0;
-			for (uint32_t i = tid; i < m; i += LV_THREADS) {
+			for (uint32_t i = tid; L > 2 && i < m; i += LV_THREADS) {
 				const uint32_t pw = pu[i];
 				if (pw & PFLAG) {
 					a.lstar[pw & PMASK] = (uint8_t)(L - 1);
@@ -1045,8 +1047,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) x3_rank_tail_kernel(RankArgs a,
 	for (int L = L0; L <= 32; ++L) {
 		uint32_t *K = TL_K(cur), *P = TL_P(cur), *KO = TL_K(cur ^ 1), *PO = TL_P(cur ^ 1);
 		if (m < la + 1u) {
-			/* nobody can pass this level: whoever passed the previous one keeps it */
-			for (uint32_t i = tid; i < m; i += TL_THREADS) {
+			/* nobody can pass this level: whoever passed the previous one keeps it (level 2's input has no
+			 * flags, and is unwritten scratch when its radix passes returned at once) */
+			for (uint32_t i = tid; L > 2 && i < m; i += TL_THREADS) {
 				const uint32_t pw = P[i];
 				if (pw & PFLAG) {
 					a.lstar[pw & PMASK] = (uint8_t)(L - 1);

@@ -1,0 +1,903 @@
+/*
+ * x3_search_seg.cu -- "segment" search: the forward-window search of reference backend.c:58-78
+ * for windows that fit on chip (D = W - 33 <= SG_DMAX), sm_100a.
+ *
+ * Same occurrence-rank formulation as x3_search_rank.cu -- count_L(p) > t  <=>  the (t+1)-th next
+ * occurrence of the L-gram x[p..p+L) starts within D bytes of p; Lstar(p) = the deepest level p
+ * passes -- but nothing except the input and the result ever touches HBM.  Lstar of a position
+ * depends on x[p .. p+W-2] only, so a CTA takes a SEGMENT of B consecutive positions together with
+ * everything they can see, as M = B + D + 3 <= 32768 elements (element e = position a - 3 + e,
+ * 15-bit ids), and runs every level in its 227 KB of shared memory:
+ *
+ *   load      the segment's bytes with one TMA bulk copy (cp.async.bulk + mbarrier, SASS UBLKCP)
+ *   levels 1-4  four stable counting sorts of all M elements on the bytes x[p+3], x[p+2], x[p+1],
+ *             x[p] (LSD).  After the pass on x[p+j] the order is by (x[p+j..p+3], p): the
+ *             level-(4-j) order of the positions q = p + j, so the NEXT pass tests that level
+ *             while it reads its input (look-ahead of t+1 by warp shuffles), and the positions
+ *             with a rare first byte (c1 <= t followers: tc* = c1 - 1 < t) are settled by
+ *             walking those followers (Lstar = min LCP32, 0 when c1 < 2: backend.c:76-78).
+ *   level >= 4  the array is a set of GROUPS (runs of equal L-grams in position order).  A group
+ *             with fewer than t+2 elements can never pass again and is dropped.  A group is
+ *             tested, pruned to the elements within D behind a passed one (the only followers
+ *             that can matter deeper down), and split by the next byte x[p+L] with a stable
+ *             counting sort inside its own index range.  Groups are independent: warps take them
+ *             from a shared-memory queue and follow one child themselves (no CTA barrier below
+ *             level 4); groups larger than SG_SMALL elements are handled by the whole CTA first.
+ *   store     Lstar of the B positions, kept in shared memory (the deepest level passed so far).
+ *
+ * HBM traffic is the algorithmic minimum: every input byte read once (plus the D-byte halo per
+ * segment: (B+D)/B = 1.33 at the default window), every Lstar byte written once.  One launch per
+ * search, no level reports to the host, no chained scans between CTAs; a persistent grid of one
+ * CTA per SM draws segments from a counter.  Any t >= SG_TMIN (queue capacity M / (t+2)), any
+ * t above; other parameters go to the rank search.  Lstar only (the 32-bin table H is the
+ * brute-force kernels' job).  tests/seg_model.py states the same rules in numpy.
+ */
+#include "x3_search_device.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+
+namespace {
+
+constexpr int SG_THREADS = 1024;
+constexpr int SG_WARPS = SG_THREADS / 32;
+constexpr uint32_t SG_MMAX = 32768;          /* elements of a segment: 15-bit ids */
+constexpr uint32_t SG_BMAX = 24592;          /* searched positions of a segment (Lstar staging) */
+constexpr uint32_t SG_XS_OFF = 13;           /* xs[k] = xsr[SG_XS_OFF + k]: the TMA source is 16-byte aligned */
+constexpr uint32_t SG_XS_BYTES = SG_MMAX + 80;
+constexpr uint32_t SG_SMALL = 2048;          /* groups up to this size are refined by one warp */
+constexpr uint32_t SG_Q = 4864;              /* queue slots: live groups <= M / (t+2) */
+constexpr uint32_t SG_BIGQ = 64;             /* live big groups <= M / SG_SMALL */
+constexpr uint32_t SG_NONE = 0xffffffffu;
+constexpr uint32_t Q_VALID = 0x80000000u;
+
+struct SegMisc {
+	unsigned long long mbar;
+	uint32_t dbase[256];
+	uint32_t wsum[36];
+	uint32_t lastp[32];
+	uint32_t q_head, q_tail;
+	int pending;
+	uint32_t big_head, big_tail;
+	uint32_t seg;
+	uint32_t flag;
+	uint2 big[SG_BIGQ];
+};
+
+constexpr size_t SG_OFF_P0 = SG_XS_BYTES;
+constexpr size_t SG_OFF_P1 = SG_OFF_P0 + SG_MMAX * 2;
+constexpr size_t SG_OFF_L8 = SG_OFF_P1 + SG_MMAX * 2;
+constexpr size_t SG_OFF_WH = SG_OFF_L8 + SG_BMAX + 16;
+constexpr size_t SG_OFF_QE = SG_OFF_WH + SG_WARPS * 256 * 2;
+constexpr size_t SG_OFF_QL = SG_OFF_QE + SG_Q * 4;
+constexpr size_t SG_OFF_MISC = (SG_OFF_QL + SG_Q + 15) & ~(size_t)15;
+constexpr size_t SG_SMEM = SG_OFF_MISC + sizeof(SegMisc);
+static_assert(SG_SMEM <= 232448, "segment kernel: shared memory over the 227 KB a CTA can have");
+static_assert(SG_XS_BYTES % 16 == 0 && SG_OFF_L8 % 16 == 0 && SG_OFF_WH % 16 == 0, "alignment");
+
+struct SegArgs {
+	const uint8_t *x;            /* 16-byte aligned, xbytes readable */
+	uint8_t *lstar;
+	unsigned long long n;        /* positions [0, n) */
+	unsigned long long xbytes;   /* multiple of 16 */
+	uint32_t D, B;               /* distances; positions per segment (multiple of 16) */
+	int t;
+	uint32_t nseg;
+	unsigned int *ticket;        /* zeroed before the launch */
+	unsigned long long *prof;    /* NULL, or 8 cycle counters per CTA (X3_SEG_PROF=1): load, pass 0, passes 1-3,
+	                              * level-4 groups, big groups, small groups, store, segments */
+};
+
+/* The CTA's shared memory, addressed through the array itself in every device function, so that the
+ * compiler keeps the accesses in the shared window (LDS/STS, 32-bit addresses). */
+extern __shared__ __align__(128) uint8_t sg_smem[];
+#define SG_XSB (sg_smem)
+#define SG_XSW (reinterpret_cast<const uint32_t *>(sg_smem))
+#define SG_P(buf) (reinterpret_cast<uint16_t *>(sg_smem + SG_OFF_P0) + (size_t)(buf) * SG_MMAX)
+#define SG_L8 (sg_smem + SG_OFF_L8)
+#define SG_WH (reinterpret_cast<uint16_t *>(sg_smem + SG_OFF_WH))
+#define SG_QENT (reinterpret_cast<volatile uint32_t *>(sg_smem + SG_OFF_QE))
+#define SG_QLVL (reinterpret_cast<volatile uint8_t *>(sg_smem + SG_OFF_QL))
+#define SG_MI (reinterpret_cast<SegMisc *>(sg_smem + SG_OFF_MISC))
+
+/* what a segment's phases share besides the shared memory: scalars only (registers) */
+struct SegCtx {
+	uint32_t M, Bs, D, la;
+	int t;
+};
+
+/* the 4 bytes x[p .. p+3] of element e, byte 0 in the low bits */
+__device__ __forceinline__ uint32_t sg_gram(uint32_t e)
+{
+	const uint32_t off = SG_XS_OFF + e;
+	const uint32_t w = off >> 2;
+	return __funnelshift_r(SG_XSW[w], SG_XSW[w + 1], (off & 3u) * 8u);
+}
+
+__device__ __forceinline__ uint32_t sg_byte(uint32_t e, uint32_t L)
+{
+	return SG_XSB[SG_XS_OFF + e + L];
+}
+
+/* ---- offsets of a CTA-wide counting sort: wh[w][d] = count of digit d in warp w's block  ->
+ * wh[w][d] = elements of digit d in the blocks in front of w's, dbase[d] = first slot of digit d.
+ * `drop_below`: digits with fewer elements than this get no slots (dbase = SG_NONE); returns the
+ * total count of digit tid (threads 0..255) for the caller. */
+__device__ __forceinline__ uint32_t sg_offsets(const SegCtx &c, uint32_t drop_below)
+{
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	uint32_t run = 0;
+	if (tid < 256) {
+#pragma unroll 8
+		for (int w = 0; w < SG_WARPS; ++w) {
+			const uint32_t v = SG_WH[w * 256 + tid];
+			SG_WH[w * 256 + tid] = (uint16_t)run;
+			run += v;
+		}
+	}
+	const uint32_t mine = run >= drop_below ? run : 0u;
+	uint32_t inc = mine;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t o = __shfl_up_sync(FULL_MASK, inc, d);
+		if (lane >= d) {
+			inc += o;
+		}
+	}
+	if (lane == 31 && warp < 8) {
+		SG_MI->wsum[warp] = inc;
+	}
+	__syncthreads();
+	if (tid < 256) {
+		uint32_t before = 0;
+		for (int w = 0; w < warp; ++w) {
+			before += SG_MI->wsum[w];
+		}
+		SG_MI->dbase[tid] = run >= drop_below && run > 0 ? before + inc - mine : SG_NONE;
+	}
+	return run;
+}
+
+/* ---- level 1, the rare first bytes: element i of the order by (x[p+3], p) stands for q = p + 3
+ * and has fewer than t+1 followers with its byte within D.  Lstar = the smallest LCP32 over
+ * them, 0 when there are fewer than 2 (backend.c:76-78 collapsed for tc* = c1 - 1). */
+__device__ __noinline__ uint32_t sg_rare(uint32_t inbuf, uint32_t i, uint32_t e, uint32_t M, uint32_t t, uint32_t D)
+{
+	const uint8_t *xq = SG_XSB + SG_XS_OFF + 3;
+	const uint16_t *In = SG_P(inbuf);
+	const uint32_t b = xq[e];
+	uint32_t c1 = 0, best = 32;
+	for (uint32_t j = i + 1; j < M && c1 < t; ++j) {
+		const uint32_t ej = In[j];
+		if (xq[ej] != b || ej - e > D) {
+			break;
+		}
+		++c1;
+		uint32_t l = 1;
+		while (l < best && xq[e + l] == xq[ej + l]) {
+			++l;
+		}
+		best = l;
+	}
+	return c1 >= 2 ? best : 0u;
+}
+
+/* ---- one LSD pass over all M elements: stable counting sort on byte 3-K of the gram.
+ * K >= 1: the input order is the level-K order of the positions q = p + 4 - K; it is tested on
+ * the way (LA32: the look-ahead t+1 <= 32 comes from the neighbouring lanes by shuffle). */
+template <int K, bool LA32, int INBUF>
+__device__ __forceinline__ void sg_lsd_pass(const SegCtx &c)
+{
+	const uint16_t *__restrict__ In = SG_P(INBUF);
+	uint16_t *__restrict__ Out = SG_P(INBUF ^ 1);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t M = c.M;
+	const uint32_t R = (M + 1023u) >> 10;      /* rounds per warp; a warp's block is 32 R elements */
+	const uint32_t blk = (uint32_t)warp * 32u * R;
+	uint16_t *myh = SG_WH + warp * 256;
+	const uint32_t lt = (1u << lane) - 1u;
+	reinterpret_cast<uint4 *>(myh)[lane] = make_uint4(0u, 0u, 0u, 0u);
+	__syncwarp();
+	uint32_t dg[8], rk[16];
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		dg[k] = 0;
+	}
+#pragma unroll
+	for (int k = 0; k < 16; ++k) {
+		rk[k] = 0;
+	}
+	uint32_t e_n = 0, g_n = 0;
+	if (K >= 1 && blk + lane < M) {
+		e_n = In[blk + lane];
+		g_n = sg_gram(e_n);
+	}
+#pragma unroll
+	for (int r = 0; r < 32; ++r) {
+		if ((uint32_t)r < R) {
+			const uint32_t i = blk + 32u * r + lane;
+			const bool valid = i < M;
+			uint32_t d;
+			if (K == 0) {
+				d = valid ? SG_XSB[SG_XS_OFF + i + 3] : 0u;
+			} else {
+				const uint32_t e = e_n, g = g_n;
+				if (i + 32u < M) {
+					e_n = In[i + 32u];
+					g_n = sg_gram(e_n);
+				}
+				d = (g >> (8 * (3 - K))) & 255u;
+				/* level K on the input order: the element t+1 places further on */
+				uint32_t ef, gf;
+				if (LA32) {
+					const int sl = (lane + (int)c.la) & 31;
+					const uint32_t e1 = __shfl_sync(FULL_MASK, e, sl), e2 = __shfl_sync(FULL_MASK, e_n, sl);
+					const uint32_t g1 = __shfl_sync(FULL_MASK, g, sl), g2 = __shfl_sync(FULL_MASK, g_n, sl);
+					const bool here = lane + (int)c.la < 32;
+					ef = here ? e1 : e2;
+					gf = here ? g1 : g2;
+				} else {
+					ef = 0;
+					gf = 0;
+					if (i + c.la < M) {
+						ef = In[i + c.la];
+						gf = sg_gram(ef);
+					}
+				}
+				const uint32_t q = e + 1u - (uint32_t)K;   /* searched position (relative to the segment) */
+				const bool subj = valid && q < c.Bs;
+				const bool pass = subj && i + c.la < M && ((g ^ gf) >> (K == 0 ? 0 : 32 - 8 * K)) == 0u && ef - e <= c.D;
+				if (pass) {
+					SG_L8[q] = (uint8_t)K;
+				} else if (K == 1 && subj) {
+					SG_L8[q] = (uint8_t)sg_rare(INBUF, i, e, M, (uint32_t)c.t, c.D);
+				}
+			}
+			const uint32_t key = valid ? d : 256u + lane;
+			const uint32_t peers = __match_any_sync(FULL_MASK, key);
+			const int leader = __ffs(peers) - 1;
+			uint32_t old = 0;
+			if (lane == leader && valid) {
+				old = myh[d];
+				myh[d] = (uint16_t)(old + __popc(peers));
+			}
+			old = __shfl_sync(FULL_MASK, old, leader);
+			dg[r >> 2] |= d << (8 * (r & 3));
+			rk[r >> 1] |= (old + __popc(peers & lt)) << (16 * (r & 1));
+			__syncwarp();
+		}
+	}
+	__syncthreads();
+	sg_offsets(c, 0u);
+	__syncthreads();
+#pragma unroll
+	for (int r = 0; r < 32; ++r) {
+		if ((uint32_t)r < R) {
+			const uint32_t i = blk + 32u * r + lane;
+			if (i < M) {
+				const uint32_t d = (dg[r >> 2] >> (8 * (r & 3))) & 255u;
+				const uint32_t rank = (rk[r >> 1] >> (16 * (r & 1))) & 0xffffu;
+				const uint32_t e = K == 0 ? i : (uint32_t)In[i];
+				Out[SG_MI->dbase[d] + myh[d] + rank] = (uint16_t)e;
+			}
+		}
+	}
+	__syncthreads();
+}
+
+/* ---- pushing a group: big ones to the CTA's list, the rest to the warps' queue ------------- */
+__device__ __forceinline__ void sg_push(const SegCtx &c, uint32_t start, uint32_t len, uint32_t L, uint32_t buf)
+{
+	if (len > SG_SMALL) {
+		const uint32_t slot = atomicAdd(&SG_MI->big_tail, 1u) % SG_BIGQ;
+		SG_MI->big[slot] = make_uint2(start | (len << 16), L | (buf << 8));
+	} else {
+		atomicAdd(&SG_MI->pending, 1);
+		const uint32_t slot = atomicAdd(&SG_MI->q_tail, 1u) % SG_Q;
+		SG_QLVL[slot] = (uint8_t)L;
+		__threadfence_block();
+		SG_QENT[slot] = Q_VALID | (buf << 26) | ((len - 1u) << 15) | start;
+	}
+}
+
+/* ---- the level-4 groups: heads of the final LSD order, every group of >= t+2 elements pushed */
+__device__ __forceinline__ void sg_groups4(const SegCtx &c, uint32_t buf)
+{
+	const uint16_t *__restrict__ P = SG_P(buf);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t M = c.M;
+	const uint32_t R = (M + 1023u) >> 10;
+	const uint32_t blk = (uint32_t)warp * 32u * R;
+	uint32_t *HB = reinterpret_cast<uint32_t *>(SG_WH);          /* head bits, 32 R words */
+	uint32_t carry = blk > 0 && blk - 1u < M ? sg_gram(P[blk - 1u]) : 0u;
+	for (uint32_t r = 0; r < R; ++r) {
+		const uint32_t i = blk + 32u * r + lane;
+		const bool valid = i < M;
+		const uint32_t g = valid ? sg_gram(P[i]) : 0u;
+		uint32_t gp = __shfl_up_sync(FULL_MASK, g, 1);
+		if (lane == 0) {
+			gp = carry;
+		}
+		const bool head = valid && (i == 0 || g != gp);
+		const uint32_t hm = __ballot_sync(FULL_MASK, head);
+		if (lane == 0) {
+			HB[(blk >> 5) + r] = hm;
+		}
+		carry = __shfl_sync(FULL_MASK, g, 31);
+	}
+	__syncthreads();
+	/* first head at or behind each word, then the first head behind it */
+	const uint32_t nwords = 32u * R;
+	const uint32_t word = (uint32_t)tid < nwords ? HB[tid] : 0u;
+	uint32_t v = word != 0u ? 32u * tid + (uint32_t)(__ffs(word) - 1) : M;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		const uint32_t o = __shfl_down_sync(FULL_MASK, v, d);
+		if (lane + d < 32) {
+			v = min(v, o);
+		}
+	}
+	if (lane == 0) {
+		SG_MI->wsum[warp] = v;
+	}
+	uint32_t nxt = __shfl_down_sync(FULL_MASK, v, 1);
+	if (lane == 31) {
+		nxt = M;
+	}
+	__syncthreads();
+	for (int w = warp + 1; w < SG_WARPS; ++w) {
+		nxt = min(nxt, SG_MI->wsum[w]);
+	}
+	uint32_t bits = word;
+	while (bits != 0u) {
+		const uint32_t start = 32u * tid + (uint32_t)(__ffs(bits) - 1);
+		bits &= bits - 1u;
+		const uint32_t end = bits != 0u ? 32u * tid + (uint32_t)(__ffs(bits) - 1) : nxt;
+		if (end - start >= (uint32_t)c.t + 2u) {
+			sg_push(c, start, end - start, 4u, buf);
+		}
+	}
+	__syncthreads();
+}
+
+/* ---- one level of one group, whole CTA (groups above SG_SMALL elements) --------------------
+ * Three sweeps over the group's range, each warp on a block of it: (A) the test, (B) kept elements
+ * and the histogram of their next bytes, (C) the placement.  The test is cheap and simply
+ * re-evaluated; what crosses warps is the last passed position in front of each block. */
+__device__ __forceinline__ void sg_big_level(const SegCtx &c, uint32_t s, uint32_t g, uint32_t L, uint32_t buf)
+{
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint16_t *__restrict__ In = SG_P(buf) + s;
+	uint16_t *__restrict__ Out = SG_P(buf ^ 1u) + s;
+	const uint32_t R = (g + 1023u) >> 10;
+	const uint32_t blk = (uint32_t)warp * 32u * R;
+	uint16_t *myh = SG_WH + warp * 256;
+	const uint32_t lt = (1u << lane) - 1u;
+	/* the test of element i (relative to s) */
+	auto test = [&](uint32_t i, uint32_t &e) -> bool {
+		e = i < g ? (uint32_t)In[i] & 0x7fffu : 0u;
+		bool pass = false;
+		if (i + c.la < g) {
+			const uint32_t ef = (uint32_t)In[i + c.la] & 0x7fffu;
+			pass = ef - e <= c.D && e - 3u < c.Bs;
+		}
+		return pass;
+	};
+	/* (A) */
+	uint32_t lastp = SG_NONE;
+	for (uint32_t r = 0; r < R; ++r) {
+		uint32_t e;
+		const bool pass = test(blk + 32u * r + lane, e);
+		if (pass) {
+			SG_L8[e - 3u] = (uint8_t)L;
+		}
+		const uint32_t pm = __ballot_sync(FULL_MASK, pass);
+		if (pm != 0u) {
+			lastp = __shfl_sync(FULL_MASK, e, 31 - __clz((int)pm));
+		}
+	}
+	if (lane == 0) {
+		SG_MI->lastp[warp] = lastp;
+	}
+	reinterpret_cast<uint4 *>(myh)[lane] = make_uint4(0u, 0u, 0u, 0u);
+	const int any = __syncthreads_or(lastp != SG_NONE);
+	if (!any || L >= 32u) {
+		return; /* nobody passed: the group is finished (uniform over the CTA) */
+	}
+	/* the last passed position in front of my block */
+	uint32_t carry0;
+	{
+		const uint32_t lp = lane < warp ? SG_MI->lastp[lane] : SG_NONE;
+		const uint32_t have = __ballot_sync(FULL_MASK, lp != SG_NONE);
+		carry0 = SG_NONE;
+		if (have != 0u) {
+			carry0 = __shfl_sync(FULL_MASK, lp, 31 - __clz((int)have));
+		}
+	}
+	/* kept and next byte of the element of round r: shared by (B) and (C) */
+	auto kept_byte = [&](uint32_t r, uint32_t &carry, uint32_t &e, uint32_t &b) -> bool {
+		const uint32_t i = blk + 32u * r + lane;
+		const bool pass = test(i, e);
+		const uint32_t pm = __ballot_sync(FULL_MASK, pass);
+		const uint32_t upto = pm & ((2u << lane) - 1u);
+		const uint32_t src = upto != 0u ? 31 - __clz((int)upto) : 0;
+		const uint32_t lpv = __shfl_sync(FULL_MASK, e, src);
+		const uint32_t lp = upto != 0u ? lpv : carry;
+		const bool kept = i < g && lp != SG_NONE && e - lp <= c.D;
+		if (pm != 0u) {
+			carry = __shfl_sync(FULL_MASK, e, 31 - __clz((int)pm));
+		}
+		b = kept ? sg_byte(e, L) : 256u + lane;
+		return kept;
+	};
+	/* (B) */
+	{
+		uint32_t carry = carry0;
+		for (uint32_t r = 0; r < R; ++r) {
+			uint32_t e, b;
+			const bool kept = kept_byte(r, carry, e, b);
+			const uint32_t peers = __match_any_sync(FULL_MASK, b);
+			if (kept && lane == __ffs(peers) - 1) {
+				myh[b] = (uint16_t)(myh[b] + __popc(peers));
+			}
+			__syncwarp();
+		}
+	}
+	__syncthreads();
+	const uint32_t total = sg_offsets(c, (uint32_t)c.t + 2u);
+	/* all elements kept and followed by one and the same byte: the group stays where it is */
+	const int whole = __syncthreads_or(tid < 256 && total == g);
+	if (whole) {
+		if (tid == 0) {
+			sg_push(c, s, g, L + 1u, buf);
+		}
+		return;
+	}
+	/* (C) */
+	{
+		uint32_t carry = carry0;
+		for (uint32_t r = 0; r < R; ++r) {
+			uint32_t e, b;
+			const bool kept = kept_byte(r, carry, e, b);
+			const uint32_t base = kept ? SG_MI->dbase[b] : SG_NONE;
+			const bool act = kept && base != SG_NONE;
+			const uint32_t peers = __match_any_sync(FULL_MASK, act ? b : 256u + lane);
+			if (act) {
+				const uint32_t o = myh[b];
+				Out[base + o + __popc(peers & lt)] = (uint16_t)e;
+			}
+			__syncwarp();
+			if (act && lane == __ffs(peers) - 1) {
+				myh[b] = (uint16_t)(myh[b] + __popc(peers));
+			}
+			__syncwarp();
+		}
+	}
+	__syncthreads();
+	if (tid < 256 && SG_MI->dbase[tid] != SG_NONE) {
+		sg_push(c, s + SG_MI->dbase[tid], total, L + 1u, buf ^ 1u);
+	}
+}
+
+/* ---- a group of at most SG_SMALL elements, one warp, down to the level where it ends --------
+ * Sweep 1: test, mark the kept elements (bit 15 of the element, the input range is this warp's),
+ * histogram of their next bytes.  Sweep 2: placement in the group's own range of the other
+ * buffer.  The warp goes on with one child itself and queues the others. */
+__device__ __forceinline__ void sg_small_chain(const SegCtx &c, uint32_t start, uint32_t len, uint32_t L, uint32_t buf)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint16_t *myh = SG_WH + warp * 256;
+	const uint32_t lt = (1u << lane) - 1u;
+	const uint32_t need = (uint32_t)c.t + 2u;
+	for (;;) {
+		uint16_t *In = SG_P(buf) + start;
+		uint16_t *Out = SG_P(buf ^ 1u) + start;
+		reinterpret_cast<uint4 *>(myh)[lane] = make_uint4(0u, 0u, 0u, 0u);
+		__syncwarp();
+		uint32_t carry = SG_NONE, anypass = 0, nkept = 0, firstb = SG_NONE;
+		bool multi = false;
+		const uint32_t R = (len + 31u) >> 5;
+		for (uint32_t r = 0; r < R; ++r) {
+			const uint32_t i = 32u * r + lane;
+			const uint32_t e = i < len ? (uint32_t)In[i] & 0x7fffu : 0u;
+			bool pass = false;
+			if (i + c.la < len) {
+				const uint32_t ef = (uint32_t)In[i + c.la] & 0x7fffu;
+				pass = ef - e <= c.D && e - 3u < c.Bs;
+			}
+			if (pass) {
+				SG_L8[e - 3u] = (uint8_t)L;
+			}
+			const uint32_t pm = __ballot_sync(FULL_MASK, pass);
+			anypass |= pm;
+			if (L < 32u) {
+				const uint32_t upto = pm & ((2u << lane) - 1u);
+				const uint32_t src = upto != 0u ? 31 - __clz((int)upto) : 0;
+				const uint32_t lpv = __shfl_sync(FULL_MASK, e, src);
+				const uint32_t lp = upto != 0u ? lpv : carry;
+				const bool kept = i < len && lp != SG_NONE && e - lp <= c.D;
+				if (pm != 0u) {
+					carry = __shfl_sync(FULL_MASK, e, 31 - __clz((int)pm));
+				}
+				const uint32_t b = kept ? sg_byte(e, L) : 256u + lane;
+				const uint32_t peers = __match_any_sync(FULL_MASK, b);
+				const uint32_t km = __ballot_sync(FULL_MASK, kept);
+				if (i < len) {
+					In[i] = (uint16_t)(kept ? e | 0x8000u : e); /* (a group that stayed in place carries old marks) */
+				}
+				if (kept && lane == __ffs(peers) - 1) {
+					myh[b] = (uint16_t)(myh[b] + __popc(peers));
+				}
+				if (km != 0u) {
+					const int fl = __ffs(km) - 1;
+					const uint32_t fb = __shfl_sync(FULL_MASK, b, fl);
+					const uint32_t fp = __shfl_sync(FULL_MASK, peers, fl);
+					if (firstb == SG_NONE) {
+						firstb = fb;
+					}
+					multi = multi || fb != firstb || fp != km;
+					nkept += __popc(km);
+				}
+				__syncwarp();
+			}
+		}
+		if (anypass == 0u || L >= 32u || nkept < need) {
+			return; /* nobody passed / the last level / too few left to pass again */
+		}
+		if (!multi) {
+			/* one and the same next byte behind every kept element: a single child */
+			if (nkept == len) {
+				L += 1u; /* nothing pruned either: it stays where it is (marks are masked on reading) */
+				continue;
+			}
+			uint32_t base = 0;
+			for (uint32_t r = 0; r < R; ++r) {
+				const uint32_t i = 32u * r + lane;
+				const uint32_t ew = i < len ? (uint32_t)In[i] : 0u;
+				const uint32_t km = __ballot_sync(FULL_MASK, (ew & 0x8000u) != 0u);
+				if (ew & 0x8000u) {
+					Out[base + __popc(km & lt)] = (uint16_t)(ew & 0x7fffu);
+				}
+				base += __popc(km);
+			}
+			__syncwarp();
+			len = nkept;
+			buf ^= 1u;
+			L += 1u;
+			continue;
+		}
+		/* slots of the children: bins of >= t+2 elements, in byte order */
+		uint32_t cnt[8], off[8];
+		uint32_t mine = 0;
+		{
+			const uint4 hv = reinterpret_cast<const uint4 *>(myh)[lane];
+			const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				cnt[k] = (hw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+				mine += cnt[k] >= need ? cnt[k] : 0u;
+			}
+		}
+		uint32_t inc = mine;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t o = __shfl_up_sync(FULL_MASK, inc, d);
+			if (lane >= d) {
+				inc += o;
+			}
+		}
+		uint32_t run = inc - mine, nchild = 0;
+		{
+			uint32_t hw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				const bool alive = cnt[k] >= need;
+				off[k] = alive ? run : 0xffffu;
+				hw[k >> 1] |= off[k] << (16 * (k & 1));
+				run += alive ? cnt[k] : 0u;
+				nchild += alive ? 1u : 0u;
+			}
+			reinterpret_cast<uint4 *>(myh)[lane] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+		}
+		const uint32_t cm = __ballot_sync(FULL_MASK, nchild != 0u);
+		if (cm == 0u) {
+			return; /* every child too small to pass again */
+		}
+		__syncwarp();
+		/* sweep 2: placement */
+		for (uint32_t r = 0; r < R; ++r) {
+			const uint32_t i = 32u * r + lane;
+			const uint32_t ew = i < len ? (uint32_t)In[i] : 0u;
+			const bool kept = (ew & 0x8000u) != 0u;
+			const uint32_t e = ew & 0x7fffu;
+			const uint32_t b = kept ? sg_byte(e, L) : 0u;
+			const uint32_t o = kept ? (uint32_t)myh[b] : 0xffffu;
+			const bool act = o != 0xffffu;
+			const uint32_t peers = __match_any_sync(FULL_MASK, act ? b : 256u + lane);
+			if (act) {
+				Out[o + __popc(peers & lt)] = (uint16_t)e;
+			}
+			__syncwarp();
+			if (act && lane == __ffs(peers) - 1) {
+				myh[b] = (uint16_t)(o + __popc(peers));
+			}
+			__syncwarp();
+		}
+		/* the first child is mine, the others are queued (their elements are written: publish behind a fence) */
+		const int fl = __ffs(cm) - 1;
+		uint32_t mystart = 0, mylen = 0;
+		bool took = false;
+		__threadfence_block();
+		__syncwarp();
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			if (off[k] != 0xffffu) {
+				if (lane == fl && !took) {
+					mystart = off[k];
+					mylen = cnt[k];
+					took = true;
+				} else {
+					sg_push(c, start + off[k], cnt[k], L + 1u, buf ^ 1u);
+				}
+			}
+		}
+		start += __shfl_sync(FULL_MASK, mystart, fl);
+		len = __shfl_sync(FULL_MASK, mylen, fl);
+		buf ^= 1u;
+		L += 1u;
+	}
+}
+
+__global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
+{
+	SegCtx c;
+	c.D = a.D;
+	c.t = a.t;
+	c.la = (uint32_t)a.t + 1u;
+	const int tid = threadIdx.x, lane = tid & 31;
+	uint64_t *bar = reinterpret_cast<uint64_t *>(&SG_MI->mbar);
+
+	if (tid == 0) {
+		mbar_init(bar, 1);
+	}
+	for (uint32_t i = tid; i < SG_Q; i += SG_THREADS) {
+		SG_QENT[i] = 0u;
+	}
+	__syncthreads();
+	uint32_t phase = 0;
+	unsigned long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = clock64();
+#define SG_LAP(k)                                  \
+	if (a.prof != nullptr && tid == 0) {           \
+		const unsigned long long now = clock64();  \
+		pt[k] += now - tp;                         \
+		tp = now;                                  \
+	}
+	for (;;) {
+		if (tid == 0) {
+			SG_MI->seg = atomicAdd(a.ticket, 1u);
+			SG_MI->q_head = SG_MI->q_tail = 0u;
+			SG_MI->pending = 0;
+			SG_MI->big_head = SG_MI->big_tail = 0u;
+		}
+		__syncthreads();
+		const uint32_t seg = SG_MI->seg;
+		if (seg >= a.nseg) {
+			break;
+		}
+		const unsigned long long a0 = (unsigned long long)seg * a.B;
+		c.Bs = (uint32_t)(a.n - a0 < a.B ? a.n - a0 : a.B);
+		c.M = c.Bs + a.D + 3u;
+		/* the segment's bytes: xs[k] = x[a0 - 3 + k], k in [0, M + 48); virtual zeros in front of the input */
+		{
+			const uint32_t want = ((a0 == 0 ? 0u : 16u) + c.M + 48u + 15u) & ~15u; /* bytes from x[a0 - 16] (or x[0]) */
+			const unsigned long long src = a0 == 0 ? 0ull : a0 - 16ull;
+			const unsigned long long avail = a.xbytes > src ? a.xbytes - src : 0ull;
+			const uint32_t bytes = (uint32_t)(avail < want ? avail : want) & ~15u;
+			uint8_t *dst = SG_XSB + (a0 == 0 ? 16 : 0);
+			if (tid == 0) {
+				/* the previous segment read this memory through the generic proxy */
+				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+				mbar_expect_tx(bar, bytes);
+				for (uint32_t o = 0; o < bytes; o += 16384u) {
+					tma_load_1d(dst + o, a.x + src + o, bytes - o < 16384u ? bytes - o : 16384u, bar);
+				}
+			}
+			/* what the copy does not cover: the virtual bytes in front, the tail behind the readable range */
+			if (a0 == 0 && tid < 16) {
+				SG_XSB[tid] = 0;
+			}
+			for (uint32_t o = (a0 == 0 ? 16u : 0u) + bytes + tid; o < SG_XS_BYTES; o += SG_THREADS) {
+				SG_XSB[o] = 0;
+			}
+			mbar_wait(bar, phase);
+			phase ^= 1u;
+			__syncthreads();
+		}
+		SG_LAP(0)
+		/* levels 1 .. 4 */
+		sg_lsd_pass<0, true, 0>(c);  /* (reads the bytes in position order) -> buffer 1 */
+		SG_LAP(1)
+		if (c.la <= 32u) {
+			sg_lsd_pass<1, true, 1>(c);
+			sg_lsd_pass<2, true, 0>(c);
+			sg_lsd_pass<3, true, 1>(c);
+		} else {
+			sg_lsd_pass<1, false, 1>(c);
+			sg_lsd_pass<2, false, 0>(c);
+			sg_lsd_pass<3, false, 1>(c);
+		}
+		SG_LAP(2)
+		sg_groups4(c, 0u);
+		SG_LAP(3)
+		/* big groups, whole CTA, one level at a time */
+		for (;;) {
+			__syncthreads();
+			const uint32_t h = SG_MI->big_head, tl = SG_MI->big_tail;
+			__syncthreads();
+			if (h == tl) {
+				break;
+			}
+			const uint2 be = SG_MI->big[h % SG_BIGQ];
+			if (tid == 0) {
+				SG_MI->big_head = h + 1u;
+			}
+			sg_big_level(c, be.x & 0xffffu, be.x >> 16, be.y & 255u, (be.y >> 8) & 1u);
+		}
+		SG_LAP(4)
+		/* small groups: the warps drain the queue */
+		for (;;) {
+			uint32_t ent = 0, L = 0;
+			if (lane == 0) {
+				const uint32_t slot = atomicAdd(&SG_MI->q_head, 1u) % SG_Q;
+				for (;;) {
+					ent = SG_QENT[slot];
+					if (ent & Q_VALID) {
+						__threadfence_block();
+						L = SG_QLVL[slot];
+						SG_QENT[slot] = 0u;
+						break;
+					}
+					if (*(volatile int *)&SG_MI->pending == 0) {
+						ent = 0;
+						break;
+					}
+					__nanosleep(200); /* nothing queued yet: leave the issue slots to the warps that work */
+				}
+			}
+			ent = __shfl_sync(FULL_MASK, ent, 0);
+			L = __shfl_sync(FULL_MASK, L, 0);
+			if (ent == 0u) {
+				break;
+			}
+			__threadfence_block();
+			sg_small_chain(c, ent & 0x7fffu, ((ent >> 15) & 0x7ffu) + 1u, L, (ent >> 26) & 1u);
+			__syncwarp();
+			if (lane == 0) {
+				atomicSub(&SG_MI->pending, 1);
+			}
+		}
+		__syncthreads();
+		SG_LAP(5)
+		/* Lstar of the segment */
+		{
+			uint8_t *dst = a.lstar + a0;
+			if (((uintptr_t)dst & 15u) == 0u) {
+				const uint32_t nv = c.Bs >> 4;
+				for (uint32_t v = tid; v < nv; v += SG_THREADS) {
+					reinterpret_cast<uint4 *>(dst)[v] = reinterpret_cast<const uint4 *>(SG_L8)[v];
+				}
+				for (uint32_t o = (nv << 4) + tid; o < c.Bs; o += SG_THREADS) {
+					dst[o] = SG_L8[o];
+				}
+			} else {
+				for (uint32_t o = tid; o < c.Bs; o += SG_THREADS) {
+					dst[o] = SG_L8[o];
+				}
+			}
+		}
+		__syncthreads();
+		SG_LAP(6)
+		pt[7] += 1;
+	}
+	if (a.prof != nullptr && tid == 0) {
+		for (int k = 0; k < 8; ++k) {
+			a.prof[blockIdx.x * 8 + k] = pt[k];
+		}
+	}
+#undef SG_LAP
+}
+
+} /* namespace */
+
+/* largest number of distances and smallest t the segment kernel takes */
+uint32_t x3k_seg_max_distances(void)
+{
+	return 16351u; /* W <= 16 KB: B >= 16 400 positions per segment */
+}
+
+int x3k_seg_min_t(void)
+{
+	/* live groups of >= t+2 elements must fit the queue: (M - 1) / (t + 2) + 1 <= SG_Q */
+	int t = 1;
+	while ((SG_MMAX - 1u) / (uint32_t)(t + 2) + 1u > SG_Q) {
+		++t;
+	}
+	return t;
+}
+
+/* positions per segment for D distances */
+uint32_t x3k_seg_positions(uint32_t D)
+{
+	uint32_t B = (SG_MMAX - D - 3u) & ~15u;
+	return B < SG_BMAX ? B : SG_BMAX;
+}
+
+cudaError_t x3k_launch_seg(const X3SearchParams &prm, cudaStream_t stream, int *launches)
+{
+	cudaError_t e;
+	if (prm.H != nullptr || prm.D == 0 || prm.D > x3k_seg_max_distances() || prm.t < x3k_seg_min_t() ||
+	    prm.tile_counter == nullptr) {
+		return cudaErrorNotSupported;
+	}
+	if (prm.n == 0) {
+		return cudaSuccess;
+	}
+	int dev = 0, sms = 0;
+	if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+	if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+	static bool attr_set[64] = {false};
+	if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+		if ((e = cudaFuncSetAttribute(x3_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM)) != cudaSuccess) return e;
+		attr_set[dev] = true;
+	}
+	SegArgs a;
+	a.x = prm.x;
+	a.lstar = prm.lstar;
+	a.n = prm.n;
+	a.xbytes = (unsigned long long)x3k_required_bytes((size_t)prm.n, (size_t)prm.D + 33u) & ~15ull;
+	a.D = prm.D;
+	a.B = x3k_seg_positions(prm.D);
+	a.t = prm.t;
+	const unsigned long long nseg = (prm.n + a.B - 1) / a.B;
+	if (nseg > 0xffffffffull) {
+		return cudaErrorNotSupported;
+	}
+	a.nseg = (uint32_t)nseg;
+	a.ticket = prm.tile_counter;
+	a.prof = nullptr;
+	if ((e = cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
+	const unsigned grid = nseg < (unsigned long long)sms ? (unsigned)nseg : (unsigned)sms;
+	const bool prof = getenv("X3_SEG_PROF") != nullptr; /* measurement knob: cycles per phase, printed */
+	if (prof) {
+		if ((e = cudaMalloc((void **)&a.prof, (size_t)grid * 64)) != cudaSuccess) return e;
+		if ((e = cudaMemsetAsync(a.prof, 0, (size_t)grid * 64, stream)) != cudaSuccess) return e;
+	}
+	x3_seg_kernel<<<grid, SG_THREADS, SG_SMEM, stream>>>(a);
+	if (launches != nullptr) {
+		*launches += 1;
+	}
+	if (prof) {
+		unsigned long long *h = (unsigned long long *)malloc((size_t)grid * 64);
+		if (h != nullptr && cudaStreamSynchronize(stream) == cudaSuccess &&
+		    cudaMemcpy(h, a.prof, (size_t)grid * 64, cudaMemcpyDeviceToHost) == cudaSuccess) {
+			static const char *name[7] = {"load", "pass 0", "passes 1-3", "groups4", "big groups", "small groups", "store"};
+			double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
+			for (unsigned b = 0; b < grid; ++b) {
+				double cta = 0;
+				for (int k = 0; k < 8; ++k) {
+					tot[k] += (double)h[b * 8 + k];
+					cta += k < 7 ? (double)h[b * 8 + k] : 0;
+				}
+				if (cta > mx) mx = cta;
+			}
+			fprintf(stderr, "x3_seg_kernel: %u CTAs, %.0f segments, busiest CTA %.0f cycles; cycles per segment:", grid, tot[7], mx);
+			for (int k = 0; k < 7; ++k) {
+				fprintf(stderr, "  %s %.0f", name[k], tot[k] / (tot[7] > 0 ? tot[7] : 1));
+			}
+			fprintf(stderr, "\n");
+		}
+		free(h);
+		cudaFree(a.prof);
+	}
+	return cudaGetLastError();
+}
