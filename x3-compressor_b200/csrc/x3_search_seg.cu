@@ -45,11 +45,18 @@ constexpr uint32_t SG_MMAX = 32768;          /* elements of a segment: 15-bit id
 constexpr uint32_t SG_BMAX = 24592;          /* searched positions of a segment (Lstar staging) */
 constexpr uint32_t SG_XS_OFF = 13;           /* xs[k] = xsr[SG_XS_OFF + k]: the TMA source is 16-byte aligned */
 constexpr uint32_t SG_XS_BYTES = SG_MMAX + 80;
-constexpr uint32_t SG_SMALL = 2048;          /* groups up to this size are refined by one warp */
-constexpr uint32_t SG_Q = 4864;              /* queue slots: live groups <= M / (t+2) */
-constexpr uint32_t SG_BIGQ = 64;             /* live big groups <= M / SG_SMALL */
+constexpr uint32_t SG_CHUNK = 256;           /* elements a warp takes per wave: one histogram row */
+constexpr uint32_t SG_WAVE_MAX = 32 * SG_CHUNK; /* groups up to this size go through the waves (<= 32 rows) */
+constexpr uint32_t SG_Q = 4864;              /* ring slots: live groups <= M / (t+2) */
+constexpr uint32_t SG_BIGQ = 16;             /* live groups above SG_WAVE_MAX: <= M / SG_WAVE_MAX */
 constexpr uint32_t SG_NONE = 0xffffffffu;
 constexpr uint32_t Q_VALID = 0x80000000u;
+
+/* a group of a wave: rows [r0, r0 + nrows) of the histogram, what the ring entry said, and what
+ * became of it (state: 0 = its elements are placed, 1 = nothing to place) */
+struct SegGroup {
+	uint32_t start, len, L, buf, r0, nrows, state, pad;
+};
 
 struct SegMisc {
 	unsigned long long mbar;
@@ -57,11 +64,11 @@ struct SegMisc {
 	uint32_t wsum[36];
 	uint32_t lastp[32];
 	uint32_t q_head, q_tail;
-	int pending;
 	uint32_t big_head, big_tail;
 	uint32_t seg;
-	uint32_t flag;
+	uint32_t wave_groups, wave_rows;
 	uint2 big[SG_BIGQ];
+	SegGroup grp[32];
 };
 
 constexpr size_t SG_OFF_P0 = SG_XS_BYTES;
@@ -96,8 +103,8 @@ extern __shared__ __align__(128) uint8_t sg_smem[];
 #define SG_P(buf) (reinterpret_cast<uint16_t *>(sg_smem + SG_OFF_P0) + (size_t)(buf) * SG_MMAX)
 #define SG_L8 (sg_smem + SG_OFF_L8)
 #define SG_WH (reinterpret_cast<uint16_t *>(sg_smem + SG_OFF_WH))
-#define SG_QENT (reinterpret_cast<volatile uint32_t *>(sg_smem + SG_OFF_QE))
-#define SG_QLVL (reinterpret_cast<volatile uint8_t *>(sg_smem + SG_OFF_QL))
+#define SG_QENT (reinterpret_cast<uint32_t *>(sg_smem + SG_OFF_QE))
+#define SG_QLVL (sg_smem + SG_OFF_QL)
 #define SG_MI (reinterpret_cast<SegMisc *>(sg_smem + SG_OFF_MISC))
 
 /* what a segment's phases share besides the shared memory: scalars only (registers) */
@@ -285,18 +292,17 @@ __device__ __forceinline__ void sg_lsd_pass(const SegCtx &c)
 	__syncthreads();
 }
 
-/* ---- pushing a group: big ones to the CTA's list, the rest to the warps' queue ------------- */
-__device__ __forceinline__ void sg_push(const SegCtx &c, uint32_t start, uint32_t len, uint32_t L, uint32_t buf)
+/* ---- pushing a group: the ring of the waves, or the list of the few groups too large for them.
+ * (Entries are read behind a CTA barrier: no flags, no fences.) */
+__device__ __forceinline__ void sg_push(uint32_t start, uint32_t len, uint32_t L, uint32_t buf)
 {
-	if (len > SG_SMALL) {
+	if (len > SG_WAVE_MAX) {
 		const uint32_t slot = atomicAdd(&SG_MI->big_tail, 1u) % SG_BIGQ;
 		SG_MI->big[slot] = make_uint2(start | (len << 16), L | (buf << 8));
 	} else {
-		atomicAdd(&SG_MI->pending, 1);
 		const uint32_t slot = atomicAdd(&SG_MI->q_tail, 1u) % SG_Q;
 		SG_QLVL[slot] = (uint8_t)L;
-		__threadfence_block();
-		SG_QENT[slot] = Q_VALID | (buf << 26) | ((len - 1u) << 15) | start;
+		SG_QENT[slot] = (buf << 28) | ((len - 1u) << 15) | start;
 	}
 }
 
@@ -354,13 +360,13 @@ __device__ __forceinline__ void sg_groups4(const SegCtx &c, uint32_t buf)
 		bits &= bits - 1u;
 		const uint32_t end = bits != 0u ? 32u * tid + (uint32_t)(__ffs(bits) - 1) : nxt;
 		if (end - start >= (uint32_t)c.t + 2u) {
-			sg_push(c, start, end - start, 4u, buf);
+			sg_push(start, end - start, 4u, buf);
 		}
 	}
 	__syncthreads();
 }
 
-/* ---- one level of one group, whole CTA (groups above SG_SMALL elements) --------------------
+/* ---- one level of one group, whole CTA (groups above SG_WAVE_MAX elements) --------------------
  * Three sweeps over the group's range, each warp on a block of it: (A) the test, (B) kept elements
  * and the histogram of their next bytes, (C) the placement.  The test is cheap and simply
  * re-evaluated; what crosses warps is the last passed position in front of each block. */
@@ -449,7 +455,7 @@ __device__ __forceinline__ void sg_big_level(const SegCtx &c, uint32_t s, uint32
 	const int whole = __syncthreads_or(tid < 256 && total == g);
 	if (whole) {
 		if (tid == 0) {
-			sg_push(c, s, g, L + 1u, buf);
+			sg_push(s, g, L + 1u, buf);
 		}
 		return;
 	}
@@ -475,110 +481,34 @@ __device__ __forceinline__ void sg_big_level(const SegCtx &c, uint32_t s, uint32
 	}
 	__syncthreads();
 	if (tid < 256 && SG_MI->dbase[tid] != SG_NONE) {
-		sg_push(c, s + SG_MI->dbase[tid], total, L + 1u, buf ^ 1u);
+		sg_push(s + SG_MI->dbase[tid], total, L + 1u, buf ^ 1u);
 	}
 }
 
-/* ---- a group of at most SG_SMALL elements, one warp, down to the level where it ends --------
- * Sweep 1: test, mark the kept elements (bit 15 of the element, the input range is this warp's),
- * histogram of their next bytes.  Sweep 2: placement in the group's own range of the other
- * buffer.  The warp goes on with one child itself and queues the others. */
-__device__ __forceinline__ void sg_small_chain(const SegCtx &c, uint32_t start, uint32_t len, uint32_t L, uint32_t buf)
+/* ---- one wave: the next groups of the ring, up to 32 rows of SG_CHUNK elements, one warp per row.
+ * A group of the ring (any level) is tested, pruned to its kept elements and split by the next byte;
+ * its children go to the ring's tail.  Per wave: (form) warp 0 takes groups while their rows fit,
+ * (1a) test + last passed position of every row, (1b) kept elements, next bytes, per-row histogram
+ * (each lane keeps its 8 elements with byte and rank in registers), (A) one warp per group: totals,
+ * children, final offsets written back into the rows, (2) placement.  Returns false when the ring
+ * is empty. */
+__device__ __forceinline__ bool sg_wave(const SegCtx &c)
 {
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	uint16_t *myh = SG_WH + warp * 256;
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t lt = (1u << lane) - 1u;
 	const uint32_t need = (uint32_t)c.t + 2u;
-	for (;;) {
-		uint16_t *In = SG_P(buf) + start;
-		uint16_t *Out = SG_P(buf ^ 1u) + start;
-		reinterpret_cast<uint4 *>(myh)[lane] = make_uint4(0u, 0u, 0u, 0u);
-		__syncwarp();
-		uint32_t carry = SG_NONE, anypass = 0, nkept = 0, firstb = SG_NONE;
-		bool multi = false;
-		const uint32_t R = (len + 31u) >> 5;
-		for (uint32_t r = 0; r < R; ++r) {
-			const uint32_t i = 32u * r + lane;
-			const uint32_t e = i < len ? (uint32_t)In[i] & 0x7fffu : 0u;
-			bool pass = false;
-			if (i + c.la < len) {
-				const uint32_t ef = (uint32_t)In[i + c.la] & 0x7fffu;
-				pass = ef - e <= c.D && e - 3u < c.Bs;
-			}
-			if (pass) {
-				SG_L8[e - 3u] = (uint8_t)L;
-			}
-			const uint32_t pm = __ballot_sync(FULL_MASK, pass);
-			anypass |= pm;
-			if (L < 32u) {
-				const uint32_t upto = pm & ((2u << lane) - 1u);
-				const uint32_t src = upto != 0u ? 31 - __clz((int)upto) : 0;
-				const uint32_t lpv = __shfl_sync(FULL_MASK, e, src);
-				const uint32_t lp = upto != 0u ? lpv : carry;
-				const bool kept = i < len && lp != SG_NONE && e - lp <= c.D;
-				if (pm != 0u) {
-					carry = __shfl_sync(FULL_MASK, e, 31 - __clz((int)pm));
-				}
-				const uint32_t b = kept ? sg_byte(e, L) : 256u + lane;
-				const uint32_t peers = __match_any_sync(FULL_MASK, b);
-				const uint32_t km = __ballot_sync(FULL_MASK, kept);
-				if (i < len) {
-					In[i] = (uint16_t)(kept ? e | 0x8000u : e); /* (a group that stayed in place carries old marks) */
-				}
-				if (kept && lane == __ffs(peers) - 1) {
-					myh[b] = (uint16_t)(myh[b] + __popc(peers));
-				}
-				if (km != 0u) {
-					const int fl = __ffs(km) - 1;
-					const uint32_t fb = __shfl_sync(FULL_MASK, b, fl);
-					const uint32_t fp = __shfl_sync(FULL_MASK, peers, fl);
-					if (firstb == SG_NONE) {
-						firstb = fb;
-					}
-					multi = multi || fb != firstb || fp != km;
-					nkept += __popc(km);
-				}
-				__syncwarp();
-			}
-		}
-		if (anypass == 0u || L >= 32u || nkept < need) {
-			return; /* nobody passed / the last level / too few left to pass again */
-		}
-		if (!multi) {
-			/* one and the same next byte behind every kept element: a single child */
-			if (nkept == len) {
-				L += 1u; /* nothing pruned either: it stays where it is (marks are masked on reading) */
-				continue;
-			}
-			uint32_t base = 0;
-			for (uint32_t r = 0; r < R; ++r) {
-				const uint32_t i = 32u * r + lane;
-				const uint32_t ew = i < len ? (uint32_t)In[i] : 0u;
-				const uint32_t km = __ballot_sync(FULL_MASK, (ew & 0x8000u) != 0u);
-				if (ew & 0x8000u) {
-					Out[base + __popc(km & lt)] = (uint16_t)(ew & 0x7fffu);
-				}
-				base += __popc(km);
-			}
-			__syncwarp();
-			len = nkept;
-			buf ^= 1u;
-			L += 1u;
-			continue;
-		}
-		/* slots of the children: bins of >= t+2 elements, in byte order */
-		uint32_t cnt[8], off[8];
-		uint32_t mine = 0;
-		{
-			const uint4 hv = reinterpret_cast<const uint4 *>(myh)[lane];
-			const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-			for (int k = 0; k < 8; ++k) {
-				cnt[k] = (hw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
-				mine += cnt[k] >= need ? cnt[k] : 0u;
-			}
-		}
-		uint32_t inc = mine;
+	__syncthreads(); /* the pushes and placements of the wave before */
+	const uint32_t head = SG_MI->q_head, tail = SG_MI->q_tail;
+	if (head == tail) {
+		return false;
+	}
+	if (warp == 0) {
+		const bool have = (uint32_t)lane < tail - head;
+		const uint32_t slot = (head + lane) % SG_Q;
+		const uint32_t ent = have ? SG_QENT[slot] : 0u;
+		const uint32_t len = ((ent >> 15) & 0x1fffu) + 1u;
+		const uint32_t nch = have ? (len + SG_CHUNK - 1u) / SG_CHUNK : 0u;
+		uint32_t inc = nch;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
 			const uint32_t o = __shfl_up_sync(FULL_MASK, inc, d);
@@ -586,66 +516,206 @@ __device__ __forceinline__ void sg_small_chain(const SegCtx &c, uint32_t start, 
 				inc += o;
 			}
 		}
-		uint32_t run = inc - mine, nchild = 0;
-		{
-			uint32_t hw[4] = {0u, 0u, 0u, 0u};
+		const bool fits = have && inc <= 32u;
+		const uint32_t fm = __ballot_sync(FULL_MASK, fits); /* a prefix of the lanes: the row count only grows */
+		if (fits) {
+			SegGroup &g = SG_MI->grp[lane];
+			g.start = ent & 0x7fffu;
+			g.len = len;
+			g.L = SG_QLVL[slot];
+			g.buf = (ent >> 28) & 1u;
+			g.r0 = inc - nch;
+			g.nrows = nch;
+			g.state = 1u;
+		}
+		const int ng = __popc(fm);
+		const uint32_t rows = __shfl_sync(FULL_MASK, inc, ng - 1);
+		if (lane == 0) {
+			SG_MI->wave_groups = (uint32_t)ng;
+			SG_MI->wave_rows = rows;
+		}
+	}
+	__syncthreads();
+	const uint32_t ng = SG_MI->wave_groups, nrows = SG_MI->wave_rows;
+	if (tid == 0) {
+		SG_MI->q_head = head + ng; /* (every thread has read the old value: it is read next behind two more barriers) */
+	}
+	/* my row's group */
+	uint32_t gi = 0, gstart = 0, glen = 0, L = 0, buf = 0, r0 = 0, gn = 0;
+	const bool rowon = (uint32_t)warp < nrows;
+	if (rowon) {
+		const uint32_t gr0 = (uint32_t)lane < ng ? SG_MI->grp[lane].r0 : 0xffffu;
+		const uint32_t m = __ballot_sync(FULL_MASK, gr0 <= (uint32_t)warp);
+		gi = 31 - __clz((int)m);
+		const SegGroup &g = SG_MI->grp[gi];
+		gstart = g.start;
+		glen = g.len;
+		L = g.L;
+		buf = g.buf;
+		r0 = g.r0;
+		gn = g.nrows;
+	}
+	const uint32_t coff = ((uint32_t)warp - r0) * SG_CHUNK;
+	const uint16_t *In = SG_P(buf) + gstart;
+	uint16_t *myh = SG_WH + warp * 256;
+	uint32_t st[8];  /* my element of round r: id | rank << 15 | byte << 23 | kept << 31 */
+	uint32_t pmk = 0; /* lane r: which lanes passed in round r */
+	/* (1a) */
+	if (rowon) {
+		uint32_t lastp = SG_NONE;
+#pragma unroll
+		for (int r = 0; r < 8; ++r) {
+			const uint32_t i = coff + 32u * r + lane;
+			const uint32_t e = i < glen ? (uint32_t)In[i] & 0x7fffu : 0u;
+			bool pass = false;
+			if (i + c.la < glen) {
+				const uint32_t ef = (uint32_t)In[i + c.la] & 0x7fffu;
+				pass = ef - e <= c.D && e - 3u < c.Bs;
+			}
+			if (pass) {
+				SG_L8[e - 3u] = (uint8_t)L;
+			}
+			const uint32_t pm = __ballot_sync(FULL_MASK, pass);
+			if (lane == r) {
+				pmk = pm;
+			}
+			if (pm != 0u) {
+				lastp = __shfl_sync(FULL_MASK, e, 31 - __clz((int)pm));
+			}
+			st[r] = e;
+		}
+		if (lane == 0) {
+			SG_MI->lastp[warp] = lastp;
+		}
+		reinterpret_cast<uint4 *>(myh)[lane] = make_uint4(0u, 0u, 0u, 0u);
+	}
+	__syncthreads();
+	/* (1b) */
+	bool alive = false; /* somebody of my group passed, and there is a deeper level */
+	if (rowon) {
+		const uint32_t lp = (uint32_t)lane < gn ? SG_MI->lastp[r0 + lane] : SG_NONE;
+		const uint32_t havem = __ballot_sync(FULL_MASK, lp != SG_NONE);
+		alive = havem != 0u && L < 32u;
+		if (alive) {
+			const uint32_t before = havem & ((1u << ((uint32_t)warp - r0)) - 1u); /* rows of my group in front of mine */
+			uint32_t carry = SG_NONE;
+			if (before != 0u) {
+				carry = __shfl_sync(FULL_MASK, lp, 31 - __clz((int)before));
+			}
+#pragma unroll
+			for (int r = 0; r < 8; ++r) {
+				const uint32_t i = coff + 32u * r + lane;
+				const uint32_t e = st[r];
+				const uint32_t pm = __shfl_sync(FULL_MASK, pmk, r);
+				const uint32_t upto = pm & ((2u << lane) - 1u);
+				const uint32_t lpv = __shfl_sync(FULL_MASK, e, upto != 0u ? 31 - __clz((int)upto) : 0);
+				const uint32_t lpos = upto != 0u ? lpv : carry;
+				const bool kept = i < glen && 32u * r + lane < SG_CHUNK && lpos != SG_NONE && e - lpos <= c.D;
+				if (pm != 0u) {
+					carry = __shfl_sync(FULL_MASK, e, 31 - __clz((int)pm));
+				}
+				const uint32_t b = kept ? sg_byte(e, L) : 256u + lane;
+				const uint32_t peers = __match_any_sync(FULL_MASK, b);
+				const int leader = __ffs(peers) - 1;
+				uint32_t old = 0;
+				if (kept && lane == leader) {
+					old = myh[b];
+					myh[b] = (uint16_t)(old + __popc(peers));
+				}
+				old = __shfl_sync(FULL_MASK, old, leader);
+				st[r] = kept ? e | ((old + __popc(peers & lt)) << 15) | (b << 23) | 0x80000000u : 0u;
+				__syncwarp();
+			}
+		}
+	}
+	__syncthreads();
+	/* (A) one warp per group: totals over its rows, children, final offsets */
+	if ((uint32_t)warp < ng) {
+		const SegGroup g = SG_MI->grp[warp];
+		const uint32_t lp = (uint32_t)lane < g.nrows ? SG_MI->lastp[g.r0 + lane] : SG_NONE;
+		const bool galive = __ballot_sync(FULL_MASK, lp != SG_NONE) != 0u && g.L < 32u;
+		if (galive) {
+			uint32_t tot[8];
 #pragma unroll
 			for (int k = 0; k < 8; ++k) {
-				const bool alive = cnt[k] >= need;
-				off[k] = alive ? run : 0xffffu;
-				hw[k >> 1] |= off[k] << (16 * (k & 1));
-				run += alive ? cnt[k] : 0u;
-				nchild += alive ? 1u : 0u;
+				tot[k] = 0;
 			}
-			reinterpret_cast<uint4 *>(myh)[lane] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-		}
-		const uint32_t cm = __ballot_sync(FULL_MASK, nchild != 0u);
-		if (cm == 0u) {
-			return; /* every child too small to pass again */
-		}
-		__syncwarp();
-		/* sweep 2: placement */
-		for (uint32_t r = 0; r < R; ++r) {
-			const uint32_t i = 32u * r + lane;
-			const uint32_t ew = i < len ? (uint32_t)In[i] : 0u;
-			const bool kept = (ew & 0x8000u) != 0u;
-			const uint32_t e = ew & 0x7fffu;
-			const uint32_t b = kept ? sg_byte(e, L) : 0u;
-			const uint32_t o = kept ? (uint32_t)myh[b] : 0xffffu;
-			const bool act = o != 0xffffu;
-			const uint32_t peers = __match_any_sync(FULL_MASK, act ? b : 256u + lane);
-			if (act) {
-				Out[o + __popc(peers & lt)] = (uint16_t)e;
-			}
-			__syncwarp();
-			if (act && lane == __ffs(peers) - 1) {
-				myh[b] = (uint16_t)(o + __popc(peers));
-			}
-			__syncwarp();
-		}
-		/* the first child is mine, the others are queued (their elements are written: publish behind a fence) */
-		const int fl = __ffs(cm) - 1;
-		uint32_t mystart = 0, mylen = 0;
-		bool took = false;
-		__threadfence_block();
-		__syncwarp();
+			for (uint32_t rr = 0; rr < g.nrows; ++rr) {
+				const uint4 hv = reinterpret_cast<const uint4 *>(SG_WH + (g.r0 + rr) * 256)[lane];
+				const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
-		for (int k = 0; k < 8; ++k) {
-			if (off[k] != 0xffffu) {
-				if (lane == fl && !took) {
-					mystart = off[k];
-					mylen = cnt[k];
-					took = true;
-				} else {
-					sg_push(c, start + off[k], cnt[k], L + 1u, buf ^ 1u);
+				for (int k = 0; k < 8; ++k) {
+					tot[k] += (hw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+				}
+			}
+			uint32_t mine = 0, whole = 0;
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				mine += tot[k] >= need ? tot[k] : 0u;
+				whole |= tot[k] == g.len ? 1u : 0u;
+			}
+			if (__ballot_sync(FULL_MASK, whole != 0u) != 0u) {
+				/* every element kept and followed by one and the same byte: the group stays where it is */
+				if (whole != 0u) {
+					sg_push(g.start, g.len, g.L + 1u, g.buf);
+				}
+			} else {
+				uint32_t inc = mine;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					const uint32_t o = __shfl_up_sync(FULL_MASK, inc, d);
+					if (lane >= d) {
+						inc += o;
+					}
+				}
+				uint32_t run[8];
+				uint32_t base = inc - mine;
+#pragma unroll
+				for (int k = 0; k < 8; ++k) {
+					const bool al = tot[k] >= need;
+					run[k] = al ? base : 0xffffu;
+					if (al) {
+						sg_push(g.start + base, tot[k], g.L + 1u, g.buf ^ 1u);
+						base += tot[k];
+					}
+				}
+				for (uint32_t rr = 0; rr < g.nrows; ++rr) {
+					uint4 *row = reinterpret_cast<uint4 *>(SG_WH + (g.r0 + rr) * 256) + lane;
+					const uint4 hv = *row;
+					const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+					uint32_t ow[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+					for (int k = 0; k < 8; ++k) {
+						const uint32_t cnt = (hw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+						ow[k >> 1] |= run[k] << (16 * (k & 1));
+						if (run[k] != 0xffffu) {
+							run[k] += cnt;
+						}
+					}
+					*row = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+				}
+				if (lane == 0) {
+					SG_MI->grp[warp].state = 0u;
 				}
 			}
 		}
-		start += __shfl_sync(FULL_MASK, mystart, fl);
-		len = __shfl_sync(FULL_MASK, mylen, fl);
-		buf ^= 1u;
-		L += 1u;
 	}
+	__syncthreads();
+	/* (2) placement into the group's own range of the other buffer */
+	if (rowon && alive && SG_MI->grp[gi].state == 0u) {
+		uint16_t *Out = SG_P(buf ^ 1u) + gstart;
+#pragma unroll
+		for (int r = 0; r < 8; ++r) {
+			const uint32_t v = st[r];
+			if (v & 0x80000000u) {
+				const uint32_t off = myh[(v >> 23) & 255u];
+				if (off != 0xffffu) {
+					Out[off + ((v >> 15) & 255u)] = (uint16_t)(v & 0x7fffu);
+				}
+			}
+		}
+	}
+	return true;
 }
 
 __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
@@ -660,9 +730,6 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 	if (tid == 0) {
 		mbar_init(bar, 1);
 	}
-	for (uint32_t i = tid; i < SG_Q; i += SG_THREADS) {
-		SG_QENT[i] = 0u;
-	}
 	__syncthreads();
 	uint32_t phase = 0;
 	unsigned long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = clock64();
@@ -676,7 +743,6 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 		if (tid == 0) {
 			SG_MI->seg = atomicAdd(a.ticket, 1u);
 			SG_MI->q_head = SG_MI->q_tail = 0u;
-			SG_MI->pending = 0;
 			SG_MI->big_head = SG_MI->big_tail = 0u;
 		}
 		__syncthreads();
@@ -744,37 +810,8 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 			sg_big_level(c, be.x & 0xffffu, be.x >> 16, be.y & 255u, (be.y >> 8) & 1u);
 		}
 		SG_LAP(4)
-		/* small groups: the warps drain the queue */
-		for (;;) {
-			uint32_t ent = 0, L = 0;
-			if (lane == 0) {
-				const uint32_t slot = atomicAdd(&SG_MI->q_head, 1u) % SG_Q;
-				for (;;) {
-					ent = SG_QENT[slot];
-					if (ent & Q_VALID) {
-						__threadfence_block();
-						L = SG_QLVL[slot];
-						SG_QENT[slot] = 0u;
-						break;
-					}
-					if (*(volatile int *)&SG_MI->pending == 0) {
-						ent = 0;
-						break;
-					}
-					__nanosleep(200); /* nothing queued yet: leave the issue slots to the warps that work */
-				}
-			}
-			ent = __shfl_sync(FULL_MASK, ent, 0);
-			L = __shfl_sync(FULL_MASK, L, 0);
-			if (ent == 0u) {
-				break;
-			}
-			__threadfence_block();
-			sg_small_chain(c, ent & 0x7fffu, ((ent >> 15) & 0x7ffu) + 1u, L, (ent >> 26) & 1u);
-			__syncwarp();
-			if (lane == 0) {
-				atomicSub(&SG_MI->pending, 1);
-			}
+		/* every other group, wave after wave */
+		while (sg_wave(c)) {
 		}
 		__syncthreads();
 		SG_LAP(5)
