@@ -46,8 +46,10 @@ constexpr uint32_t SG_BMAX = 24592;          /* searched positions of a segment 
 constexpr uint32_t SG_XS_OFF = 13;           /* xs[k] = xsr[SG_XS_OFF + k]: the TMA source is 16-byte aligned */
 constexpr uint32_t SG_XS_BYTES = SG_MMAX + 80;
 constexpr uint32_t SG_CHUNK = 256;           /* elements a warp takes per wave: one histogram row */
+constexpr uint32_t SG_CHAIN_MAX = SG_CHUNK;  /* groups up to this size are followed down by one warp (8 elements per lane) */
 constexpr uint32_t SG_WAVE_MAX = 32 * SG_CHUNK; /* groups up to this size go through the waves (<= 32 rows) */
-constexpr uint32_t SG_Q = 4864;              /* ring slots: live groups <= M / (t+2) */
+constexpr uint32_t SG_Q = 4864;              /* queue slots of the chains: live groups <= M / (t+2) */
+constexpr uint32_t SG_RING = 128;            /* ring slots of the waves: live groups above SG_CHAIN_MAX <= M / 257 */
 constexpr uint32_t SG_BIGQ = 16;             /* live groups above SG_WAVE_MAX: <= M / SG_WAVE_MAX */
 constexpr uint32_t SG_NONE = 0xffffffffu;
 constexpr uint32_t Q_VALID = 0x80000000u;
@@ -63,12 +65,14 @@ struct SegMisc {
 	uint32_t dbase[256];
 	uint32_t wsum[36];
 	uint32_t lastp[32];
-	uint32_t q_head, q_tail;
+	uint32_t q_head, q_tail, q_done; /* chains: tickets taken, entries pushed, entries finished */
+	uint32_t r_head, r_tail;
 	uint32_t big_head, big_tail;
 	uint32_t seg;
 	uint32_t wave_groups, wave_rows;
 	uint2 big[SG_BIGQ];
-	SegGroup grp[32];
+	uint2 ring[SG_RING];
+	SegGroup grp[16];            /* (a group of a wave has at least 2 rows) */
 };
 
 constexpr size_t SG_OFF_P0 = SG_XS_BYTES;
@@ -79,7 +83,7 @@ constexpr size_t SG_OFF_QE = SG_OFF_WH + SG_WARPS * 256 * 2;
 constexpr size_t SG_OFF_QL = SG_OFF_QE + SG_Q * 4;
 constexpr size_t SG_OFF_MISC = (SG_OFF_QL + SG_Q + 15) & ~(size_t)15;
 constexpr size_t SG_SMEM = SG_OFF_MISC + sizeof(SegMisc);
-static_assert(SG_SMEM <= 232448, "segment kernel: shared memory over the 227 KB a CTA can have");
+static_assert(SG_SMEM + 128 <= 232448, "segment kernel: shared memory over the 227 KB a CTA can have");
 static_assert(SG_XS_BYTES % 16 == 0 && SG_OFF_L8 % 16 == 0 && SG_OFF_WH % 16 == 0, "alignment");
 
 struct SegArgs {
@@ -91,8 +95,8 @@ struct SegArgs {
 	int t;
 	uint32_t nseg;
 	unsigned int *ticket;        /* zeroed before the launch */
-	unsigned long long *prof;    /* NULL, or 8 cycle counters per CTA (X3_SEG_PROF=1): load, pass 0, passes 1-3,
-	                              * level-4 groups, big groups, small groups, store, segments */
+	unsigned long long *prof;    /* NULL, or 9 counters per CTA (X3_SEG_PROF=1): cycles of load, pass 0, passes 1-3,
+	                              * level-4 groups, big groups, waves, chains, store; segments */
 };
 
 /* The CTA's shared memory, addressed through the array itself in every device function, so that the
@@ -103,8 +107,8 @@ extern __shared__ __align__(128) uint8_t sg_smem[];
 #define SG_P(buf) (reinterpret_cast<uint16_t *>(sg_smem + SG_OFF_P0) + (size_t)(buf) * SG_MMAX)
 #define SG_L8 (sg_smem + SG_OFF_L8)
 #define SG_WH (reinterpret_cast<uint16_t *>(sg_smem + SG_OFF_WH))
-#define SG_QENT (reinterpret_cast<uint32_t *>(sg_smem + SG_OFF_QE))
-#define SG_QLVL (sg_smem + SG_OFF_QL)
+#define SG_QENT (reinterpret_cast<volatile uint32_t *>(sg_smem + SG_OFF_QE))
+#define SG_QLVL (reinterpret_cast<volatile uint8_t *>(sg_smem + SG_OFF_QL))
 #define SG_MI (reinterpret_cast<SegMisc *>(sg_smem + SG_OFF_MISC))
 
 /* what a segment's phases share besides the shared memory: scalars only (registers) */
@@ -202,16 +206,16 @@ __device__ __forceinline__ void sg_lsd_pass(const SegCtx &c)
 	const uint32_t R = (M + 1023u) >> 10;      /* rounds per warp; a warp's block is 32 R elements */
 	const uint32_t blk = (uint32_t)warp * 32u * R;
 	uint16_t *myh = SG_WH + warp * 256;
+	/* the warp's mask row: 256 words in the output buffer, which nobody writes before the placement */
+	uint32_t *mym = reinterpret_cast<uint32_t *>(SG_P(INBUF ^ 1)) + warp * 256;
 	const uint32_t lt = (1u << lane) - 1u;
 	reinterpret_cast<uint4 *>(myh)[lane] = make_uint4(0u, 0u, 0u, 0u);
+	reinterpret_cast<uint4 *>(mym)[lane] = make_uint4(0u, 0u, 0u, 0u);
+	reinterpret_cast<uint4 *>(mym)[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
 	__syncwarp();
-	uint32_t dg[8], rk[16];
+	uint32_t rk[11]; /* rank of my element of round r among its digit in the warp's block (< 1024): 3 per word */
 #pragma unroll
-	for (int k = 0; k < 8; ++k) {
-		dg[k] = 0;
-	}
-#pragma unroll
-	for (int k = 0; k < 16; ++k) {
+	for (int k = 0; k < 11; ++k) {
 		rk[k] = 0;
 	}
 	uint32_t e_n = 0, g_n = 0;
@@ -224,6 +228,7 @@ __device__ __forceinline__ void sg_lsd_pass(const SegCtx &c)
 		if ((uint32_t)r < R) {
 			const uint32_t i = blk + 32u * r + lane;
 			const bool valid = i < M;
+			const uint32_t nvalid = M > blk + 32u * r ? M - (blk + 32u * r) : 0u; /* lanes of the round with an element */
 			uint32_t d;
 			if (K == 0) {
 				d = valid ? SG_XSB[SG_XS_OFF + i + 3] : 0u;
@@ -260,17 +265,35 @@ __device__ __forceinline__ void sg_lsd_pass(const SegCtx &c)
 					SG_L8[q] = (uint8_t)sg_rare(INBUF, i, e, M, (uint32_t)c.t, c.D);
 				}
 			}
-			const uint32_t key = valid ? d : 256u + lane;
-			const uint32_t peers = __match_any_sync(FULL_MASK, key);
-			const int leader = __ffs(peers) - 1;
-			uint32_t old = 0;
-			if (lane == leader && valid) {
-				old = myh[d];
+			/* which lanes of the round hold my digit.  MATCH.ANY takes 2 cycles per distinct value of the warp,
+			 * SM-wide (profiles/r2_ubench.json: 32 cycles on text, 64 on noise), so it only serves rounds
+			 * with few values; the others set their lane bits in the warp's mask row (shared-memory atomics:
+			 * the row ends up the same in whatever order they are served) and read the row back. */
+			const uint32_t vm = nvalid >= 32u ? FULL_MASK : (1u << nvalid) - 1u;
+			const uint32_t d0 = __shfl_sync(FULL_MASK, d, 0); /* (every lane takes part: not inside the && below) */
+			const uint32_t m0 = __ballot_sync(FULL_MASK, valid && d == d0);
+			uint32_t peers;
+			if (m0 == vm) {
+				peers = vm;
+			} else if (__popc(m0) >= 11) {
+				peers = __match_any_sync(FULL_MASK, valid ? d : 256u + lane);
+			} else {
+				if (valid) {
+					atomicOr(&mym[d], 1u << lane);
+				}
+				__syncwarp();
+				peers = valid ? mym[d] : 0u;
+				__syncwarp();
+				if (valid && (peers & lt) == 0u) {
+					mym[d] = 0u;
+				}
+			}
+			const uint32_t old = valid ? (uint32_t)myh[d] : 0u;
+			__syncwarp();
+			if (valid && (peers & lt) == 0u) {
 				myh[d] = (uint16_t)(old + __popc(peers));
 			}
-			old = __shfl_sync(FULL_MASK, old, leader);
-			dg[r >> 2] |= d << (8 * (r & 3));
-			rk[r >> 1] |= (old + __popc(peers & lt)) << (16 * (r & 1));
+			rk[r / 3] |= (old + __popc(peers & lt)) << (10 * (r % 3));
 			__syncwarp();
 		}
 	}
@@ -282,9 +305,9 @@ __device__ __forceinline__ void sg_lsd_pass(const SegCtx &c)
 		if ((uint32_t)r < R) {
 			const uint32_t i = blk + 32u * r + lane;
 			if (i < M) {
-				const uint32_t d = (dg[r >> 2] >> (8 * (r & 3))) & 255u;
-				const uint32_t rank = (rk[r >> 1] >> (16 * (r & 1))) & 0xffffu;
+				const uint32_t rank = (rk[r / 3] >> (10 * (r % 3))) & 1023u;
 				const uint32_t e = K == 0 ? i : (uint32_t)In[i];
+				const uint32_t d = SG_XSB[SG_XS_OFF + e + 3 - K]; /* the digit again: byte 3-K of the gram */
 				Out[SG_MI->dbase[d] + myh[d] + rank] = (uint16_t)e;
 			}
 		}
@@ -292,18 +315,48 @@ __device__ __forceinline__ void sg_lsd_pass(const SegCtx &c)
 	__syncthreads();
 }
 
-/* ---- pushing a group: the ring of the waves, or the list of the few groups too large for them.
- * (Entries are read behind a CTA barrier: no flags, no fences.) */
+/* ---- pushing a group, by size: the CTA's list (above SG_WAVE_MAX), the ring of the waves (above
+ * SG_CHAIN_MAX; read behind CTA barriers: no flags, no fences), or the queue of the chains, whose
+ * entries are taken by polling warps: the entry is published behind a fence, with its valid bit. */
 __device__ __forceinline__ void sg_push(uint32_t start, uint32_t len, uint32_t L, uint32_t buf)
 {
 	if (len > SG_WAVE_MAX) {
 		const uint32_t slot = atomicAdd(&SG_MI->big_tail, 1u) % SG_BIGQ;
 		SG_MI->big[slot] = make_uint2(start | (len << 16), L | (buf << 8));
+	} else if (len > SG_CHAIN_MAX) {
+		const uint32_t slot = atomicAdd(&SG_MI->r_tail, 1u) % SG_RING;
+		SG_MI->ring[slot] = make_uint2(start | (len << 16), L | (buf << 8));
 	} else {
 		const uint32_t slot = atomicAdd(&SG_MI->q_tail, 1u) % SG_Q;
 		SG_QLVL[slot] = (uint8_t)L;
-		SG_QENT[slot] = (buf << 28) | ((len - 1u) << 15) | start;
+		__threadfence_block();
+		SG_QENT[slot] = Q_VALID | (buf << 26) | ((len - 1u) << 15) | start;
 	}
+}
+
+/* how many levels from Lfrom on the n elements In[0 .. n) (all of one group) go on with one and the
+ * same byte: the first level at which their bytes differ, or 32 (whole warp; 4 bytes per step) */
+__device__ __forceinline__ uint32_t sg_common_levels(const uint16_t *In, uint32_t n, uint32_t Lfrom)
+{
+	const int lane = threadIdx.x & 31;
+	const uint32_t e0 = In[0];
+	uint32_t Ln = Lfrom;
+	while (Ln < 32u) {
+		const uint32_t g0 = sg_gram(e0 + Ln);
+		uint32_t m = 4u;
+		for (uint32_t i = lane; i < n; i += 32u) {
+			const uint32_t x = sg_gram((uint32_t)In[i] + Ln) ^ g0;
+			if (x != 0u) {
+				m = min(m, (uint32_t)(__ffs((int)x) - 1) >> 3);
+			}
+		}
+		m = __reduce_min_sync(FULL_MASK, m);
+		Ln += m;
+		if (m < 4u) {
+			break;
+		}
+	}
+	return min(Ln, 32u);
 }
 
 /* ---- the level-4 groups: heads of the final LSD order, every group of >= t+2 elements pushed */
@@ -498,15 +551,14 @@ __device__ __forceinline__ bool sg_wave(const SegCtx &c)
 	const uint32_t lt = (1u << lane) - 1u;
 	const uint32_t need = (uint32_t)c.t + 2u;
 	__syncthreads(); /* the pushes and placements of the wave before */
-	const uint32_t head = SG_MI->q_head, tail = SG_MI->q_tail;
+	const uint32_t head = SG_MI->r_head, tail = SG_MI->r_tail;
 	if (head == tail) {
 		return false;
 	}
 	if (warp == 0) {
 		const bool have = (uint32_t)lane < tail - head;
-		const uint32_t slot = (head + lane) % SG_Q;
-		const uint32_t ent = have ? SG_QENT[slot] : 0u;
-		const uint32_t len = ((ent >> 15) & 0x1fffu) + 1u;
+		const uint2 ent = have ? SG_MI->ring[(head + lane) % SG_RING] : make_uint2(0u, 0u);
+		const uint32_t len = ent.x >> 16;
 		const uint32_t nch = have ? (len + SG_CHUNK - 1u) / SG_CHUNK : 0u;
 		uint32_t inc = nch;
 #pragma unroll
@@ -520,10 +572,10 @@ __device__ __forceinline__ bool sg_wave(const SegCtx &c)
 		const uint32_t fm = __ballot_sync(FULL_MASK, fits); /* a prefix of the lanes: the row count only grows */
 		if (fits) {
 			SegGroup &g = SG_MI->grp[lane];
-			g.start = ent & 0x7fffu;
+			g.start = ent.x & 0xffffu;
 			g.len = len;
-			g.L = SG_QLVL[slot];
-			g.buf = (ent >> 28) & 1u;
+			g.L = ent.y & 255u;
+			g.buf = (ent.y >> 8) & 1u;
 			g.r0 = inc - nch;
 			g.nrows = nch;
 			g.state = 1u;
@@ -538,7 +590,7 @@ __device__ __forceinline__ bool sg_wave(const SegCtx &c)
 	__syncthreads();
 	const uint32_t ng = SG_MI->wave_groups, nrows = SG_MI->wave_rows;
 	if (tid == 0) {
-		SG_MI->q_head = head + ng; /* (every thread has read the old value: it is read next behind two more barriers) */
+		SG_MI->r_head = head + ng; /* (every thread has read the old value: it is read next behind two more barriers) */
 	}
 	/* my row's group */
 	uint32_t gi = 0, gstart = 0, glen = 0, L = 0, buf = 0, r0 = 0, gn = 0;
@@ -655,9 +707,11 @@ __device__ __forceinline__ bool sg_wave(const SegCtx &c)
 				whole |= tot[k] == g.len ? 1u : 0u;
 			}
 			if (__ballot_sync(FULL_MASK, whole != 0u) != 0u) {
-				/* every element kept and followed by one and the same byte: the group stays where it is */
-				if (whole != 0u) {
-					sg_push(g.start, g.len, g.L + 1u, g.buf);
+				/* every element kept and followed by one and the same byte: the group stays where it is, and
+				 * nothing changes (same array, same test) down to the level where the bytes differ */
+				const uint32_t Ln = sg_common_levels(SG_P(g.buf) + g.start, g.len, g.L + 1u);
+				if (lane == 0) {
+					sg_push(g.start, g.len, Ln, g.buf);
 				}
 			} else {
 				uint32_t inc = mine;
@@ -718,6 +772,170 @@ __device__ __forceinline__ bool sg_wave(const SegCtx &c)
 	return true;
 }
 
+/* ---- a group of at most SG_CHAIN_MAX elements: one warp follows it down to the level where it
+ * ends, 8 elements per lane in registers, no CTA barrier.  Per level: the test, the kept elements,
+ * their next bytes and ranks (histogram row of the warp), the children's slots, the placement in the
+ * group's own range of the other buffer.  The warp goes on with one child and queues the others. */
+__device__ __forceinline__ void sg_chain(const SegCtx &c, uint32_t start, uint32_t len, uint32_t L, uint32_t buf)
+{
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint16_t *myh = SG_WH + warp * 256;
+	const uint32_t lt = (1u << lane) - 1u;
+	const uint32_t need = (uint32_t)c.t + 2u;
+	for (;;) {
+		const uint16_t *In = SG_P(buf) + start;
+		const uint32_t R = (len + 31u) >> 5;
+		reinterpret_cast<uint4 *>(myh)[lane] = make_uint4(0u, 0u, 0u, 0u);
+		__syncwarp();
+		uint32_t st[8]; /* my element of round r: id | rank << 15 | byte << 23 | kept << 31 */
+		uint32_t carry = SG_NONE, anypass = 0, nkept = 0;
+#pragma unroll
+		for (int r = 0; r < 8; ++r) {
+			st[r] = 0u;
+			if ((uint32_t)r < R) {
+				const uint32_t i = 32u * r + lane;
+				const uint32_t e = i < len ? (uint32_t)In[i] : 0u;
+				bool pass = false;
+				if (i + c.la < len) {
+					const uint32_t ef = In[i + c.la];
+					pass = ef - e <= c.D && e - 3u < c.Bs;
+				}
+				if (pass) {
+					SG_L8[e - 3u] = (uint8_t)L;
+				}
+				const uint32_t pm = __ballot_sync(FULL_MASK, pass);
+				anypass |= pm;
+				if (L < 32u) {
+					const uint32_t upto = pm & ((2u << lane) - 1u);
+					const uint32_t lpv = __shfl_sync(FULL_MASK, e, upto != 0u ? 31 - __clz((int)upto) : 0);
+					const uint32_t lpos = upto != 0u ? lpv : carry;
+					const bool kept = i < len && lpos != SG_NONE && e - lpos <= c.D;
+					if (pm != 0u) {
+						carry = __shfl_sync(FULL_MASK, e, 31 - __clz((int)pm));
+					}
+					const uint32_t b = kept ? sg_byte(e, L) : 256u + lane;
+					const uint32_t peers = __match_any_sync(FULL_MASK, b);
+					const int leader = __ffs(peers) - 1;
+					uint32_t old = 0;
+					if (kept && lane == leader) {
+						old = myh[b];
+						myh[b] = (uint16_t)(old + __popc(peers));
+					}
+					old = __shfl_sync(FULL_MASK, old, leader);
+					st[r] = kept ? e | ((old + __popc(peers & lt)) << 15) | (b << 23) | 0x80000000u : e;
+					nkept += __popc(__ballot_sync(FULL_MASK, kept));
+					__syncwarp();
+				}
+			}
+		}
+		if (anypass == 0u || L >= 32u || nkept < need) {
+			return; /* nobody passed / the last level / too few left to pass again */
+		}
+		uint32_t cnt[8], off[8];
+		uint32_t mine = 0, whole = 0;
+		{
+			const uint4 hv = reinterpret_cast<const uint4 *>(myh)[lane];
+			const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				cnt[k] = (hw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+				mine += cnt[k] >= need ? cnt[k] : 0u;
+				whole |= cnt[k] == len ? 1u : 0u;
+			}
+		}
+		if (__any_sync(FULL_MASK, whole != 0u)) {
+			/* every element kept and followed by one and the same byte: the group stays where it is, and
+			 * nothing changes (same array, same test) down to the level where the bytes differ */
+			uint32_t Ln = L + 1u;
+			const uint32_t e0 = In[0];
+			while (Ln < 32u) {
+				const uint32_t g0 = sg_gram(e0 + Ln);
+				uint32_t m = 4u;
+#pragma unroll
+				for (int r = 0; r < 8; ++r) {
+					if (32u * r + lane < len) {
+						const uint32_t x = sg_gram((st[r] & 0x7fffu) + Ln) ^ g0;
+						if (x != 0u) {
+							m = min(m, (uint32_t)(__ffs((int)x) - 1) >> 3);
+						}
+					}
+				}
+				m = __reduce_min_sync(FULL_MASK, m);
+				Ln += m;
+				if (m < 4u) {
+					break;
+				}
+			}
+			L = min(Ln, 32u);
+			continue;
+		}
+		/* slots of the children: bins of >= t+2 elements, in byte order */
+		uint32_t inc = mine;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t o = __shfl_up_sync(FULL_MASK, inc, d);
+			if (lane >= d) {
+				inc += o;
+			}
+		}
+		uint32_t run = inc - mine, nchild = 0;
+		{
+			uint32_t hw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+			for (int k = 0; k < 8; ++k) {
+				const bool al = cnt[k] >= need;
+				off[k] = al ? run : 0xffffu;
+				hw[k >> 1] |= off[k] << (16 * (k & 1));
+				run += al ? cnt[k] : 0u;
+				nchild += al ? 1u : 0u;
+			}
+			reinterpret_cast<uint4 *>(myh)[lane] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+		}
+		const uint32_t cm = __ballot_sync(FULL_MASK, nchild != 0u);
+		if (cm == 0u) {
+			return; /* every child too small to pass again */
+		}
+		__syncwarp();
+		/* placement, from the registers */
+		{
+			uint16_t *Out = SG_P(buf ^ 1u) + start;
+#pragma unroll
+			for (int r = 0; r < 8; ++r) {
+				const uint32_t v = st[r];
+				if ((uint32_t)r < R && (v & 0x80000000u) != 0u) {
+					const uint32_t o = myh[(v >> 23) & 255u];
+					if (o != 0xffffu) {
+						Out[o + ((v >> 15) & 255u)] = (uint16_t)(v & 0x7fffu);
+					}
+				}
+			}
+		}
+		/* the first child is mine, the others are queued (their elements are written: publish behind a fence) */
+		const int fl = __ffs(cm) - 1;
+		uint32_t mystart = 0, mylen = 0;
+		bool took = false;
+		__threadfence_block();
+		__syncwarp();
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			if (off[k] != 0xffffu) {
+				if (lane == fl && !took) {
+					mystart = off[k];
+					mylen = cnt[k];
+					took = true;
+				} else {
+					sg_push(start + off[k], cnt[k], L + 1u, buf ^ 1u);
+				}
+			}
+		}
+		start += __shfl_sync(FULL_MASK, mystart, fl);
+		len = __shfl_sync(FULL_MASK, mylen, fl);
+		buf ^= 1u;
+		L += 1u;
+	}
+}
+
+template <bool PROF>
 __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 {
 	SegCtx c;
@@ -730,19 +948,31 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 	if (tid == 0) {
 		mbar_init(bar, 1);
 	}
+	for (uint32_t i = tid; i < SG_Q; i += SG_THREADS) {
+		SG_QENT[i] = 0u; /* (a taken entry is cleared by the warp that took it) */
+	}
 	__syncthreads();
 	uint32_t phase = 0;
-	unsigned long long pt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tp = clock64();
+	/* (the cycle counters of the measurement build live in shared memory behind the CTA's own data: no registers) */
+	unsigned long long *pt = reinterpret_cast<unsigned long long *>(sg_smem + SG_SMEM);
+	if (PROF && tid == 0) {
+		for (int k = 0; k < 9; ++k) {
+			pt[k] = 0;
+		}
+		pt[9] = clock64();
+	}
 #define SG_LAP(k)                                  \
-	if (a.prof != nullptr && tid == 0) {           \
+	if (PROF && tid == 0) {                        \
 		const unsigned long long now = clock64();  \
-		pt[k] += now - tp;                         \
-		tp = now;                                  \
+		pt[k] += now - pt[9];                      \
+		pt[9] = now;                               \
 	}
 	for (;;) {
 		if (tid == 0) {
 			SG_MI->seg = atomicAdd(a.ticket, 1u);
 			SG_MI->q_head = SG_MI->q_tail = 0u;
+			SG_MI->q_done = 0u;
+			SG_MI->r_head = SG_MI->r_tail = 0u;
 			SG_MI->big_head = SG_MI->big_tail = 0u;
 		}
 		__syncthreads();
@@ -810,11 +1040,48 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 			sg_big_level(c, be.x & 0xffffu, be.x >> 16, be.y & 255u, (be.y >> 8) & 1u);
 		}
 		SG_LAP(4)
-		/* every other group, wave after wave */
+		/* groups above SG_CHAIN_MAX elements, wave after wave */
 		while (sg_wave(c)) {
 		}
 		__syncthreads();
 		SG_LAP(5)
+		/* every other group: the warps drain the queue, each following its group down */
+		for (;;) {
+			uint32_t ent = 0, L = 0;
+			if (lane == 0) {
+				const uint32_t slot = atomicAdd(&SG_MI->q_head, 1u) % SG_Q;
+				for (;;) {
+					ent = SG_QENT[slot];
+					if (ent & Q_VALID) {
+						__threadfence_block();
+						L = SG_QLVL[slot];
+						SG_QENT[slot] = 0u;
+						break;
+					}
+					/* every pushed group finished (finished count first: it never overtakes the pushes) */
+					const uint32_t done = *(volatile uint32_t *)&SG_MI->q_done;
+					if (done == *(volatile uint32_t *)&SG_MI->q_tail) {
+						ent = 0;
+						break;
+					}
+					__nanosleep(100); /* nothing queued yet: leave the issue slots to the warps that work */
+				}
+			}
+			ent = __shfl_sync(FULL_MASK, ent, 0);
+			L = __shfl_sync(FULL_MASK, L, 0);
+			if (ent == 0u) {
+				break;
+			}
+			__threadfence_block();
+			sg_chain(c, ent & 0x7fffu, ((ent >> 15) & 0xffu) + 1u, L, (ent >> 26) & 1u);
+			__syncwarp();
+			if (lane == 0) {
+				__threadfence_block();
+				atomicAdd(&SG_MI->q_done, 1u);
+			}
+		}
+		__syncthreads();
+		SG_LAP(6)
 		/* Lstar of the segment */
 		{
 			uint8_t *dst = a.lstar + a0;
@@ -833,12 +1100,14 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 			}
 		}
 		__syncthreads();
-		SG_LAP(6)
-		pt[7] += 1;
+		SG_LAP(7)
+		if (PROF && tid == 0) {
+			pt[8] += 1;
+		}
 	}
-	if (a.prof != nullptr && tid == 0) {
-		for (int k = 0; k < 8; ++k) {
-			a.prof[blockIdx.x * 8 + k] = pt[k];
+	if (PROF && tid == 0) {
+		for (int k = 0; k < 9; ++k) {
+			a.prof[blockIdx.x * 9 + k] = pt[k];
 		}
 	}
 #undef SG_LAP
@@ -884,7 +1153,8 @@ cudaError_t x3k_launch_seg(const X3SearchParams &prm, cudaStream_t stream, int *
 	if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
 	static bool attr_set[64] = {false};
 	if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-		if ((e = cudaFuncSetAttribute(x3_seg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM)) != cudaSuccess) return e;
+		if ((e = cudaFuncSetAttribute(x3_seg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM)) != cudaSuccess) return e;
+		if ((e = cudaFuncSetAttribute(x3_seg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM + 128)) != cudaSuccess) return e;
 		attr_set[dev] = true;
 	}
 	SegArgs a;
@@ -906,30 +1176,34 @@ cudaError_t x3k_launch_seg(const X3SearchParams &prm, cudaStream_t stream, int *
 	const unsigned grid = nseg < (unsigned long long)sms ? (unsigned)nseg : (unsigned)sms;
 	const bool prof = getenv("X3_SEG_PROF") != nullptr; /* measurement knob: cycles per phase, printed */
 	if (prof) {
-		if ((e = cudaMalloc((void **)&a.prof, (size_t)grid * 64)) != cudaSuccess) return e;
-		if ((e = cudaMemsetAsync(a.prof, 0, (size_t)grid * 64, stream)) != cudaSuccess) return e;
+		if ((e = cudaMalloc((void **)&a.prof, (size_t)grid * 72)) != cudaSuccess) return e;
+		if ((e = cudaMemsetAsync(a.prof, 0, (size_t)grid * 72, stream)) != cudaSuccess) return e;
 	}
-	x3_seg_kernel<<<grid, SG_THREADS, SG_SMEM, stream>>>(a);
+	if (prof) {
+		x3_seg_kernel<true><<<grid, SG_THREADS, SG_SMEM + 128, stream>>>(a);
+	} else {
+		x3_seg_kernel<false><<<grid, SG_THREADS, SG_SMEM, stream>>>(a);
+	}
 	if (launches != nullptr) {
 		*launches += 1;
 	}
 	if (prof) {
-		unsigned long long *h = (unsigned long long *)malloc((size_t)grid * 64);
+		unsigned long long *h = (unsigned long long *)malloc((size_t)grid * 72);
 		if (h != nullptr && cudaStreamSynchronize(stream) == cudaSuccess &&
-		    cudaMemcpy(h, a.prof, (size_t)grid * 64, cudaMemcpyDeviceToHost) == cudaSuccess) {
-			static const char *name[7] = {"load", "pass 0", "passes 1-3", "groups4", "big groups", "small groups", "store"};
-			double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
+		    cudaMemcpy(h, a.prof, (size_t)grid * 72, cudaMemcpyDeviceToHost) == cudaSuccess) {
+			static const char *name[8] = {"load", "pass 0", "passes 1-3", "groups4", "big groups", "waves", "chains", "store"};
+			double tot[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
 			for (unsigned b = 0; b < grid; ++b) {
 				double cta = 0;
-				for (int k = 0; k < 8; ++k) {
-					tot[k] += (double)h[b * 8 + k];
-					cta += k < 7 ? (double)h[b * 8 + k] : 0;
+				for (int k = 0; k < 9; ++k) {
+					tot[k] += (double)h[b * 9 + k];
+					cta += k < 8 ? (double)h[b * 9 + k] : 0;
 				}
 				if (cta > mx) mx = cta;
 			}
-			fprintf(stderr, "x3_seg_kernel: %u CTAs, %.0f segments, busiest CTA %.0f cycles; cycles per segment:", grid, tot[7], mx);
-			for (int k = 0; k < 7; ++k) {
-				fprintf(stderr, "  %s %.0f", name[k], tot[k] / (tot[7] > 0 ? tot[7] : 1));
+			fprintf(stderr, "x3_seg_kernel: %u CTAs, %.0f segments, busiest CTA %.0f cycles; cycles per segment:", grid, tot[8], mx);
+			for (int k = 0; k < 8; ++k) {
+				fprintf(stderr, "  %s %.0f", name[k], tot[k] / (tot[8] > 0 ? tot[8] : 1));
 			}
 			fprintf(stderr, "\n");
 		}
