@@ -133,6 +133,12 @@ int x3s_host_register(void *p, size_t bytes);
 int x3s_host_unregister(void *p);
 
 /*
+ * Which kernel X3S_KERNEL_DEFAULT runs for window W and max match count t (no device needed):
+ * X3S_KERNEL_SEG, X3S_KERNEL_RANK or X3S_KERNEL_STREAM (want_table != 0: the 32-bin table is asked for).
+ */
+int x3s_default_kernel(size_t W, int t, int want_table);
+
+/*
  * Measurement hook of the rank search.  With the environment variable X3_RANK_PROFILE=1 the
  * library brackets every launch of a rank search with CUDA events (and synchronises at the
  * end of the search); this call returns, for the last such search on `device`, the device

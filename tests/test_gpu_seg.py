@@ -1,0 +1,107 @@
+"""GPU parity tests of the segment search (x3_search_seg.cu, X3S_KERNEL_SEG -- what
+X3S_KERNEL_DEFAULT runs at the reference's default flags): the table it returns through the C ABI
+against the oracle (reference backend.c:58-78 restated in oracle/x3_oracle.c) on the same seeded
+inputs, across input shapes, windows, thresholds, segment seams and the pipelined host path."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(corpus, kind, n):
+    rng = np.random.Generator(np.random.PCG64(n + len(kind)))
+    if kind in ("C1", "C2", "C4", "C5"):
+        return np.frombuffer(corpus.generate(kind, n), dtype=np.uint8)
+    if kind in ("text", "exe", "img", "chem", "rec", "web", "xml", "mix"):
+        return np.frombuffer(corpus._member(kind, n, 500 + n % 7), dtype=np.uint8)
+    if kind == "zeros":
+        return np.zeros(n, dtype=np.uint8)
+    if kind == "period":
+        return (np.arange(n) % 7).astype(np.uint8)
+    if kind == "rand2":
+        return rng.integers(0, 2, n).astype(np.uint8)
+    if kind == "rand256":
+        return rng.integers(0, 256, n).astype(np.uint8)
+    if kind == "runs":
+        return np.frombuffer((b"abcabcabcabd" * 40 + b"\0" * 3000 + b"xyzw" * 2000 + bytes(range(256)) * 20) * 40, dtype=np.uint8)[:n]
+    raise KeyError(kind)
+
+
+def _assert_seg_same(pkg, data, W, t, pinned=False, variant=None):
+    variant = pkg.KERNEL_SEG if variant is None else variant
+    lstar, _, tm = pkg.search_host(data, W=W, t=t, ngpus=1, variant=variant, pinned=pinned)
+    _, ls_ref = ol.table(data, W, t)
+    bad = np.nonzero(lstar != ls_ref)[0]
+    assert len(bad) == 0, (f"segment search: Lstar differs at {len(bad)} positions, first {bad[:5].tolist()} "
+                           f"got {lstar[bad[:5]].tolist()} oracle {ls_ref[bad[:5]].tolist()} (n={len(data)} W={W} t={t})")
+    return tm
+
+
+@pytest.mark.parametrize("kind,n", [("C1", 1), ("C1", 31), ("C1", 33), ("C1", 5000), ("C1", 30000), ("C4", 30000),
+                                    ("C5", 60000), ("zeros", 40000), ("period", 30000), ("rand2", 30000),
+                                    ("rand256", 30000), ("runs", 90000), ("C1", 200000), ("C5", 300000)])
+def test_seg_search_equals_oracle_default_flags(pkg, corpus, kind, n):
+    _assert_seg_same(pkg, _inputs(corpus, kind, n), 8192, 15)
+
+
+@pytest.mark.parametrize("kind", ["text", "exe", "img", "chem", "rec", "web", "xml", "mix"])
+def test_seg_search_equals_oracle_every_member_kind(pkg, corpus, kind):
+    """every member shape of the C5 mix: the deep levels (chains, waves, whole-CTA groups) differ a lot between them"""
+    _assert_seg_same(pkg, _inputs(corpus, kind, 150_000), 8192, 15)
+
+
+@pytest.mark.parametrize("W", [34, 35, 64, 65, 100, 1024, 4096, 8191, 8193, 10000, 16384])
+def test_seg_search_equals_oracle_window_sweep(pkg, corpus, W):
+    _assert_seg_same(pkg, _inputs(corpus, "C1", 40000), W, 15)
+    _assert_seg_same(pkg, _inputs(corpus, "rand2", 20000), W, 7)
+
+
+@pytest.mark.parametrize("t", [5, 6, 15, 16, 30, 31, 32, 33, 64, 200, 254, 255, 300, 1000, 70000])
+def test_seg_search_equals_oracle_threshold_sweep(pkg, corpus, t):
+    _assert_seg_same(pkg, _inputs(corpus, "C5", 50000), 2048, t)
+    _assert_seg_same(pkg, _inputs(corpus, "zeros", 30000), 1024, t)
+    _assert_seg_same(pkg, _inputs(corpus, "C4", 40000), 8192, t)
+
+
+def test_seg_search_segment_seams(pkg, corpus):
+    """inputs a few positions around whole numbers of segments (B = 24 592 positions at W = 8192):
+    the last segment is short, its window is the reference's zero padding (x3.c:579,590)"""
+    B = 24592
+    for n in (B - 1, B, B + 1, 2 * B, 2 * B + 17, 3 * B - 16):
+        _assert_seg_same(pkg, _inputs(corpus, "C5", n), 8192, 15)
+        _assert_seg_same(pkg, _inputs(corpus, "zeros", n), 8192, 15)
+
+
+def test_seg_search_is_the_default_at_reference_flags(pkg, corpus):
+    assert pkg.default_kernel(8192, 15, False) == pkg.KERNEL_SEG
+    assert pkg.default_kernel(8192, 15, True) == pkg.KERNEL_STREAM        # the 32-bin table: brute force
+    assert pkg.default_kernel(1 << 20, 64, False) == pkg.KERNEL_RANK      # C3's window does not fit on chip
+    assert pkg.default_kernel(8192, 2, False) == pkg.KERNEL_RANK          # too many tiny groups for the queue
+    data = _inputs(corpus, "C5", 400_000)
+    tm = _assert_seg_same(pkg, data, 8192, 15, variant=pkg.KERNEL_DEFAULT)
+    assert tm.launches == 1
+
+
+@pytest.mark.parametrize("piece_mb", ["1", "2", None])
+def test_seg_search_pipelined_pieces_do_not_change_results(pkg, corpus, monkeypatch, piece_mb):
+    """between page-locked buffers a shard is uploaded, searched and copied back piece by piece
+    (x3_search_api.cu); the pieces only change the queueing, never the table"""
+    if piece_mb is not None:
+        monkeypatch.setenv("X3_SEG_PIECE_MB", piece_mb)
+    data = _inputs(corpus, "C5", 5_000_000)
+    tm = _assert_seg_same(pkg, data, 8192, 15, pinned=True)
+    if piece_mb is not None:
+        assert tm.launches >= 2
+    a, _, _ = pkg.search_host(data, W=8192, t=15, variant=pkg.KERNEL_SEG, pinned=False)
+    b, _, _ = pkg.search_host(data, W=8192, t=15, variant=pkg.KERNEL_RANK, pinned=True)
+    assert np.array_equal(a, b)
+
+
+def test_seg_search_rejects_what_it_cannot_take(pkg):
+    data = np.zeros(1000, dtype=np.uint8)
+    for kw in (dict(W=8192, t=15, want_table=True), dict(W=1 << 20, t=15), dict(W=8192, t=2), dict(W=33, t=15)):
+        with pytest.raises(pkg.X3SearchError) as ei:
+            pkg.search_host(data, variant=pkg.KERNEL_SEG, **kw)
+        assert ei.value.code == pkg.X3S_ERR_UNSUPP

@@ -74,6 +74,8 @@ def lib() -> C.CDLL:
     L.x3s_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.x3s_host_unregister.restype = C.c_int
     L.x3s_host_unregister.argtypes = [C.c_void_p]
+    L.x3s_default_kernel.restype = C.c_int
+    L.x3s_default_kernel.argtypes = [C.c_size_t, C.c_int, C.c_int]
     L.x3s_rank_profile.restype = C.c_int
     L.x3s_rank_profile.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     L.x3s_rank_plan.restype = C.c_int
@@ -106,6 +108,11 @@ def lib() -> C.CDLL:
 
 def device_count() -> int:
     return int(lib().x3s_device_count())
+
+
+def default_kernel(W: int = 8192, t: int = 15, want_table: bool = False) -> int:
+    """The kernel KERNEL_DEFAULT resolves to for these parameters (x3s_default_kernel)."""
+    return int(lib().x3s_default_kernel(W, t, int(want_table)))
 
 
 def rank_profile(device: int = 0):

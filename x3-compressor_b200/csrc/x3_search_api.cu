@@ -247,6 +247,12 @@ const char *x3s_version(void)
 	return "x3-b200 search 0.4 (sm_100a; kernels: seg, rank, stream, bitsliced, naive)";
 }
 
+int x3s_default_kernel(size_t W, int t, int want_table)
+{
+	const int kind = x3k_default_kind(distances(W), t, want_table != 0);
+	return kind == 2 ? X3S_KERNEL_SEG : (kind == 1 ? X3S_KERNEL_RANK : X3S_KERNEL_STREAM);
+}
+
 size_t x3s_required_bytes(size_t n_positions, size_t W)
 {
 	return x3k_required_bytes(n_positions, W);

@@ -47,7 +47,7 @@ constexpr uint32_t SG_XS_OFF = 13;           /* xs[k] = xsr[SG_XS_OFF + k]: the 
 constexpr uint32_t SG_XS_BYTES = SG_MMAX + 80;
 constexpr uint32_t SG_CHUNK = 256;           /* elements a warp takes per wave: one histogram row */
 constexpr uint32_t SG_CHAIN_MAX = SG_CHUNK;  /* groups up to this size are followed down by one warp (8 elements per lane) */
-constexpr uint32_t SG_WAVE_MAX = 32 * SG_CHUNK; /* groups up to this size go through the waves (<= 32 rows) */
+constexpr uint32_t SG_WAVE_MAX = 31 * SG_CHUNK; /* groups up to this size go through the waves (31 rows + the totals row) */
 constexpr uint32_t SG_Q = 4864;              /* queue slots of the chains: live groups <= M / (t+2) */
 constexpr uint32_t SG_RING = 128;            /* ring slots of the waves: live groups above SG_CHAIN_MAX <= M / 257 */
 constexpr uint32_t SG_BIGQ = 16;             /* live groups above SG_WAVE_MAX: <= M / SG_WAVE_MAX */
@@ -213,7 +213,9 @@ __device__ __forceinline__ void sg_lsd_pass(const SegCtx &c)
 	reinterpret_cast<uint4 *>(mym)[lane] = make_uint4(0u, 0u, 0u, 0u);
 	reinterpret_cast<uint4 *>(mym)[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
 	__syncwarp();
-	uint32_t rk[11]; /* rank of my element of round r among its digit in the warp's block (< 1024): 3 per word */
+	/* rank of my element of round r among its digit in the warp's block (< 1024): 3 per word.  (Rolled loops
+	 * with this array in local memory were measured: 12 % slower -- the unrolled rounds overlap.) */
+	uint32_t rk[11];
 #pragma unroll
 	for (int k = 0; k < 11; ++k) {
 		rk[k] = 0;
@@ -276,7 +278,7 @@ __device__ __forceinline__ void sg_lsd_pass(const SegCtx &c)
 			if (m0 == vm) {
 				peers = vm;
 			} else if (__popc(m0) >= 11) {
-				peers = __match_any_sync(FULL_MASK, valid ? d : 256u + lane);
+				peers = __match_any_sync(FULL_MASK, valid ? d : 256u);
 			} else {
 				if (valid) {
 					atomicOr(&mym[d], 1u << lane);
@@ -318,7 +320,7 @@ __device__ __forceinline__ void sg_lsd_pass(const SegCtx &c)
 /* ---- pushing a group, by size: the CTA's list (above SG_WAVE_MAX), the ring of the waves (above
  * SG_CHAIN_MAX; read behind CTA barriers: no flags, no fences), or the queue of the chains, whose
  * entries are taken by polling warps: the entry is published behind a fence, with its valid bit. */
-__device__ __forceinline__ void sg_push(uint32_t start, uint32_t len, uint32_t L, uint32_t buf)
+__device__ __noinline__ void sg_push(uint32_t start, uint32_t len, uint32_t L, uint32_t buf)
 {
 	if (len > SG_WAVE_MAX) {
 		const uint32_t slot = atomicAdd(&SG_MI->big_tail, 1u) % SG_BIGQ;
@@ -486,7 +488,7 @@ __device__ __forceinline__ void sg_big_level(const SegCtx &c, uint32_t s, uint32
 		if (pm != 0u) {
 			carry = __shfl_sync(FULL_MASK, e, 31 - __clz((int)pm));
 		}
-		b = kept ? sg_byte(e, L) : 256u + lane;
+		b = kept ? sg_byte(e, L) : 256u; /* (one value for all the others: MATCH.ANY takes 2 cycles per distinct value) */
 		return kept;
 	};
 	/* (B) */
@@ -520,7 +522,7 @@ __device__ __forceinline__ void sg_big_level(const SegCtx &c, uint32_t s, uint32
 			const bool kept = kept_byte(r, carry, e, b);
 			const uint32_t base = kept ? SG_MI->dbase[b] : SG_NONE;
 			const bool act = kept && base != SG_NONE;
-			const uint32_t peers = __match_any_sync(FULL_MASK, act ? b : 256u + lane);
+			const uint32_t peers = __match_any_sync(FULL_MASK, act ? b : 256u);
 			if (act) {
 				const uint32_t o = myh[b];
 				Out[base + o + __popc(peers & lt)] = (uint16_t)e;
@@ -538,15 +540,35 @@ __device__ __forceinline__ void sg_big_level(const SegCtx &c, uint32_t s, uint32
 	}
 }
 
-/* ---- one wave: the next groups of the ring, up to 32 rows of SG_CHUNK elements, one warp per row.
- * A group of the ring (any level) is tested, pruned to its kept elements and split by the next byte;
- * its children go to the ring's tail.  Per wave: (form) warp 0 takes groups while their rows fit,
- * (1a) test + last passed position of every row, (1b) kept elements, next bytes, per-row histogram
- * (each lane keeps its 8 elements with byte and rank in registers), (A) one warp per group: totals,
- * children, final offsets written back into the rows, (2) placement.  Returns false when the ring
- * is empty. */
+/* ---- one wave: the next groups of the ring, up to 32 rows, one warp per row.  A group takes one row
+ * per SG_CHUNK elements plus one row for its totals.  A group of the ring (any level) is tested,
+ * pruned to its kept elements and split by the next byte; its children are pushed by size.
+ *   form   warp 0 takes groups while their rows fit
+ *   (1)    every row: test, kept elements, next bytes, histogram row (each lane keeps its 8 elements with
+ *          byte and rank in registers).  What crosses rows -- the last passed element in front of a row --
+ *          is looked for in the 64 elements in front of the row; when they hold none (and are not out of
+ *          reach already) the element in front of the row stands in for it: the kept set only grows,
+ *          which never changes a result (every kept element is a real occurrence of the group's gram)
+ *   (2)    the group's threads, one byte value each: running sums down the group's rows (a row's count ->
+ *          the elements of that byte in the rows in front), the totals of the children that live on
+ *          (>= t+2 elements) into the group's totals row
+ *   (3)    every row: the children's slots from the totals row, its own final offsets, the placement into
+ *          the group's own range of the other buffer; the group's first row pushes the children
+ * Returns false when the ring is empty. */
+constexpr uint32_t SG_WHOLE = 2u;
+
+template <bool PROF>
 __device__ __forceinline__ bool sg_wave(const SegCtx &c)
 {
+	/* measurement build: cycles of the wave's parts and the wave count, behind the phase counters */
+	unsigned long long *wp = reinterpret_cast<unsigned long long *>(sg_smem + SG_SMEM) + 10;
+	unsigned long long wt = 0;
+#define SG_WLAP(k)                                 \
+	if (PROF && threadIdx.x == 0) {                \
+		const unsigned long long now = clock64();  \
+		wp[k] += now - wt;                         \
+		wt = now;                                  \
+	}
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t lt = (1u << lane) - 1u;
 	const uint32_t need = (uint32_t)c.t + 2u;
@@ -555,11 +577,15 @@ __device__ __forceinline__ bool sg_wave(const SegCtx &c)
 	if (head == tail) {
 		return false;
 	}
+	if (PROF && threadIdx.x == 0) {
+		wt = clock64();
+		wp[5] += 1;
+	}
 	if (warp == 0) {
-		const bool have = (uint32_t)lane < tail - head;
+		const bool have = (uint32_t)lane < tail - head && lane < 16;
 		const uint2 ent = have ? SG_MI->ring[(head + lane) % SG_RING] : make_uint2(0u, 0u);
 		const uint32_t len = ent.x >> 16;
-		const uint32_t nch = have ? (len + SG_CHUNK - 1u) / SG_CHUNK : 0u;
+		const uint32_t nch = have ? (len + SG_CHUNK - 1u) / SG_CHUNK + 1u : 0u; /* + the totals row */
 		uint32_t inc = nch;
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
@@ -577,25 +603,23 @@ __device__ __forceinline__ bool sg_wave(const SegCtx &c)
 			g.L = ent.y & 255u;
 			g.buf = (ent.y >> 8) & 1u;
 			g.r0 = inc - nch;
-			g.nrows = nch;
-			g.state = 1u;
+			g.nrows = nch - 1u;
+			g.state = 0u;
 		}
 		const int ng = __popc(fm);
 		const uint32_t rows = __shfl_sync(FULL_MASK, inc, ng - 1);
 		if (lane == 0) {
 			SG_MI->wave_groups = (uint32_t)ng;
 			SG_MI->wave_rows = rows;
+			SG_MI->r_head = head + (uint32_t)ng;
 		}
 	}
 	__syncthreads();
+	SG_WLAP(0)
 	const uint32_t ng = SG_MI->wave_groups, nrows = SG_MI->wave_rows;
-	if (tid == 0) {
-		SG_MI->r_head = head + ng; /* (every thread has read the old value: it is read next behind two more barriers) */
-	}
 	/* my row's group */
 	uint32_t gi = 0, gstart = 0, glen = 0, L = 0, buf = 0, r0 = 0, gn = 0;
-	const bool rowon = (uint32_t)warp < nrows;
-	if (rowon) {
+	if ((uint32_t)warp < nrows) {
 		const uint32_t gr0 = (uint32_t)lane < ng ? SG_MI->grp[lane].r0 : 0xffffu;
 		const uint32_t m = __ballot_sync(FULL_MASK, gr0 <= (uint32_t)warp);
 		gi = 31 - __clz((int)m);
@@ -607,168 +631,171 @@ __device__ __forceinline__ bool sg_wave(const SegCtx &c)
 		r0 = g.r0;
 		gn = g.nrows;
 	}
-	const uint32_t coff = ((uint32_t)warp - r0) * SG_CHUNK;
+	const uint32_t myrow = (uint32_t)warp - r0;
+	const bool rowon = (uint32_t)warp < nrows && myrow < gn; /* (the totals row's warp has no elements) */
+	const uint32_t coff = myrow * SG_CHUNK;
 	const uint16_t *In = SG_P(buf) + gstart;
 	uint16_t *myh = SG_WH + warp * 256;
-	uint32_t st[8];  /* my element of round r: id | rank << 15 | byte << 23 | kept << 31 */
-	uint32_t pmk = 0; /* lane r: which lanes passed in round r */
-	/* (1a) */
+	uint32_t st[8]; /* my element of round r: id | rank << 15 | byte << 23 | kept << 31 */
+	/* (1) */
 	if (rowon) {
-		uint32_t lastp = SG_NONE;
+		reinterpret_cast<uint4 *>(myh)[lane] = make_uint4(0u, 0u, 0u, 0u);
+		uint32_t ef[8];
+#pragma unroll
+		for (int r = 0; r < 8; ++r) { /* all the loads first: nothing between them that they could depend on */
+			const uint32_t i = coff + 32u * r + lane;
+			st[r] = i < glen ? (uint32_t)In[i] : 0u;
+			ef[r] = i + c.la < glen ? (uint32_t)In[i + c.la] : 0xffffffu;
+		}
+		uint32_t pmk[8];
 #pragma unroll
 		for (int r = 0; r < 8; ++r) {
-			const uint32_t i = coff + 32u * r + lane;
-			const uint32_t e = i < glen ? (uint32_t)In[i] & 0x7fffu : 0u;
-			bool pass = false;
-			if (i + c.la < glen) {
-				const uint32_t ef = (uint32_t)In[i + c.la] & 0x7fffu;
-				pass = ef - e <= c.D && e - 3u < c.Bs;
-			}
+			const bool pass = ef[r] - st[r] <= c.D && st[r] - 3u < c.Bs; /* (no element t+1 places on: a huge distance) */
 			if (pass) {
-				SG_L8[e - 3u] = (uint8_t)L;
+				SG_L8[st[r] - 3u] = (uint8_t)L;
 			}
-			const uint32_t pm = __ballot_sync(FULL_MASK, pass);
-			if (lane == r) {
-				pmk = pm;
-			}
-			if (pm != 0u) {
-				lastp = __shfl_sync(FULL_MASK, e, 31 - __clz((int)pm));
-			}
-			st[r] = e;
+			pmk[r] = __ballot_sync(FULL_MASK, pass);
 		}
-		if (lane == 0) {
-			SG_MI->lastp[warp] = lastp;
-		}
-		reinterpret_cast<uint4 *>(myh)[lane] = make_uint4(0u, 0u, 0u, 0u);
-	}
-	__syncthreads();
-	/* (1b) */
-	bool alive = false; /* somebody of my group passed, and there is a deeper level */
-	if (rowon) {
-		const uint32_t lp = (uint32_t)lane < gn ? SG_MI->lastp[r0 + lane] : SG_NONE;
-		const uint32_t havem = __ballot_sync(FULL_MASK, lp != SG_NONE);
-		alive = havem != 0u && L < 32u;
-		if (alive) {
-			const uint32_t before = havem & ((1u << ((uint32_t)warp - r0)) - 1u); /* rows of my group in front of mine */
+		if (L < 32u) {
+			/* the last passed element in front of my row */
 			uint32_t carry = SG_NONE;
-			if (before != 0u) {
-				carry = __shfl_sync(FULL_MASK, lp, 31 - __clz((int)before));
+			if (myrow > 0u) {
+				const uint32_t first = __shfl_sync(FULL_MASK, st[0], 0);
+				bool settled = false;
+#pragma unroll
+				for (int back = 1; back <= 2; ++back) {
+					if (!settled) {
+						const uint32_t j = coff - 32u * back + lane;
+						const uint32_t ej = In[j];
+						const uint32_t efj = j + c.la < glen ? (uint32_t)In[j + c.la] : 0xffffffu;
+						const uint32_t pmj = __ballot_sync(FULL_MASK, efj - ej <= c.D && ej - 3u < c.Bs);
+						const uint32_t lastj = __shfl_sync(FULL_MASK, ej, pmj != 0u ? 31 - __clz((int)pmj) : 0);
+						if (pmj != 0u) {
+							carry = lastj;
+							settled = true;
+						} else if (first - lastj > c.D) { /* (lastj: lane 0's, the smallest position of the 32) */
+							settled = true; /* nothing further back can reach into my row */
+						}
+					}
+				}
+				if (!settled) {
+					carry = In[coff - 1u];
+				}
 			}
+			uint32_t bb[8];
 #pragma unroll
 			for (int r = 0; r < 8; ++r) {
 				const uint32_t i = coff + 32u * r + lane;
 				const uint32_t e = st[r];
-				const uint32_t pm = __shfl_sync(FULL_MASK, pmk, r);
+				const uint32_t pm = pmk[r];
 				const uint32_t upto = pm & ((2u << lane) - 1u);
 				const uint32_t lpv = __shfl_sync(FULL_MASK, e, upto != 0u ? 31 - __clz((int)upto) : 0);
 				const uint32_t lpos = upto != 0u ? lpv : carry;
-				const bool kept = i < glen && 32u * r + lane < SG_CHUNK && lpos != SG_NONE && e - lpos <= c.D;
+				const bool kept = i < glen && lpos != SG_NONE && e - lpos <= c.D;
 				if (pm != 0u) {
 					carry = __shfl_sync(FULL_MASK, e, 31 - __clz((int)pm));
 				}
-				const uint32_t b = kept ? sg_byte(e, L) : 256u + lane;
+				bb[r] = kept ? sg_byte(e, L) : 256u; /* (one value for all the others: a distinct value costs MATCH.ANY 2 cycles) */
+			}
+#pragma unroll
+			for (int r = 0; r < 8; ++r) {
+				const uint32_t b = bb[r];
+				const bool kept = b < 256u;
 				const uint32_t peers = __match_any_sync(FULL_MASK, b);
-				const int leader = __ffs(peers) - 1;
-				uint32_t old = 0;
-				if (kept && lane == leader) {
-					old = myh[b];
+				const uint32_t old = kept ? (uint32_t)myh[b] : 0u;
+				__syncwarp();
+				if (kept && (peers & lt) == 0u) {
 					myh[b] = (uint16_t)(old + __popc(peers));
 				}
-				old = __shfl_sync(FULL_MASK, old, leader);
-				st[r] = kept ? e | ((old + __popc(peers & lt)) << 15) | (b << 23) | 0x80000000u : 0u;
+				st[r] = kept ? st[r] | ((old + __popc(peers & lt)) << 15) | (b << 23) | 0x80000000u : 0u;
 				__syncwarp();
 			}
 		}
 	}
 	__syncthreads();
-	/* (A) one warp per group: totals over its rows, children, final offsets */
-	if ((uint32_t)warp < ng) {
-		const SegGroup g = SG_MI->grp[warp];
-		const uint32_t lp = (uint32_t)lane < g.nrows ? SG_MI->lastp[g.r0 + lane] : SG_NONE;
-		const bool galive = __ballot_sync(FULL_MASK, lp != SG_NONE) != 0u && g.L < 32u;
-		if (galive) {
-			uint32_t tot[8];
-#pragma unroll
-			for (int k = 0; k < 8; ++k) {
-				tot[k] = 0;
+	SG_WLAP(1)
+	/* (2) */
+	if (rowon && L < 32u) {
+		const uint32_t nthr = gn * 32u;
+		uint16_t *col = SG_WH + r0 * 256;
+		for (uint32_t dig = myrow * 32u + lane; dig < 256u; dig += nthr) {
+			uint32_t run = 0;
+#pragma unroll 4
+			for (uint32_t rr = 0; rr < gn; ++rr) {
+				const uint32_t v = col[rr * 256u + dig];
+				col[rr * 256u + dig] = (uint16_t)run;
+				run += v;
 			}
-			for (uint32_t rr = 0; rr < g.nrows; ++rr) {
-				const uint4 hv = reinterpret_cast<const uint4 *>(SG_WH + (g.r0 + rr) * 256)[lane];
-				const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-				for (int k = 0; k < 8; ++k) {
-					tot[k] += (hw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
-				}
-			}
-			uint32_t mine = 0, whole = 0;
-#pragma unroll
-			for (int k = 0; k < 8; ++k) {
-				mine += tot[k] >= need ? tot[k] : 0u;
-				whole |= tot[k] == g.len ? 1u : 0u;
-			}
-			if (__ballot_sync(FULL_MASK, whole != 0u) != 0u) {
-				/* every element kept and followed by one and the same byte: the group stays where it is, and
-				 * nothing changes (same array, same test) down to the level where the bytes differ */
-				const uint32_t Ln = sg_common_levels(SG_P(g.buf) + g.start, g.len, g.L + 1u);
-				if (lane == 0) {
-					sg_push(g.start, g.len, Ln, g.buf);
-				}
-			} else {
-				uint32_t inc = mine;
-#pragma unroll
-				for (int d = 1; d < 32; d <<= 1) {
-					const uint32_t o = __shfl_up_sync(FULL_MASK, inc, d);
-					if (lane >= d) {
-						inc += o;
-					}
-				}
-				uint32_t run[8];
-				uint32_t base = inc - mine;
-#pragma unroll
-				for (int k = 0; k < 8; ++k) {
-					const bool al = tot[k] >= need;
-					run[k] = al ? base : 0xffffu;
-					if (al) {
-						sg_push(g.start + base, tot[k], g.L + 1u, g.buf ^ 1u);
-						base += tot[k];
-					}
-				}
-				for (uint32_t rr = 0; rr < g.nrows; ++rr) {
-					uint4 *row = reinterpret_cast<uint4 *>(SG_WH + (g.r0 + rr) * 256) + lane;
-					const uint4 hv = *row;
-					const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-					uint32_t ow[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-					for (int k = 0; k < 8; ++k) {
-						const uint32_t cnt = (hw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
-						ow[k >> 1] |= run[k] << (16 * (k & 1));
-						if (run[k] != 0xffffu) {
-							run[k] += cnt;
-						}
-					}
-					*row = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-				}
-				if (lane == 0) {
-					SG_MI->grp[warp].state = 0u;
-				}
+			col[gn * 256u + dig] = (uint16_t)(run >= need ? run : 0u);
+			if (run == glen) {
+				SG_MI->grp[gi].state = SG_WHOLE; /* (one byte value at most) */
 			}
 		}
 	}
 	__syncthreads();
-	/* (2) placement into the group's own range of the other buffer */
-	if (rowon && alive && SG_MI->grp[gi].state == 0u) {
-		uint16_t *Out = SG_P(buf ^ 1u) + gstart;
+	SG_WLAP(2)
+	/* (3) */
+	if (rowon && L < 32u) {
+		if (SG_MI->grp[gi].state == SG_WHOLE) {
+			/* every element kept and followed by one and the same byte: the group stays where it is, and
+			 * nothing changes (same array, same test) down to the level where the bytes differ */
+			if (myrow == 0u) {
+				const uint32_t Ln = sg_common_levels(In, glen, L + 1u);
+				if (lane == 0) {
+					sg_push(gstart, glen, Ln, buf);
+				}
+			}
+		} else {
+			const uint4 tv = reinterpret_cast<const uint4 *>(SG_WH + (r0 + gn) * 256)[lane];
+			const uint32_t tw[4] = {tv.x, tv.y, tv.z, tv.w};
+			uint32_t tot[8], mine = 0;
 #pragma unroll
-		for (int r = 0; r < 8; ++r) {
-			const uint32_t v = st[r];
-			if (v & 0x80000000u) {
-				const uint32_t off = myh[(v >> 23) & 255u];
-				if (off != 0xffffu) {
-					Out[off + ((v >> 15) & 255u)] = (uint16_t)(v & 0x7fffu);
+			for (int k = 0; k < 8; ++k) {
+				tot[k] = (tw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+				mine += tot[k];
+			}
+			uint32_t inc = mine;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t o = __shfl_up_sync(FULL_MASK, inc, d);
+				if (lane >= d) {
+					inc += o;
+				}
+			}
+			if (__ballot_sync(FULL_MASK, mine != 0u) != 0u) {
+				const uint4 hv = reinterpret_cast<const uint4 *>(myh)[lane];
+				const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+				uint32_t ow[4] = {0u, 0u, 0u, 0u};
+				uint32_t base = inc - mine;
+#pragma unroll
+				for (int k = 0; k < 8; ++k) {
+					const uint32_t pre = (hw[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+					ow[k >> 1] |= (tot[k] != 0u ? base + pre : 0xffffu) << (16 * (k & 1));
+					if (tot[k] != 0u) {
+						if (myrow == 0u) {
+							sg_push(gstart + base, tot[k], L + 1u, buf ^ 1u);
+						}
+						base += tot[k];
+					}
+				}
+				reinterpret_cast<uint4 *>(myh)[lane] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+				__syncwarp();
+				uint16_t *Out = SG_P(buf ^ 1u) + gstart;
+#pragma unroll
+				for (int r = 0; r < 8; ++r) {
+					const uint32_t v = st[r];
+					if (v & 0x80000000u) {
+						const uint32_t off = myh[(v >> 23) & 255u];
+						if (off != 0xffffu) {
+							Out[off + ((v >> 15) & 255u)] = (uint16_t)(v & 0x7fffu);
+						}
+					}
 				}
 			}
 		}
 	}
+	SG_WLAP(3)
+#undef SG_WLAP
 	return true;
 }
 
@@ -813,7 +840,7 @@ __device__ __forceinline__ void sg_chain(const SegCtx &c, uint32_t start, uint32
 					if (pm != 0u) {
 						carry = __shfl_sync(FULL_MASK, e, 31 - __clz((int)pm));
 					}
-					const uint32_t b = kept ? sg_byte(e, L) : 256u + lane;
+					const uint32_t b = kept ? sg_byte(e, L) : 256u; /* (one value for all the others: a distinct value costs MATCH.ANY 2 cycles) */
 					const uint32_t peers = __match_any_sync(FULL_MASK, b);
 					const int leader = __ffs(peers) - 1;
 					uint32_t old = 0;
@@ -956,7 +983,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 	/* (the cycle counters of the measurement build live in shared memory behind the CTA's own data: no registers) */
 	unsigned long long *pt = reinterpret_cast<unsigned long long *>(sg_smem + SG_SMEM);
 	if (PROF && tid == 0) {
-		for (int k = 0; k < 9; ++k) {
+		for (int k = 0; k < 16; ++k) {
 			pt[k] = 0;
 		}
 		pt[9] = clock64();
@@ -1041,7 +1068,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 		}
 		SG_LAP(4)
 		/* groups above SG_CHAIN_MAX elements, wave after wave */
-		while (sg_wave(c)) {
+		while (sg_wave<PROF>(c)) {
 		}
 		__syncthreads();
 		SG_LAP(5)
@@ -1106,8 +1133,8 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 		}
 	}
 	if (PROF && tid == 0) {
-		for (int k = 0; k < 9; ++k) {
-			a.prof[blockIdx.x * 9 + k] = pt[k];
+		for (int k = 0; k < 16; ++k) {
+			a.prof[blockIdx.x * 16 + k] = pt[k];
 		}
 	}
 #undef SG_LAP
@@ -1176,8 +1203,8 @@ cudaError_t x3k_launch_seg(const X3SearchParams &prm, cudaStream_t stream, int *
 	const unsigned grid = nseg < (unsigned long long)sms ? (unsigned)nseg : (unsigned)sms;
 	const bool prof = getenv("X3_SEG_PROF") != nullptr; /* measurement knob: cycles per phase, printed */
 	if (prof) {
-		if ((e = cudaMalloc((void **)&a.prof, (size_t)grid * 72)) != cudaSuccess) return e;
-		if ((e = cudaMemsetAsync(a.prof, 0, (size_t)grid * 72, stream)) != cudaSuccess) return e;
+		if ((e = cudaMalloc((void **)&a.prof, (size_t)grid * 128)) != cudaSuccess) return e;
+		if ((e = cudaMemsetAsync(a.prof, 0, (size_t)grid * 128, stream)) != cudaSuccess) return e;
 	}
 	if (prof) {
 		x3_seg_kernel<true><<<grid, SG_THREADS, SG_SMEM + 128, stream>>>(a);
@@ -1188,16 +1215,16 @@ cudaError_t x3k_launch_seg(const X3SearchParams &prm, cudaStream_t stream, int *
 		*launches += 1;
 	}
 	if (prof) {
-		unsigned long long *h = (unsigned long long *)malloc((size_t)grid * 72);
+		unsigned long long *h = (unsigned long long *)malloc((size_t)grid * 128);
 		if (h != nullptr && cudaStreamSynchronize(stream) == cudaSuccess &&
-		    cudaMemcpy(h, a.prof, (size_t)grid * 72, cudaMemcpyDeviceToHost) == cudaSuccess) {
+		    cudaMemcpy(h, a.prof, (size_t)grid * 128, cudaMemcpyDeviceToHost) == cudaSuccess) {
 			static const char *name[8] = {"load", "pass 0", "passes 1-3", "groups4", "big groups", "waves", "chains", "store"};
-			double tot[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
+			double tot[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
 			for (unsigned b = 0; b < grid; ++b) {
 				double cta = 0;
-				for (int k = 0; k < 9; ++k) {
-					tot[k] += (double)h[b * 9 + k];
-					cta += k < 8 ? (double)h[b * 9 + k] : 0;
+				for (int k = 0; k < 16; ++k) {
+					tot[k] += (double)h[b * 16 + k];
+					cta += k < 8 ? (double)h[b * 16 + k] : 0;
 				}
 				if (cta > mx) mx = cta;
 			}
@@ -1205,7 +1232,9 @@ cudaError_t x3k_launch_seg(const X3SearchParams &prm, cudaStream_t stream, int *
 			for (int k = 0; k < 8; ++k) {
 				fprintf(stderr, "  %s %.0f", name[k], tot[k] / (tot[8] > 0 ? tot[8] : 1));
 			}
-			fprintf(stderr, "\n");
+			fprintf(stderr, ";  %.1f waves per segment, cycles per wave: form %.0f  (1) %.0f  (2) %.0f  (3) %.0f\n",
+			        tot[15] / (tot[8] > 0 ? tot[8] : 1), tot[10] / (tot[15] > 0 ? tot[15] : 1), tot[11] / (tot[15] > 0 ? tot[15] : 1),
+			        tot[12] / (tot[15] > 0 ? tot[15] : 1), tot[13] / (tot[15] > 0 ? tot[15] : 1));
 		}
 		free(h);
 		cudaFree(a.prof);
