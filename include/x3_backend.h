@@ -63,7 +63,19 @@ void set_magic_factor2(size_t factor);
  */
 void x3_search_prepare(const char *base, size_t isize);
 
-/* NEW.  Drops the tables of the last x3_search_prepare(). */
+/*
+ * NEW.  x3_search_prepare() starts the search on a thread of its own and returns; the table lands
+ * piece by piece from the left and find_best_match(p) waits until p has landed, so a host that reads
+ * positions in increasing order (reference x3.c:379) starts on the first piece.  (X3_PREPARE_SYNC=1 in the
+ * environment, or a request for the full table, makes prepare wait for the whole table itself.)
+ * x3_search_wait() blocks until the whole table has landed, x3_search_ready() says how many leading
+ * positions have, x3_search_landed_ms() how long it took from entering prepare to the last one.
+ */
+void x3_search_wait(void);
+size_t x3_search_ready(void);
+double x3_search_landed_ms(void);
+
+/* NEW.  Drops the tables of the last x3_search_prepare() (waits for a search still running). */
 void x3_search_release(void);
 
 /*

@@ -113,6 +113,17 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
                     void *lstar, void *H, x3s_timing *timing);
 
 /*
+ * x3s_search_host() for a consumer that reads the table from left to right while it is still being
+ * made (the reference's compress() visits positions in increasing order, x3.c:379): the call itself
+ * returns when the whole table has landed, but while it runs -- call it from a thread of its own --
+ * *ready is kept at the number of leading positions whose Lstar is final in `lstar` (stored with
+ * release order; it only grows, and ends at n).  Lstar only.  With more than one GPU the prefix moves
+ * on through the shards in position order.
+ */
+int x3s_search_host_stream(const void *x, size_t n, size_t W, int t, int ngpus, int variant, void *lstar,
+                           x3s_timing *timing, volatile size_t *ready);
+
+/*
  * Restricts x3s_search_host() to the given CUDA device ordinals, in this order
  * (count <= 0 restores "devices 0 .. ngpus-1").  One process per GPU launchers
  * (torchrun) call it with their LOCAL_RANK.

@@ -105,3 +105,79 @@ def test_seg_search_rejects_what_it_cannot_take(pkg):
         with pytest.raises(pkg.X3SearchError) as ei:
             pkg.search_host(data, variant=pkg.KERNEL_SEG, **kw)
         assert ei.value.code == pkg.X3S_ERR_UNSUPP
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_streamed_table_lands_from_the_left(pkg, corpus, pinned, monkeypatch):
+    """x3s_search_host_stream: while the call runs, *ready only grows, every position below it already holds
+    its final Lstar, and it ends at n with the same table as x3s_search_host"""
+    import ctypes as C
+    import threading
+
+    monkeypatch.setenv("X3_SEG_PIECE_MB", "1")
+    data = _inputs(corpus, "C5", 6_000_000)
+    n, W, t = len(data), 8192, 15
+    want, _, _ = pkg.search_host(data, W=W, t=t, variant=pkg.KERNEL_SEG)
+    L = pkg.lib()
+    if pinned:
+        px, pl = L.x3s_host_alloc(n + W), L.x3s_host_alloc(n)
+        x = np.ctypeslib.as_array(C.cast(px, C.POINTER(C.c_uint8)), shape=(n + W,))
+        out = np.ctypeslib.as_array(C.cast(pl, C.POINTER(C.c_uint8)), shape=(n,))
+    else:
+        x, out = np.zeros(n + W, dtype=np.uint8), np.empty(n, dtype=np.uint8)
+    x[:n] = data
+    x[n:] = 0
+    out[:] = 255
+    ready = C.c_size_t(0)
+    rc = []
+    th = threading.Thread(target=lambda: rc.append(L.x3s_search_host_stream(
+        x.ctypes.data, n, W, t, 1, pkg.KERNEL_DEFAULT, out.ctypes.data, None, C.byref(ready))))
+    th.start()
+    seen, checks = 0, 0
+    while th.is_alive():
+        r = ready.value
+        assert r >= seen
+        if r > seen:
+            assert np.array_equal(out[seen:r], want[seen:r])
+            checks += 1
+            seen = r
+    th.join()
+    assert rc == [0] and ready.value == n
+    assert np.array_equal(out, want)
+    assert checks >= 2          # it did arrive in pieces
+    if pinned:
+        L.x3s_host_free(px)
+        L.x3s_host_free(pl)
+
+
+def test_backend_prepare_returns_before_the_table_and_find_best_match_waits(pkg, corpus):
+    """the backend.h drop-in: prepare starts the search and returns; find_best_match(p) answers once p has landed;
+    x3_search_table() (which waits) shows the oracle's table"""
+    import ctypes as C
+
+    data = _inputs(corpus, "C5", 3_000_000)
+    n, W, t = len(data), 8192, 15
+    buf = pkg.padded(data, W)
+    L = pkg.lib()
+    L.set_forward_window(W)
+    L.set_max_match_count(t)
+    L.set_magic_factor1(4)
+    L.set_magic_factor2(0)
+    no_find = pkg.DICT_FIND_FN(lambda p: (1 << 64) - 1)
+    no_len = pkg.DICT_LEN_FN(lambda i: 0)
+    L.x3_backend_set_dict(C.cast(no_find, C.c_void_p), C.cast(no_len, C.c_void_p))
+    try:
+        L.x3_search_prepare(buf.ctypes.data, n)
+        _, ls_ref = ol.table(data, W, t)
+        L.find_best_match.restype = C.c_size_t
+        L.find_best_match.argtypes = [C.c_void_p]
+        for p in (0, 1, n // 2, n - 1):          # each waits for its piece; empty dictionary: the answer is max(Lstar, 1)
+            assert L.find_best_match(buf.ctypes.data + p) == max(int(ls_ref[p]), 1)
+        Lp, nn = C.c_void_p(), C.c_size_t()
+        L.x3_search_table(None, C.byref(Lp), C.byref(nn))
+        tab = np.ctypeslib.as_array(C.cast(Lp, C.POINTER(C.c_uint8)), shape=(nn.value,))
+        assert nn.value == n and L.x3_search_ready() == n and np.array_equal(tab, ls_ref)
+        assert L.x3_search_landed_ms() > 0
+    finally:
+        L.x3_search_release()
+        L.x3_backend_set_dict(None, None)

@@ -100,6 +100,12 @@ def lib() -> C.CDLL:
     L.x3_search_release.restype = None
     L.x3_search_prepare_ms.restype = C.c_double
     L.x3_search_startup_ms.restype = C.c_double
+    L.x3_search_landed_ms.restype = C.c_double
+    L.x3_search_ready.restype = C.c_size_t
+    L.x3_search_wait.restype = None
+    L.x3s_search_host_stream.restype = C.c_int
+    L.x3s_search_host_stream.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                         C.POINTER(Timing), C.POINTER(C.c_size_t)]
     L.x3_search_table.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
     L.x3_backend_set_dict.argtypes = [C.c_void_p, C.c_void_p]
     _lib = L

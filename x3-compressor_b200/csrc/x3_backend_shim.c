@@ -9,14 +9,21 @@
  *
  * C99, no CUDA types.  Talks to the device layer only through x3_search.h.
  */
-#define _POSIX_C_SOURCE 200809L
+#define _GNU_SOURCE
 #include "x3_backend.h"
 #include "x3_search.h"
 
+#include <pthread.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <time.h>
+
+#ifndef MADV_POPULATE_WRITE
+#define MADV_POPULATE_WRITE 23
+#endif
 
 /* reference backend.c:8,21,33,34 */
 static size_t g_forward_window = 8 * 1024;
@@ -59,14 +66,89 @@ static double g_prepare_ms = 0.0;
 static double g_startup_ms = 0.0; /* one-off CUDA start-up (driver + first context) inside the last prepare */
 static double g_register_ms = 0.0; /* page-locking the caller's buffer inside the last prepare */
 
+/* The search runs on a thread of its own (x3s_search_host_stream) and the table lands piece by piece,
+ * from the left: find_best_match(p) answers as soon as position p has landed -- the reference's
+ * compress() reads positions in increasing order (x3.c:379), so it starts on the first piece while
+ * the rest of the input is still being uploaded and searched. */
+static volatile size_t g_ready = 0;     /* leading positions of g_lstar that are final */
+static size_t g_ready_seen = 0;         /* the consumer's last look at it */
+static pthread_t g_worker, g_toucher;
+static int g_worker_on = 0, g_toucher_on = 0;
+static volatile int g_worker_done = 0;
+static double g_landed_ms = 0.0;        /* prepare entered -> whole table landed */
+static struct timespec g_t_enter;
+static struct {
+	int t, ngpus, variant;
+} g_job;
+
+static double ms_since(const struct timespec *t0)
+{
+	struct timespec t1;
+	clock_gettime(CLOCK_MONOTONIC, &t1);
+	return (t1.tv_sec - t0->tv_sec) * 1e3 + (t1.tv_nsec - t0->tv_nsec) * 1e-6;
+}
+
 static void die(const char *what)
 {
 	fprintf(stderr, "x3 search backend: %s\n", what);
 	abort();
 }
 
+static void die(const char *what);
+
+static void *worker_main(void *arg)
+{
+	(void)arg;
+	int rc = x3s_search_host_stream(g_base, g_isize, g_forward_window, g_job.t, g_job.ngpus, g_job.variant, g_lstar, NULL,
+	                                &g_ready);
+	if (rc != X3S_OK) {
+		die(x3s_last_error());
+	}
+	g_landed_ms = ms_since(&g_t_enter);
+	__atomic_store_n(&g_worker_done, 1, __ATOMIC_RELEASE);
+	return NULL;
+}
+
+/* the table is fresh memory: have the kernel map it (a copy from the device into unmapped pages spends
+ * most of its time in page faults) while the input is uploaded and searched; nothing is written */
+static void *toucher_main(void *arg)
+{
+	(void)arg;
+	const size_t step = (size_t)8 << 20;
+	for (size_t o = 0; o < g_isize; o += step) {
+		const size_t len = g_isize - o < step ? g_isize - o : step;
+		if (madvise(g_lstar + o, len, MADV_POPULATE_WRITE) != 0) {
+			break; /* an older kernel: the copies fault the pages in themselves */
+		}
+	}
+	return NULL;
+}
+
+void x3_search_wait(void)
+{
+	if (g_worker_on) {
+		pthread_join(g_worker, NULL);
+		g_worker_on = 0;
+	}
+	if (g_toucher_on) {
+		pthread_join(g_toucher, NULL);
+		g_toucher_on = 0;
+	}
+}
+
+size_t x3_search_ready(void)
+{
+	return g_base == NULL ? 0 : __atomic_load_n(&g_ready, __ATOMIC_ACQUIRE);
+}
+
+double x3_search_landed_ms(void)
+{
+	return g_landed_ms;
+}
+
 void x3_search_release(void)
 {
+	x3_search_wait();
 	if (g_registered != NULL) {
 		x3s_host_unregister(g_registered);
 		g_registered = NULL;
@@ -77,6 +159,9 @@ void x3_search_release(void)
 		free(g_lstar);
 	}
 	g_lstar_pinned = 0;
+	g_ready = 0;
+	g_ready_seen = 0;
+	g_worker_done = 0;
 	free(g_table);
 	g_lstar = NULL;
 	g_table = NULL;
@@ -90,6 +175,8 @@ void x3_search_prepare(const char *base, size_t isize)
 	clock_gettime(CLOCK_MONOTONIC, &t0);
 
 	x3_search_release();
+	g_t_enter = t0;
+	g_landed_ms = 0.0;
 
 	int ngpus = 0;
 	const char *env = getenv("X3_GPUS");
@@ -141,26 +228,41 @@ void x3_search_prepare(const char *base, size_t isize)
 		clock_gettime(CLOCK_MONOTONIC, &s1);
 		g_register_ms = (s1.tv_sec - s0.tv_sec) * 1e3 + (s1.tv_nsec - s0.tv_nsec) * 1e-6;
 	}
+	int fresh = 0;
 	if (g_lstar == NULL) {
-		g_lstar = malloc(isize > 0 ? isize : 1);
-		if (g_lstar == NULL) {
+		/* 2 MB aligned, so that the kernel may back it with huge pages */
+		void *mem = NULL;
+		const size_t bytes = ((isize > 0 ? isize : 1) + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+		if (posix_memalign(&mem, (size_t)2 << 20, bytes) != 0 || mem == NULL) {
 			die("out of memory");
 		}
+		(void)madvise(mem, bytes, MADV_HUGEPAGE);
+		g_lstar = mem;
+		fresh = 1;
 	}
-	if (isize > 0) {
-		/* backend.c:76: the selection loop never runs for t <= 0 */
-		int t = g_max_match_count;
-		if (t < 0) {
-			t = 0;
+	g_base = base;
+	g_isize = isize;
+	/* backend.c:76: the selection loop never runs for t <= 0 */
+	g_job.t = g_max_match_count < 0 ? 0 : g_max_match_count;
+	g_job.ngpus = ngpus;
+	g_job.variant = variant;
+	if (isize > 0 && !want_table && getenv("X3_PREPARE_SYNC") == NULL) {
+		/* the search on its own thread; the caller goes on and find_best_match() waits where it must */
+		if (fresh && isize >= ((size_t)4 << 20)) {
+			g_toucher_on = pthread_create(&g_toucher, NULL, toucher_main, NULL) == 0;
 		}
-		int rc = x3s_search_host(base, isize, g_forward_window, t, ngpus, variant, g_lstar, g_table, NULL);
+		if (pthread_create(&g_worker, NULL, worker_main, NULL) != 0) {
+			die("cannot start the search thread");
+		}
+		g_worker_on = 1;
+	} else if (isize > 0) {
+		int rc = x3s_search_host(base, isize, g_forward_window, g_job.t, ngpus, variant, g_lstar, g_table, NULL);
 		if (rc != X3S_OK) {
 			die(x3s_last_error());
 		}
+		g_ready = isize;
+		g_landed_ms = ms_since(&t0);
 	}
-
-	g_base = base;
-	g_isize = isize;
 
 	clock_gettime(CLOCK_MONOTONIC, &t1);
 	g_prepare_ms = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
@@ -183,6 +285,7 @@ double x3_search_register_ms(void)
 
 void x3_search_table(const uint8_t **H, const uint8_t **Lstar, size_t *n)
 {
+	x3_search_wait(); /* the whole table */
 	if (H != NULL) {
 		*H = g_table;
 	}
@@ -210,7 +313,17 @@ size_t find_best_match(char *p)
 	/* Lstar = number of i with count[i] > tc*, the only tc the reference's loop
 	 * nest returns from (count is non-increasing in i and i == 0 is never
 	 * filtered).  0 stands for "return 1 without looking at the dictionary". */
-	const int lstar = g_lstar[p - g_base];
+	const size_t pos = (size_t)(p - g_base);
+	if (pos >= g_ready_seen) {
+		/* not landed the last time we looked: look again, and wait for the piece if it is still on its way */
+		size_t r = __atomic_load_n(&g_ready, __ATOMIC_ACQUIRE);
+		while (pos >= r) {
+			sched_yield();
+			r = __atomic_load_n(&g_ready, __ATOMIC_ACQUIRE);
+		}
+		g_ready_seen = r;
+	}
+	const int lstar = g_lstar[pos];
 
 	for (int i = lstar - 1; i >= 0; --i) {
 		/* backend.c:79-83 */

@@ -14,7 +14,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <atomic>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -61,8 +63,16 @@ struct DevState {
 	cudaEvent_t pev[X3S_MAX_PIECES][2] = {}; /* per lane: last search queued so far done, its Lstar back */
 	std::vector<cudaEvent_t> upev;           /* per chunk: uploaded */
 	bool pinited = false;
+	bool follow_pageable = false; /* last search: a host thread brought the pieces home (pageable table) */
 	int pieces = 1;  /* lanes of the last search on this device */
 	int pfirst = 0;  /* chunk whose upload lets the first search start */
+};
+
+/* the host thread that follows a shard's pieces home (segment search, see x3s_search_host) */
+struct FollowCtx {
+	std::thread thr;
+	std::atomic<size_t> queued{0}; /* pieces whose search (and, page-locked table, copy) is queued */
+	std::atomic<int> failed{0};
 };
 
 /* what the rank search's per-chunk hooks need */
@@ -289,10 +299,17 @@ int x3s_search_device(int device, const void *d_x, size_t n_positions, size_t W,
 	return launch_on(device, variant, prm, (cudaStream_t)stream, nullptr);
 }
 
-int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int variant, void *lstar, void *H,
-                    x3s_timing *timing)
+} /* extern "C" */
+
+namespace {
+
+int search_host_impl(const void *x, size_t n, size_t W, int t, int ngpus, int variant, void *lstar, void *H,
+                     x3s_timing *timing, volatile size_t *ready)
 {
 	const auto wall0 = std::chrono::steady_clock::now();
+	if (ready != nullptr) {
+		__atomic_store_n(ready, (size_t)0, __ATOMIC_RELEASE);
+	}
 	int rc = check_params(W, t, H, variant);
 	if (rc != X3S_OK) {
 		return rc;
@@ -337,6 +354,39 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 	std::vector<int> shard_launches(G, 0);
 	std::vector<int> shard_rc(G, X3S_OK);
 	std::vector<std::string> shard_err(G);
+	/* how far the table has landed: per shard, and as the prefix of the whole input a consumer that reads
+	 * left to right (the reference's compress(), x3.c:379) may use */
+	std::unique_ptr<FollowCtx[]> follow(new FollowCtx[G]);
+	std::unique_ptr<std::atomic<size_t>[]> landed(new std::atomic<size_t>[G]);
+	for (int g = 0; g < G; ++g) {
+		landed[g].store(0);
+	}
+	std::mutex pub_mu;
+	auto publish = [&](int g, size_t upto) {
+		landed[g].store(upto, std::memory_order_release);
+		if (ready == nullptr) {
+			return;
+		}
+		std::lock_guard<std::mutex> lk(pub_mu);
+		size_t w = 0;
+		for (int k = 0; k < G; ++k) {
+			const size_t pk = landed[k].load(std::memory_order_acquire);
+			w = a[k] + pk;
+			if (pk < a[k + 1] - a[k]) {
+				break;
+			}
+		}
+		if (w > *ready) {
+			__atomic_store_n(ready, w, __ATOMIC_RELEASE);
+		}
+	};
+	auto join_followers = [&]() {
+		for (int g = 0; g < G; ++g) {
+			if (follow[g].thr.joinable()) {
+				follow[g].thr.join();
+			}
+		}
+	};
 	/* one shard: upload the slice with its trailing halo, search, bring Lstar back */
 	auto shard = [&](int g) -> int {
 		const int dev = g_ids.empty() ? g : g_ids[g];
@@ -345,6 +395,7 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 		if (np == 0) {
 			return X3S_OK;
 		}
+		ds.follow_pageable = false;
 		CU_TRY(cudaSetDevice(dev));
 		int rc2 = ensure_kernel_init(dev);
 		if (rc2 != X3S_OK) {
@@ -376,18 +427,24 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 		const int kind = variant == X3S_KERNEL_DEFAULT ? x3k_default_kind(D, t, H != nullptr)
 		                 : (variant == X3S_KERNEL_RANK ? 1 : (variant == X3S_KERNEL_SEG ? 2 : 0));
 		const bool rank = H == nullptr && kind == 1;
-		if (kind == 2 && pinned_io && getenv("X3_HOST_PIECES") == nullptr) {
-			/* Segment search between page-locked buffers, piece by piece: the upload runs ahead on ds.stream,
-			 * a piece (a whole number of segments, 32 MB unless X3_SEG_PIECE_MB says otherwise) is searched on a
-			 * second stream as soon as the bytes it reads -- its own and the window behind them -- have
-			 * arrived, and its Lstar goes back on a third while the next pieces are searched. */
+		if (kind == 2 && getenv("X3_HOST_PIECES") == nullptr) {
+			/* Segment search, piece by piece: the upload runs ahead on ds.stream, a piece (a whole number of
+			 * segments; 32 MB between page-locked buffers, 16 MB otherwise, X3_SEG_PIECE_MB overrides) is
+			 * searched on a second stream as soon as the bytes it reads -- its own and the window behind
+			 * them -- have arrived, and its Lstar goes back on a third while the next pieces are searched.
+			 * Pageable buffers (what the backend.h drop-in gets from the reference's main, x3.c:579) take the
+			 * same route: an upload from pageable memory holds this thread only while the driver stages it,
+			 * and the copies back to a pageable table -- which hold their caller until they are done -- are
+			 * made by a second host thread, which also publishes how far the table has landed (`ready`). */
+			const bool x_pinned = host_pinned(x), l_pinned = host_pinned(lstar);
 			const size_t B = x3k_seg_positions(D);
 			const char *pm = getenv("X3_SEG_PIECE_MB");
-			const size_t mb = pm != nullptr && atoi(pm) >= 1 ? (size_t)atoi(pm) : 32;
+			const size_t mb = pm != nullptr && atoi(pm) >= 1 ? (size_t)atoi(pm) : (x_pinned && l_pinned ? 32 : 16);
 			size_t PS = ((mb << 20) / B) * B;
 			if (PS < B) PS = B;
 			const size_t nps = (np + PS - 1) / PS;
-			if (nps >= 2) {
+			const bool follower = !l_pinned || ready != nullptr; /* a host thread follows the pieces home */
+			if (nps >= 2 || (follower && nps >= 1)) {
 				if (!ds.pinited) {
 					for (int p = 0; p < X3S_MAX_PIECES; ++p) {
 						CU_TRY(cudaStreamCreateWithFlags(&ds.ps[p], cudaStreamNonBlocking));
@@ -397,7 +454,7 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 					}
 					ds.pinited = true;
 				}
-				while (ds.upev.size() < 2 * nps) {
+				while (ds.upev.size() < 3 * nps) {
 					cudaEvent_t ev = nullptr;
 					CU_TRY(cudaEventCreate(&ev));
 					ds.upev.push_back(ev);
@@ -408,21 +465,71 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 				CU_TRY(cudaEventRecord(ds.ev[0], U));
 				CU_TRY(cudaStreamWaitEvent(K, ds.ev[0], 0));
 				CU_TRY(cudaStreamWaitEvent(Cc, ds.ev[0], 0));
-				for (size_t q = 0; q < nps; ++q) {
-					const size_t b0 = q * PS, b1 = q + 1 == nps ? have : (q + 1) * PS;
-					CU_TRY(cudaMemcpyAsync(ds.d_x + b0, (const uint8_t *)x + a[g] + b0, b1 - b0, cudaMemcpyHostToDevice, U));
-					if (q + 1 == nps && need > have) {
-						CU_TRY(cudaMemsetAsync(ds.d_x + have, 0, need - have, U));
-					}
-					CU_TRY(cudaEventRecord(ds.upev[q], U));
+				/* the follower: piece q is taken home (pageable table) or waited for (page-locked table: the copy
+				 * is queued by this thread) once this thread has queued its search */
+				FollowCtx &fc = follow[g];
+				fc.queued.store(0);
+				fc.failed.store(0);
+				if (follower) {
+					uint8_t *dst0 = (uint8_t *)lstar + a[g];
+					fc.thr = std::thread([&, dev, nps, PS, np, dst0, l_pinned, Cc, g]() {
+						if (cudaSetDevice(dev) != cudaSuccess) {
+							fc.failed.store(1);
+						}
+						for (size_t q = 0; q < nps && fc.failed.load() == 0; ++q) {
+							while (fc.queued.load(std::memory_order_acquire) <= q && fc.failed.load() == 0) {
+								std::this_thread::yield();
+							}
+							if (fc.failed.load() != 0) {
+								break;
+							}
+							const size_t p0 = q * PS, len = np - p0 < PS ? np - p0 : PS;
+							cudaError_t e;
+							if (l_pinned) {
+								e = cudaEventSynchronize(ds.upev[2 * nps + q]);
+							} else {
+								e = cudaEventSynchronize(ds.upev[nps + q]);
+								if (e == cudaSuccess) e = cudaMemcpyAsync(dst0 + p0, ds.d_l + p0, len, cudaMemcpyDeviceToHost, Cc);
+								if (e == cudaSuccess) e = cudaStreamSynchronize(Cc);
+							}
+							if (e != cudaSuccess) {
+								fc.failed.store(1);
+								break;
+							}
+							publish(g, p0 + len);
+						}
+						if (!l_pinned && fc.failed.load() == 0) {
+							(void)cudaEventRecord(ds.pev[0][1], Cc);
+							(void)cudaEventSynchronize(ds.pev[0][1]);
+						}
+					});
 				}
-				CU_TRY(cudaEventRecord(ds.ev[1], U));
+				auto bail = [&](cudaError_t e) -> int { /* never leave the follower spinning */
+					fc.failed.store(1);
+					return fail(X3S_ERR_CUDA, "segment pieces: %s", cudaGetErrorString(e));
+				};
+				cudaError_t ce = cudaSuccess;
+				size_t up = 0; /* pieces uploaded so far */
+				auto upload = [&](size_t q) -> cudaError_t {
+					const size_t b0 = q * PS, b1 = q + 1 == nps ? have : (q + 1) * PS;
+					cudaError_t e = cudaMemcpyAsync(ds.d_x + b0, (const uint8_t *)x + a[g] + b0, b1 - b0, cudaMemcpyHostToDevice, U);
+					if (e == cudaSuccess && q + 1 == nps && need > have) {
+						e = cudaMemsetAsync(ds.d_x + have, 0, need - have, U);
+					}
+					if (e == cudaSuccess) e = cudaEventRecord(ds.upev[q], U);
+					return e;
+				};
 				for (size_t q = 0; q < nps; ++q) {
 					const size_t p0 = q * PS, len = np - p0 < PS ? np - p0 : PS;
 					size_t last = (p0 + len + W + 64) / PS; /* the piece that brings the last byte this one reads */
 					if (last >= nps) last = nps - 1;
 					if (q == 0) ds.pfirst = (int)last;
-					CU_TRY(cudaStreamWaitEvent(K, ds.upev[last], 0));
+					/* uploads interleaved with the launches: from pageable memory each one holds this thread */
+					while (up <= last && ce == cudaSuccess) {
+						ce = upload(up++);
+					}
+					if (ce != cudaSuccess) return bail(ce);
+					if ((ce = cudaStreamWaitEvent(K, ds.upev[last], 0)) != cudaSuccess) return bail(ce);
 					X3SearchParams prm;
 					prm.x = ds.d_x + p0;
 					prm.n = len;
@@ -434,19 +541,29 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 					prm.deep = nullptr;
 					prm.ntiles = 0;
 					prm.kd = 0;
-					CU_TRY(x3k_launch_seg(prm, K, &shard_launches[g]));
-					CU_TRY(cudaEventRecord(ds.upev[nps + q], K));
-					CU_TRY(cudaStreamWaitEvent(Cc, ds.upev[nps + q], 0));
-					CU_TRY(cudaMemcpyAsync((uint8_t *)lstar + a[g] + p0, ds.d_l + p0, len, cudaMemcpyDeviceToHost, Cc));
+					if ((ce = x3k_launch_seg(prm, K, &shard_launches[g])) != cudaSuccess) return bail(ce);
+					if ((ce = cudaEventRecord(ds.upev[nps + q], K)) != cudaSuccess) return bail(ce);
+					if (l_pinned) {
+						if ((ce = cudaStreamWaitEvent(Cc, ds.upev[nps + q], 0)) != cudaSuccess) return bail(ce);
+						if ((ce = cudaMemcpyAsync((uint8_t *)lstar + a[g] + p0, ds.d_l + p0, len, cudaMemcpyDeviceToHost, Cc)) != cudaSuccess) return bail(ce);
+						if ((ce = cudaEventRecord(ds.upev[2 * nps + q], Cc)) != cudaSuccess) return bail(ce);
+					}
+					fc.queued.store(q + 1, std::memory_order_release);
 				}
-				CU_TRY(cudaEventRecord(ds.pev[0][0], K));
-				CU_TRY(cudaEventRecord(ds.pev[1][0], K));
-				CU_TRY(cudaEventRecord(ds.pev[0][1], Cc));
-				CU_TRY(cudaStreamWaitEvent(U, ds.pev[0][0], 0));
-				CU_TRY(cudaStreamWaitEvent(U, ds.pev[0][1], 0));
-				CU_TRY(cudaEventRecord(ds.ev[3], U));
-				CU_TRY(cudaEventRecord(sc.last, U));
+				if ((ce = cudaEventRecord(ds.ev[1], U)) != cudaSuccess) return bail(ce);
+				if ((ce = cudaEventRecord(ds.pev[0][0], K)) != cudaSuccess) return bail(ce);
+				if ((ce = cudaEventRecord(ds.pev[1][0], K)) != cudaSuccess) return bail(ce);
+				if (l_pinned) {
+					if ((ce = cudaEventRecord(ds.pev[0][1], Cc)) != cudaSuccess) return bail(ce);
+				}
+				if ((ce = cudaStreamWaitEvent(U, ds.pev[0][0], 0)) != cudaSuccess) return bail(ce);
+				if (l_pinned) {
+					if ((ce = cudaStreamWaitEvent(U, ds.pev[0][1], 0)) != cudaSuccess) return bail(ce);
+				}
+				if ((ce = cudaEventRecord(ds.ev[3], U)) != cudaSuccess) return bail(ce);
+				if ((ce = cudaEventRecord(sc.last, U)) != cudaSuccess) return bail(ce);
 				ds.pieces = 2;
+				ds.follow_pageable = !l_pinned;
 				return X3S_OK;
 			}
 		}
@@ -548,6 +665,8 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 		rc = shard(0);
 		lap("shard queued");
 		if (rc != X3S_OK) {
+			follow[0].failed.store(1);
+			join_followers();
 			return rc;
 		}
 	} else {
@@ -568,10 +687,21 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 		lap("shards queued");
 		for (int g = 0; g < G; ++g) {
 			if (shard_rc[g] != X3S_OK) {
+				for (int k = 0; k < G; ++k) {
+					follow[k].failed.store(1);
+				}
+				join_followers();
 				return fail(shard_rc[g], "GPU shard %d: %s", g, shard_err[g].c_str());
 			}
 		}
 	}
+	join_followers();
+	for (int g = 0; g < G; ++g) {
+		if (follow[g].failed.load() != 0) {
+			return fail(X3S_ERR_CUDA, "GPU shard %d: bringing the table home failed: %s", g, cudaGetErrorString(cudaGetLastError()));
+		}
+	}
+	lap("pieces home");
 	int launches = 0;
 	for (int g = 0; g < G; ++g) {
 		launches += shard_launches[g];
@@ -595,7 +725,7 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 			 * can start, from there to the end of the last search, from there to the last byte back */
 			float up = 0.f, all = 0.f, kend = 0.f;
 			CU_TRY(cudaEventElapsedTime(&up, ds.ev[0], ds.upev[(size_t)ds.pfirst]));
-			CU_TRY(cudaEventElapsedTime(&all, ds.ev[0], ds.ev[3]));
+			CU_TRY(cudaEventElapsedTime(&all, ds.ev[0], ds.follow_pageable ? ds.pev[0][1] : ds.ev[3]));
 			for (int p = 0; p < ds.pieces; ++p) {
 				CU_TRY(cudaEventElapsedTime(&ms, ds.ev[0], ds.pev[p][0]));
 				if (ms > kend) kend = ms;
@@ -613,11 +743,33 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 		if (ms > tm.d2h_ms) tm.d2h_ms = ms;
 	}
 	lap("done");
+	if (ready != nullptr) {
+		__atomic_store_n(ready, n, __ATOMIC_RELEASE);
+	}
 	tm.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
 	if (timing != nullptr) {
 		*timing = tm;
 	}
 	return X3S_OK;
+}
+
+} /* namespace */
+
+extern "C" {
+
+int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int variant, void *lstar, void *H,
+                    x3s_timing *timing)
+{
+	return search_host_impl(x, n, W, t, ngpus, variant, lstar, H, timing, nullptr);
+}
+
+int x3s_search_host_stream(const void *x, size_t n, size_t W, int t, int ngpus, int variant, void *lstar,
+                           x3s_timing *timing, volatile size_t *ready)
+{
+	if (ready == nullptr) {
+		return fail(X3S_ERR_ARG, "x3s_search_host_stream: null progress word");
+	}
+	return search_host_impl(x, n, W, t, ngpus, variant, lstar, nullptr, timing, ready);
 }
 
 int x3s_set_devices(const int *ids, int count)

@@ -317,6 +317,308 @@ __device__ __forceinline__ void sg_lsd_pass(const SegCtx &c)
 	__syncthreads();
 }
 
+/* ---- the LSD pass, two sub-blocks per warp in flight (the production form; sg_lsd_pass above is the
+ * one-block statement of the same pass, kept for -DX3_SEG_LSD1 comparisons).  A round of the pass is one
+ * long dependent chain (load, gram, shuffles, atomics, read back, histogram update) and a CTA has only 8
+ * warps per scheduler to hide it with, so every warp works on TWO sub-blocks at once -- sub-block s =
+ * elements [s * 32 RH, (s + 1) * 32 RH), s = 2 warp and 2 warp + 1, RH = ceil(M / 2048) rounds each -- with
+ * a histogram row and a mask row per sub-block: 64 histogram rows (the second 32 lie over the chains'
+ * queue, which is empty during the passes and cleared again behind them), 64 mask rows = the whole
+ * output buffer.  The offsets come out absolute (first slot of sub-block s's elements of digit d), by all
+ * 1024 threads: 16 rows each. */
+constexpr int SG_SUB = 64;
+/* The level-1 pass only MARKS the positions with a rare first byte -- one bit per element of the level-1
+ * order, a round's vote is a word of the map -- and every thread takes its share of them behind the
+ * ranking (the k-th marked element goes to thread k mod 1024, found through a prefix sum over the words).
+ * Walked where they are met they sit in one or two warps' blocks (the order is by that byte) and hold up the
+ * whole CTA; and a call in the unrolled rounds keeps the compiler from overlapping them (the level-1 pass
+ * took 98 K cycles of a text segment's 330 K where levels 2 and 3 take 30 K each).  Map and prefix sums lie
+ * behind the 64 histogram rows, over the rest of the chains' queue. */
+constexpr size_t SG_OFF_RARE = SG_OFF_WH + SG_SUB * 256 * 2;
+static_assert(SG_OFF_RARE % 4 == 0 && SG_OFF_RARE + 4096 + 2048 <= SG_OFF_MISC, "rare map");
+#define SG_RAREMAP (reinterpret_cast<uint32_t *>(sg_smem + SG_OFF_RARE))
+#define SG_RAREPRE (reinterpret_cast<uint16_t *>(sg_smem + SG_OFF_RARE + 4096))
+
+template <int INBUF>
+__device__ __forceinline__ void sg_offsets64()
+{
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t d = (uint32_t)tid & 255u, part = (uint32_t)tid >> 8;
+	uint32_t *scr = reinterpret_cast<uint32_t *>(SG_P(INBUF ^ 1)); /* the mask rows: all zero again, free until the placement */
+	uint16_t *col = SG_WH + (16u * part) * 256u + d;
+	uint32_t pre[16];
+	uint32_t run = 0;
+#pragma unroll
+	for (int k = 0; k < 16; ++k) {
+		pre[k] = col[k * 256];
+	}
+#pragma unroll
+	for (int k = 0; k < 16; ++k) {
+		const uint32_t v = pre[k];
+		pre[k] = run;
+		run += v;
+	}
+	scr[part * 256u + d] = run;
+	__syncthreads();
+	if (tid < 256) {
+		const uint32_t p0 = scr[d], p1 = scr[256u + d], p2 = scr[512u + d], p3 = scr[768u + d];
+		const uint32_t tot = p0 + p1 + p2 + p3;
+		uint32_t inc = tot;
+#pragma unroll
+		for (int s = 1; s < 32; s <<= 1) {
+			const uint32_t o = __shfl_up_sync(FULL_MASK, inc, s);
+			if (lane >= s) {
+				inc += o;
+			}
+		}
+		if (lane == 31) {
+			SG_MI->wsum[warp] = inc;
+		}
+		asm volatile("bar.sync 1, 256;" ::: "memory"); /* the 8 warps of the digits only */
+		uint32_t before = 0;
+		for (int w = 0; w < warp; ++w) {
+			before += SG_MI->wsum[w];
+		}
+		const uint32_t start = before + inc - tot;
+		scr[1024u + d] = start;
+		scr[1280u + d] = start + p0;
+		scr[1536u + d] = start + p0 + p1;
+		scr[1792u + d] = start + p0 + p1 + p2;
+	}
+	__syncthreads();
+	const uint32_t base = scr[1024u + part * 256u + d];
+#pragma unroll
+	for (int k = 0; k < 16; ++k) {
+		col[k * 256] = (uint16_t)(base + pre[k]);
+	}
+	__syncthreads();
+}
+
+template <int K, bool LA32, int INBUF, bool PROF>
+__device__ __forceinline__ void sg_lsd_pass2(const SegCtx &c, unsigned long long *gp)
+{
+	/* measurement build: cycles of the pass's parts (ranking, offsets, placement) into the CTA's global counters 16 + 4 K .. */
+	unsigned long long pt0 = 0, wstart = 0;
+	if (PROF && threadIdx.x == 0) {
+		pt0 = clock64();
+	}
+	if (PROF && K == 1) {
+		wstart = clock64();
+	}
+#define SG_PLAP(k)                                 \
+	if (PROF && threadIdx.x == 0) {                \
+		const unsigned long long now = clock64();  \
+		gp[16 + 4 * K + (k)] += now - pt0;         \
+		pt0 = now;                                 \
+	}
+	const uint16_t *__restrict__ In = SG_P(INBUF);
+	uint16_t *__restrict__ Out = SG_P(INBUF ^ 1);
+	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t M = c.M;
+	const uint32_t RH = (M + 2047u) >> 11;     /* rounds per sub-block */
+	const uint32_t lt = (1u << lane) - 1u;
+	const uint32_t bit = 1u << lane;
+	uint32_t blk[2];
+	uint16_t *myh[2];
+	uint32_t *mym[2];
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		const uint32_t sub = 2u * (uint32_t)warp + h;
+		blk[h] = sub * 32u * RH;
+		myh[h] = SG_WH + sub * 256u;
+		mym[h] = reinterpret_cast<uint32_t *>(SG_P(INBUF ^ 1)) + sub * 256u;
+		reinterpret_cast<uint4 *>(myh[h])[lane] = make_uint4(0u, 0u, 0u, 0u);
+		reinterpret_cast<uint4 *>(mym[h])[lane] = make_uint4(0u, 0u, 0u, 0u);
+		reinterpret_cast<uint4 *>(mym[h])[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
+	}
+	__syncwarp();
+	uint32_t rk[2][6]; /* rank of my element of round r of sub-block h among its digit in the sub-block (< 512): 3 per word */
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+#pragma unroll
+		for (int k = 0; k < 6; ++k) {
+			rk[h][k] = 0;
+		}
+	}
+	uint32_t e_n[2] = {0u, 0u}, g_n[2] = {0u, 0u};
+	if (K >= 1) {
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+			if (blk[h] + lane < M) {
+				e_n[h] = In[blk[h] + lane];
+				g_n[h] = sg_gram(e_n[h]);
+			}
+		}
+	}
+#pragma unroll
+	for (int r = 0; r < 16; ++r) {
+		if ((uint32_t)r < RH) {
+			uint32_t d[2], vm[2], m0[2];
+			bool valid[2];
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const uint32_t i0 = blk[h] + 32u * r, i = i0 + lane;
+				valid[h] = i < M;
+				const uint32_t nvalid = M > i0 ? M - i0 : 0u; /* lanes of the round with an element */
+				vm[h] = nvalid >= 32u ? FULL_MASK : (1u << nvalid) - 1u;
+				if (K == 0) {
+					d[h] = valid[h] ? SG_XSB[SG_XS_OFF + i + 3] : 0u;
+				} else {
+					const uint32_t e = e_n[h], g = g_n[h];
+					if (i + 32u < M) {
+						e_n[h] = In[i + 32u];
+						g_n[h] = sg_gram(e_n[h]);
+					}
+					d[h] = (g >> (8 * (3 - K))) & 255u;
+					/* level K on the input order: the element t+1 places further on */
+					uint32_t ef, gf;
+					if (LA32) {
+						const int sl = (lane + (int)c.la) & 31;
+						const uint32_t e1 = __shfl_sync(FULL_MASK, e, sl), e2 = __shfl_sync(FULL_MASK, e_n[h], sl);
+						const uint32_t g1 = __shfl_sync(FULL_MASK, g, sl), g2 = __shfl_sync(FULL_MASK, g_n[h], sl);
+						const bool here = lane + (int)c.la < 32;
+						ef = here ? e1 : e2;
+						gf = here ? g1 : g2;
+					} else {
+						ef = 0;
+						gf = 0;
+						if (i + c.la < M) {
+							ef = In[i + c.la];
+							gf = sg_gram(ef);
+						}
+					}
+					const uint32_t q = e + 1u - (uint32_t)K;   /* searched position (relative to the segment) */
+					const bool subj = valid[h] && q < c.Bs;
+					const bool pass = subj && i + c.la < M && ((g ^ gf) >> (K == 0 ? 0 : 32 - 8 * K)) == 0u && ef - e <= c.D;
+					if (pass) {
+						SG_L8[q] = (uint8_t)K;
+					}
+					if (K == 1) {
+						/* a rare first byte: marked in the map (this round's word), walked behind the ranking */
+						const uint32_t rm = __ballot_sync(FULL_MASK, subj && !pass);
+						if (lane == 0) {
+							SG_RAREMAP[i0 >> 5] = rm;
+						}
+					}
+				}
+				/* the lanes with lane 0's digit know their peers from one vote */
+				const uint32_t d0 = __shfl_sync(FULL_MASK, d[h], 0);
+				m0[h] = __ballot_sync(FULL_MASK, valid[h] && d[h] == d0);
+			}
+			/* the others set their lane bits in the sub-block's mask row (shared-memory atomics: the row ends
+			 * up the same in whatever order they are served; MATCH.ANY would take 2 cycles per distinct value,
+			 * SM-wide: profiles/r2_ubench.json) and read the row back */
+			bool mine0[2];
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				mine0[h] = (m0[h] >> lane) & 1u;
+				if (m0[h] != vm[h] && valid[h] && !mine0[h]) {
+					atomicOr(&mym[h][d[h]], bit);
+				}
+			}
+			__syncwarp();
+			uint32_t peers[2], old[2];
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				peers[h] = mine0[h] ? m0[h] : (valid[h] ? mym[h][d[h]] : 0u);
+				old[h] = valid[h] ? (uint32_t)myh[h][d[h]] : 0u;
+			}
+			__syncwarp();
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				if (valid[h] && (peers[h] & lt) == 0u) {
+					if (!mine0[h]) {
+						mym[h][d[h]] = 0u;
+					}
+					myh[h][d[h]] = (uint16_t)(old[h] + __popc(peers[h]));
+				}
+				rk[h][r / 3] |= (old[h] + __popc(peers[h] & lt)) << (10 * (r % 3));
+			}
+			__syncwarp();
+		}
+	}
+	if (PROF && K == 1 && (threadIdx.x & 31) == 0) {
+		/* measurement build: how long each warp spent in the level-1 ranking: the slowest (24) and the sum (25) */
+		const unsigned long long dur = clock64() - wstart;
+		atomicMax(&gp[24], dur);
+		atomicAdd(&gp[25], dur);
+	}
+	__syncthreads();
+	if (K == 1) {
+		if (PROF && threadIdx.x == 0) {
+			const unsigned long long now = clock64();
+			gp[16 + 3] += now - pt0; /* K = 0's spare slot: the level-1 pass's ranking alone */
+			pt0 = now;
+		}
+		/* words of the map: one per thread (M <= 32768); rounds beyond M never wrote theirs */
+		const uint32_t nwords = 64u * RH;
+		const uint32_t word = (uint32_t)tid < nwords && 32u * (uint32_t)tid < M ? SG_RAREMAP[tid] : 0u;
+		uint32_t inc = __popc(word);
+#pragma unroll
+		for (int s = 1; s < 32; s <<= 1) {
+			const uint32_t o = __shfl_up_sync(FULL_MASK, inc, s);
+			if (lane >= s) {
+				inc += o;
+			}
+		}
+		if (lane == 31) {
+			SG_MI->wsum[warp] = inc;
+		}
+		__syncthreads();
+		uint32_t before = 0, nr = 0;
+		for (int w = 0; w < SG_WARPS; ++w) {
+			const uint32_t v = SG_MI->wsum[w];
+			before += w < warp ? v : 0u;
+			nr += v;
+		}
+		SG_RAREPRE[tid] = (uint16_t)(before + inc - __popc(word)); /* marked elements in front of my word */
+		__syncthreads();
+		if (PROF && threadIdx.x == 0) {
+			gp[16 + 7] += nr; /* K = 1's spare slot: marked positions */
+		}
+		for (uint32_t k = tid; k < nr; k += SG_THREADS) {
+			/* the k-th marked element: the last word with at most k marked elements in front of it, then the bit */
+			uint32_t lo = 0, hi = 1023;
+			while (lo < hi) {
+				const uint32_t mid = (lo + hi + 1u) >> 1;
+				if ((uint32_t)SG_RAREPRE[mid] <= k) {
+					lo = mid;
+				} else {
+					hi = mid - 1u;
+				}
+			}
+			uint32_t wbits = SG_RAREMAP[lo];
+			for (uint32_t skip = k - SG_RAREPRE[lo]; skip > 0u; --skip) {
+				wbits &= wbits - 1u;
+			}
+			const uint32_t i = 32u * lo + (uint32_t)(__ffs((int)wbits) - 1);
+			const uint32_t e = In[i];
+			SG_L8[e] = (uint8_t)sg_rare(INBUF, i, e, M, (uint32_t)c.t, c.D); /* (q = e + 1 - K = e) */
+		}
+	}
+	SG_PLAP(0)
+	sg_offsets64<INBUF>();
+	SG_PLAP(1)
+#pragma unroll
+	for (int r = 0; r < 16; ++r) {
+		if ((uint32_t)r < RH) {
+#pragma unroll
+			for (int h = 0; h < 2; ++h) {
+				const uint32_t i = blk[h] + 32u * r + lane;
+				if (i < M) {
+					const uint32_t rank = (rk[h][r / 3] >> (10 * (r % 3))) & 1023u;
+					const uint32_t e = K == 0 ? i : (uint32_t)In[i];
+					const uint32_t dd = SG_XSB[SG_XS_OFF + e + 3 - K]; /* the digit again: byte 3-K of the gram */
+					Out[myh[h][dd] + rank] = (uint16_t)e;
+				}
+			}
+		}
+	}
+	__syncthreads();
+	SG_PLAP(2)
+#undef SG_PLAP
+}
+
 /* ---- pushing a group, by size: the CTA's list (above SG_WAVE_MAX), the ring of the waves (above
  * SG_CHAIN_MAX; read behind CTA barriers: no flags, no fences), or the queue of the chains, whose
  * entries are taken by polling warps: the entry is published behind a fence, with its valid bit. */
@@ -1038,6 +1340,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 		}
 		SG_LAP(0)
 		/* levels 1 .. 4 */
+#ifdef X3_SEG_LSD1
 		sg_lsd_pass<0, true, 0>(c);  /* (reads the bytes in position order) -> buffer 1 */
 		SG_LAP(1)
 		if (c.la <= 32u) {
@@ -1050,6 +1353,24 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 			sg_lsd_pass<3, false, 1>(c);
 		}
 		SG_LAP(2)
+#else
+		sg_lsd_pass2<0, true, 0, PROF>(c, a.prof + blockIdx.x * 64);  /* (reads the bytes in position order) -> buffer 1 */
+		SG_LAP(1)
+		if (c.la <= 32u) {
+			sg_lsd_pass2<1, true, 1, PROF>(c, a.prof + blockIdx.x * 64);
+			sg_lsd_pass2<2, true, 0, PROF>(c, a.prof + blockIdx.x * 64);
+			sg_lsd_pass2<3, true, 1, PROF>(c, a.prof + blockIdx.x * 64);
+		} else {
+			sg_lsd_pass2<1, false, 1, PROF>(c, a.prof + blockIdx.x * 64);
+			sg_lsd_pass2<2, false, 0, PROF>(c, a.prof + blockIdx.x * 64);
+			sg_lsd_pass2<3, false, 1, PROF>(c, a.prof + blockIdx.x * 64);
+		}
+		/* the histogram rows of the second sub-blocks lay over the chains' queue: empty again */
+		for (uint32_t i = tid; i < SG_Q; i += SG_THREADS) {
+			SG_QENT[i] = 0u;
+		}
+		SG_LAP(2)
+#endif
 		sg_groups4(c, 0u);
 		SG_LAP(3)
 		/* big groups, whole CTA, one level at a time */
@@ -1134,7 +1455,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 	}
 	if (PROF && tid == 0) {
 		for (int k = 0; k < 16; ++k) {
-			a.prof[blockIdx.x * 16 + k] = pt[k];
+			a.prof[blockIdx.x * 64 + k] = pt[k];
 		}
 	}
 #undef SG_LAP
@@ -1203,8 +1524,8 @@ cudaError_t x3k_launch_seg(const X3SearchParams &prm, cudaStream_t stream, int *
 	const unsigned grid = nseg < (unsigned long long)sms ? (unsigned)nseg : (unsigned)sms;
 	const bool prof = getenv("X3_SEG_PROF") != nullptr; /* measurement knob: cycles per phase, printed */
 	if (prof) {
-		if ((e = cudaMalloc((void **)&a.prof, (size_t)grid * 128)) != cudaSuccess) return e;
-		if ((e = cudaMemsetAsync(a.prof, 0, (size_t)grid * 128, stream)) != cudaSuccess) return e;
+		if ((e = cudaMalloc((void **)&a.prof, (size_t)grid * 512)) != cudaSuccess) return e;
+		if ((e = cudaMemsetAsync(a.prof, 0, (size_t)grid * 512, stream)) != cudaSuccess) return e;
 	}
 	if (prof) {
 		x3_seg_kernel<true><<<grid, SG_THREADS, SG_SMEM + 128, stream>>>(a);
@@ -1215,16 +1536,19 @@ cudaError_t x3k_launch_seg(const X3SearchParams &prm, cudaStream_t stream, int *
 		*launches += 1;
 	}
 	if (prof) {
-		unsigned long long *h = (unsigned long long *)malloc((size_t)grid * 128);
+		unsigned long long *h = (unsigned long long *)malloc((size_t)grid * 512);
 		if (h != nullptr && cudaStreamSynchronize(stream) == cudaSuccess &&
-		    cudaMemcpy(h, a.prof, (size_t)grid * 128, cudaMemcpyDeviceToHost) == cudaSuccess) {
+		    cudaMemcpy(h, a.prof, (size_t)grid * 512, cudaMemcpyDeviceToHost) == cudaSuccess) {
 			static const char *name[8] = {"load", "pass 0", "passes 1-3", "groups4", "big groups", "waves", "chains", "store"};
-			double tot[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
+			double tot[32], mx = 0;
+			for (int k = 0; k < 32; ++k) {
+				tot[k] = 0;
+			}
 			for (unsigned b = 0; b < grid; ++b) {
 				double cta = 0;
-				for (int k = 0; k < 16; ++k) {
-					tot[k] += (double)h[b * 16 + k];
-					cta += k < 8 ? (double)h[b * 16 + k] : 0;
+				for (int k = 0; k < 32; ++k) {
+					tot[k] += (double)h[b * 64 + k];
+					cta += k < 8 ? (double)h[b * 64 + k] : 0;
 				}
 				if (cta > mx) mx = cta;
 			}
@@ -1235,6 +1559,18 @@ cudaError_t x3k_launch_seg(const X3SearchParams &prm, cudaStream_t stream, int *
 			fprintf(stderr, ";  %.1f waves per segment, cycles per wave: form %.0f  (1) %.0f  (2) %.0f  (3) %.0f\n",
 			        tot[15] / (tot[8] > 0 ? tot[8] : 1), tot[10] / (tot[15] > 0 ? tot[15] : 1), tot[11] / (tot[15] > 0 ? tot[15] : 1),
 			        tot[12] / (tot[15] > 0 ? tot[15] : 1), tot[13] / (tot[15] > 0 ? tot[15] : 1));
+			fprintf(stderr, "x3_seg_kernel: passes, cycles per segment (ranking / offsets / placement):");
+			for (int K = 0; K < 4; ++K) {
+				fprintf(stderr, "  K=%d %.0f / %.0f / %.0f", K, tot[16 + 4 * K] / (tot[8] > 0 ? tot[8] : 1),
+				        tot[17 + 4 * K] / (tot[8] > 0 ? tot[8] : 1), tot[18 + 4 * K] / (tot[8] > 0 ? tot[8] : 1));
+			}
+			/* (in this build warp 0 -- the one that keeps the counters -- takes 3x as long over the level-1 ranking as the
+			 * other 31, which the production build does not show: its whole segment takes less than this build's passes;
+			 * read the per-warp mean for that pass) */
+			fprintf(stderr, ";  level-1 ranking per warp: mean %.0f, slowest warp of a CTA %.0f;",
+			        tot[25] / 32.0 / (tot[8] > 0 ? tot[8] : 1), tot[24] / grid);
+			fprintf(stderr, "  as thread 0 saw it %.0f, %.0f rare positions marked per segment\n", tot[19] / (tot[8] > 0 ? tot[8] : 1),
+			        tot[23] / (tot[8] > 0 ? tot[8] : 1));
 		}
 		free(h);
 		cudaFree(a.prof);

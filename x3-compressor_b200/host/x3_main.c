@@ -157,12 +157,14 @@ int main(int argc, char *argv[])
 
 		x3_backend_set_dict(x3_codec_dict_find, x3_codec_dict_len);
 		const double t0 = now_s();
-		x3_search_prepare(iptr, isize); /* GPU: every position at once */
+		x3_search_prepare(iptr, isize); /* GPU: every position at once; the table lands piece by piece from the left */
 		const double t1 = now_s();
-		void *optr = x3_compress(codec, iptr, isize, find_best_match, &asize);
+		void *optr = x3_compress(codec, iptr, isize, find_best_match, &asize); /* starts on the first piece */
 		const double t2 = now_s();
+		x3_search_wait();
 		fprintf(stderr, "elapsed time: %f\n", (float)(t2 - t0));
-		fprintf(stderr, "of which match search (GPU, incl. transfers): %f\n", (float)(t1 - t0));
+		fprintf(stderr, "of which match search (GPU, incl. transfers): %f\n", (float)(x3_search_landed_ms() * 1e-3));
+		fprintf(stderr, "of which before the sequential pass could start: %f\n", (float)(t1 - t0));
 		fprintf(stderr, "of which CUDA start-up (driver + first context, once per process): %f\n",
 		        (float)(x3_search_startup_ms() * 1e-3));
 		x3_search_release();
