@@ -72,6 +72,18 @@ def shard_cuts(n: int, world: int, align: int = 4096):
     return cuts
 
 
+def part_pieces(n: int, world: int, piece: int):
+    """Position ranges of ONE input dealt out to `world` ranks in turn, `piece` positions each (the partition
+    x3s_search_host_part / x3s_search_device_part use: x3_search_api.cu, piece = x3s_part_positions(W)): rank r takes
+    the pieces r, r + world, ...  Returns one list of (first position, length) per rank."""
+    out = [[] for _ in range(world)]
+    if piece <= 0:
+        return out
+    for q in range((n + piece - 1) // piece):
+        out[q % world].append((q * piece, min(piece, n - q * piece)))
+    return out
+
+
 # ----------------------------------------------------------------------------------------
 # clocks sampling (B200_PROFILING.md "clocks DURING the timed region")
 # ----------------------------------------------------------------------------------------
@@ -353,28 +365,36 @@ def run_b200(args):
 
     golden = json.loads(TABLES.read_text()) if TABLES.exists() else {}
 
+    PIECE = int(L.x3s_part_positions(W_BYTES))
+
     def legs(name, X, T, nn, steps, warm, flush, check_sha):
         """device-resident leg and host-to-host leg of one input split over the ranks"""
-        cuts = shard_cuts(nn, world)
-        a0, a1 = cuts[rank], cuts[rank + 1]
-        np_r = a1 - a0
-        have = min(np_r + W_BYTES, nn + W_BYTES - a0)
-        need = pkg.required_bytes(np_r, W_BYTES)
-        # page-lock this rank's ranges of the two shared buffers where they lie
+        if world == 1:
+            mine = [(0, nn)]
+        else:
+            mine = part_pieces(nn, world, PIECE)[rank]
+        np_r = sum(ln for (_, ln) in mine)
+        need = pkg.required_bytes(nn, W_BYTES)
+        # page-lock the two shared buffers where they lie (every rank reads its pieces and the windows behind them
+        # out of the one input and writes its pieces of the one table)
         reg = []
-        if np_r > 0:
-            for (p, b) in ((X.ptr + a0, have), (T.ptr + a0, np_r)):
-                if L.x3s_host_register(p, b) == 0:
-                    reg.append(p)
-        # (1) shard resident in HBM, CUDA events around the search
+        for (p, b) in ((X.ptr, nn + W_BYTES), (T.ptr, nn)):
+            if L.x3s_host_register(p, b) == 0:
+                reg.append(p)
+        # (1) input resident in HBM, CUDA events around the search of this rank's pieces (ONE launch)
         d_x = torch.zeros(max(need, 16), dtype=torch.uint8, device=dev)
-        d_x[:have].copy_(torch.from_numpy(X.arr[a0:a0 + have]))
-        d_l = torch.empty(max(np_r, 1), dtype=torch.uint8, device=dev)
+        d_x[:nn + W_BYTES].copy_(torch.from_numpy(X.arr[:nn + W_BYTES]))
+        d_l = torch.zeros(max(nn, 1), dtype=torch.uint8, device=dev)
         stream = torch.cuda.current_stream()
 
         def step_device():
-            if np_r > 0:
-                pkg.search_device(local, d_x.data_ptr(), np_r, W_BYTES, T_COUNT, d_l.data_ptr(), None, stream.cuda_stream)
+            if world == 1:
+                pkg.search_device(local, d_x.data_ptr(), nn, W_BYTES, T_COUNT, d_l.data_ptr(), None, stream.cuda_stream)
+            else:
+                rc = L.x3s_search_device_part(local, d_x.data_ptr(), nn, W_BYTES, T_COUNT, d_l.data_ptr(),
+                                              stream.cuda_stream, rank, world)
+                if rc != 0:
+                    raise SystemExit("x3s_search_device_part: " + L.x3s_last_error().decode())
 
         for _ in range(warm):
             step_device()
@@ -388,22 +408,23 @@ def run_b200(args):
             e1.record(stream)
         barrier()
         dev_ms = sum(e0.elapsed_time(e1) for (e0, e1) in ev)
-        lstar_dev = d_l[:np_r].cpu().numpy()
+        lstar_dev = d_l.cpu().numpy()
         # (2) host memory to host memory through the C ABI
         tm = pkg.Timing()
 
         def step_host():
-            if np_r == 0:
-                return 0
-            rc = L.x3s_search_host(X.ptr + a0, np_r, W_BYTES, T_COUNT, 1, pkg.KERNEL_DEFAULT, T.ptr + a0, None, C.byref(tm))
+            if world == 1:
+                rc = L.x3s_search_host(X.ptr, nn, W_BYTES, T_COUNT, 1, pkg.KERNEL_DEFAULT, T.ptr, None, C.byref(tm))
+            else:
+                rc = L.x3s_search_host_part(X.ptr, nn, W_BYTES, T_COUNT, T.ptr, C.byref(tm), rank, world)
             if rc != 0:
-                raise SystemExit("x3s_search_host: " + L.x3s_last_error().decode())
+                raise SystemExit("x3s_search_host(_part): " + L.x3s_last_error().decode())
             return tm.launches
 
         for _ in range(warm):
             step_host()
         barrier()
-        # the whole table, assembled from every rank's shard in the one host buffer, against the
+        # the whole table, assembled from every rank's pieces in the one host buffer, against the
         # oracle-derived hash of the 1-GPU table -- before anything is timed
         sha = None
         if rank == 0:
@@ -411,8 +432,9 @@ def run_b200(args):
             want = golden.get(name, {}).get("lstar_sha256")
             if check_sha and want is not None and sha != want:
                 raise SystemExit(f"bench.py: {name} table over {world} GPU(s) has sha256 {sha}, expected {want}")
-        if not np.array_equal(T.arr[a0:a1], lstar_dev):
-            raise SystemExit(f"bench.py: rank {rank}: device-resident and host-buffer runs disagree on {name}")
+        for (p0, ln) in mine:
+            if not np.array_equal(T.arr[p0:p0 + ln], lstar_dev[p0:p0 + ln]):
+                raise SystemExit(f"bench.py: rank {rank}: device-resident and host-buffer runs disagree on {name} at piece {p0}")
         barrier()
         t0 = time.perf_counter()
         launches = 0
@@ -425,19 +447,21 @@ def run_b200(args):
             L.x3s_host_unregister(p)
         per_rank = [dev_ms / steps]
         if dist is not None:
-            mine = torch.tensor([dev_ms / steps, e2e_s / steps * 1e3, float(launches)], dtype=torch.float64, device=dev)
-            every = [torch.zeros_like(mine) for _ in range(world)]
-            dist.all_gather(every, mine)
+            mine_t = torch.tensor([dev_ms / steps, e2e_s / steps * 1e3, float(launches)], dtype=torch.float64, device=dev)
+            every = [torch.zeros_like(mine_t) for _ in range(world)]
+            dist.all_gather(every, mine_t)
             per_rank = [float(v[0]) for v in every]
             dev_ms = max(float(v[0]) for v in every) * steps
             e2e_s = max(float(v[1]) for v in every) * steps / 1e3
             launches = int(sum(float(v[2]) for v in every))
         del d_x, d_l
+        allp = [(0, nn)] if world == 1 else [pc for r in part_pieces(nn, world, PIECE) for pc in r]
         return {"ms_per_step": dev_ms / steps, "value": nn / (dev_ms / steps * 1e-3) / 1e6,
                 "e2e_ms_per_step": e2e_s / steps * 1e3, "e2e_value": nn * steps / e2e_s / 1e6,
-                "h2d": int(sum(min(cuts[r + 1] - cuts[r] + W_BYTES, nn + W_BYTES - cuts[r]) for r in range(world))),
+                "h2d": int(sum(min(ln + W_BYTES + (128 if world > 1 else 0), nn + W_BYTES - p0) for (p0, ln) in allp)),
                 "d2h": int(nn), "launches": launches, "per_rank_ms": per_rank, "sha256": sha,
-                "registered": len(reg) == 2, "positions_rank0": cuts[1] - cuts[0]}
+                "registered": len(reg) == 2, "positions_rank0": np_r if rank == 0 else None, "piece": PIECE,
+                "positions_per_rank": [sum(ln for (_, ln) in r) for r in part_pieces(nn, world, PIECE)] if world > 1 else [nn]}
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     steps, warm = args.steps, max(3, args.warmup)
@@ -519,10 +543,13 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD_TEXT,
                    "window_bytes": W_BYTES, "max_match_count": T_COUNT, "positions": n,
-                   "positions_per_gpu": [shard_cuts(n, world)[r + 1] - shard_cuts(n, world)[r] for r in range(world)],
+                   "positions_per_gpu": main["positions_per_rank"],
+                   "piece_positions": PIECE if world > 1 else None,
                    "l2": "flushed between timed steps (256 MiB fill, outside the event pairs)",
-                   "sharding": "contiguous position ranges of ONE input with trailing window halo, no collective; "
-                               "shards go straight from each GPU to one shared host table",
+                   "sharding": "ONE input; contiguous position ranges (pieces of piece_positions positions, each read with its "
+                               "trailing window halo) dealt out to the ranks in turn, no collective; every rank's pieces go "
+                               "straight from its GPU to one shared host table" if world > 1 else
+                               "one GPU: the whole input",
                    "table_sha256": main["sha256"],
                    "table_sha256_expected": golden.get("C5", {}).get("lstar_sha256"),
                    "table_checked_before_timing": True,
@@ -531,8 +558,8 @@ def run_b200(args):
                    "bound_cpus": near if near is None else [near[0], near[-1], len(near)]},
         "e2e": {"value": main["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": main["h2d"],
                 "d2h_bytes_per_step": main["d2h"], "ms_per_step": main["e2e_ms_per_step"],
-                "api": "x3s_search_host (include/x3_search.h) on each rank's range of the shared host buffers "
-                       "(page-locked in place with x3s_host_register)",
+                "api": ("x3s_search_host_part" if world > 1 else "x3s_search_host") + " (include/x3_search.h) on the shared host "
+                       "buffers (page-locked in place with x3s_host_register)",
                 "plugin": plugin},
         # timed regions only: the host leg's launches (a shard goes piece by piece) + the device leg's
         "gpu_launches": main["launches"] + device_launches_per_search * steps * world,
@@ -556,13 +583,13 @@ def roofline_seg(main, n, world, peak, peak_src):
     (production mode): 1 B read + 1 B written per position + the shard's trailing halo.
     The kernel's own HBM traffic is that minimum times (B + D) / B for the re-read halo of every segment
     (profiles/traffic.json, ncu); everything else happens in shared memory, which is what bounds it."""
-    cuts = shard_cuts(n, world)
-    np0 = cuts[1] - cuts[0]
+    np0 = main["positions_per_rank"][0]
+    npieces0 = 1 if world == 1 else -(-np0 // max(1, main.get("piece", np0)))
     launch_ms = main["per_rank_ms"][0]
-    abytes = 2.0 * np0 + (W_BYTES - 2)
+    abytes = 2.0 * np0 + npieces0 * (W_BYTES - 2)     # rank 0's positions: 1 B in, 1 B out, + the window behind each piece
     achieved = abytes / (launch_ms * 1e-3) / 1e9
     ms_per_step = main["ms_per_step"]
-    algo_bytes = 2 * n + world * (W_BYTES - 2)
+    algo_bytes = 2 * n + (1 if world == 1 else -(-n // max(1, main.get("piece", n)))) * (W_BYTES - 2)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "kernel": "x3_seg_kernel",
                 "algorithmic_bytes_per_launch": abytes, "launches_per_search": 1, "avg_launch_ms": launch_ms,

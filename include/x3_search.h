@@ -113,6 +113,23 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
                     void *lstar, void *H, x3s_timing *timing);
 
 /*
+ * ONE input searched by several processes / GPUs (one rank per GPU under torchrun, say): the positions
+ * [0, n) are cut into pieces of x3s_part_positions(W) positions (a whole number of the segment search's
+ * segments; 0 when the window does not fit the segment search), and part `part` of `parts` takes the pieces
+ * part, part + parts, ...: contiguous position ranges, each read with the window behind it, dealt out in
+ * turn so that every part sees every region of the input.  x, lstar (host) and d_x, d_lstar (device) are
+ * the buffers of the WHOLE input in both calls: n + W readable bytes (x3s_required_bytes(n, W) on the
+ * device) and n table bytes, of which a part reads and writes its own pieces only (plus, reading, the W
+ * bytes behind each).  The parts may run in different processes over shared host buffers.  Lstar only,
+ * segment search only (X3S_ERR_UNSUPP otherwise).  x3s_search_host_part runs on the first device of
+ * x3s_set_devices() (default device 0).
+ */
+size_t x3s_part_positions(size_t W);
+int x3s_search_device_part(int device, const void *d_x, size_t n_positions, size_t W, int t, void *d_lstar,
+                           void *stream, int part, int parts);
+int x3s_search_host_part(const void *x, size_t n, size_t W, int t, void *lstar, x3s_timing *timing, int part, int parts);
+
+/*
  * x3s_search_host() for a consumer that reads the table from left to right while it is still being
  * made (the reference's compress() visits positions in increasing order, x3.c:379): the call itself
  * returns when the whole table has landed, but while it runs -- call it from a thread of its own --

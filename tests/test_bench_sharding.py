@@ -32,6 +32,25 @@ def test_shard_cuts_cover_align_and_match_the_package():
             assert [(cuts[r], cuts[r + 1]) for r in range(world)] == pkg.shard_ranges(n, world)
 
 
+def test_part_pieces_cover_the_input_in_turn():
+    """the partition of the N > 1 legs (x3s_search_host_part / x3s_search_device_part): pieces dealt out in turn"""
+    for n in (0, 1, 4095, 4096, 10_192_446, 211_938_580):
+        for world in (1, 2, 3, 4, 8):
+            for piece in (4096, 24592 * 170):
+                parts = bench.part_pieces(n, world, piece)
+                assert len(parts) == world
+                flat = sorted(pc for r in parts for pc in r)
+                assert sum(ln for (_, ln) in flat) == n
+                pos = 0
+                for (p0, ln) in flat:                     # contiguous, no overlap, no gap
+                    assert p0 == pos and 0 < ln <= piece and p0 % piece == 0
+                    pos += ln
+                for r, lst in enumerate(parts):           # rank r: pieces r, r + world, ...
+                    assert all((p0 // piece) % world == r for (p0, _) in lst)
+                sizes = [sum(ln for (_, ln) in r) for r in parts]
+                assert max(sizes) - min(sizes) <= piece
+
+
 def test_parallel_corpus_generation_is_byte_identical():
     corpus = g.load_submodule("corpus")
     a = corpus.silesia_mix(2_000_000, 5)
@@ -55,7 +74,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, n, W, t, tag):
+def _worker(rank, world, port, n, W, t, tag, piece):
     sys.path.insert(0, str(ROOT / "tests"))
     import oracle_lib as ol
     corpus = g.load_submodule("corpus")
@@ -77,10 +96,14 @@ def _worker(rank, world, port, n, W, t, tag):
     if rank == 0:
         X.unlink()
         T.unlink()
-    cuts = bench.shard_cuts(n, world)
-    a0, a1 = cuts[rank], cuts[rank + 1]
-    if a1 > a0:
-        # what x3s_search_host(X + a0, a1 - a0, W, ...) sees: the range followed by W bytes of halo
+    if piece == 0:
+        cuts = bench.shard_cuts(n, world)
+        mine = [(cuts[rank], cuts[rank + 1] - cuts[rank])] if cuts[rank + 1] > cuts[rank] else []
+    else:
+        mine = bench.part_pieces(n, world, piece)[rank]
+    for (a0, ln) in mine:
+        # what a search of the range sees: its positions followed by W bytes of halo
+        a1 = a0 + ln
         sl = np.array(X.arr[a0: a1 + W])
         _, ls = ol.table(sl[: a1 - a0 + W], W, t, p0=0, p1=a1 - a0)
         T.arr[a0:a1] = ls
@@ -95,7 +118,16 @@ def _worker(rank, world, port, n, W, t, tag):
 
 def test_one_input_sharded_into_one_shared_table_world2_gloo():
     tag = f"pytest_{os.getpid()}"
-    mp.spawn(_worker, args=(2, _free_port(), 40_000, 8192, 15, tag), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), 40_000, 8192, 15, tag, 0), nprocs=2, join=True)
+    res = Path(f"/tmp/{tag}.ok")
+    assert res.read_text() == "1"
+    res.unlink()
+
+
+def test_one_input_dealt_out_in_pieces_into_one_shared_table_world2_gloo():
+    """the N > 1 partition of bench.py: pieces in turn, each read with the window behind it"""
+    tag = f"pytest_pc_{os.getpid()}"
+    mp.spawn(_worker, args=(2, _free_port(), 40_000, 8192, 15, tag, 6000), nprocs=2, join=True)
     res = Path(f"/tmp/{tag}.ok")
     assert res.read_text() == "1"
     res.unlink()

@@ -181,3 +181,50 @@ def test_backend_prepare_returns_before_the_table_and_find_best_match_waits(pkg,
     finally:
         L.x3_search_release()
         L.x3_backend_set_dict(None, None)
+
+
+@pytest.mark.parametrize("parts", [1, 2, 3, 8])
+def test_pieces_dealt_out_in_turn_assemble_the_table(pkg, corpus, monkeypatch, parts):
+    """x3s_search_host_part / x3s_search_device_part: ONE input, part p takes the pieces p, p + parts, ...; all parts
+    together (here one after the other on one GPU, under torchrun one rank each) give the table of the plain search"""
+    import ctypes as C
+    import torch
+
+    monkeypatch.setenv("X3_PART_PIECE_KB", "200")
+    data = _inputs(corpus, "C5", 2_500_000)
+    n, W, t = len(data), 8192, 15
+    want, _, _ = pkg.search_host(data, W=W, t=t, variant=pkg.KERNEL_SEG)
+    _, ls_ref = ol.table(data, W, t)
+    assert np.array_equal(want, ls_ref)
+    L = pkg.lib()
+    piece = int(L.x3s_part_positions(W))
+    assert piece > 0 and piece % 16 == 0 and (n + piece - 1) // piece >= 8
+    x = pkg.padded(data, W)
+    out = np.full(n, 255, dtype=np.uint8)
+    tm = pkg.Timing()
+    launches = 0
+    for p in range(parts):
+        assert L.x3s_search_host_part(x.ctypes.data, n, W, t, out.ctypes.data, C.byref(tm), p, parts) == 0, L.x3s_last_error()
+        launches += tm.launches
+        # only this part's pieces (and those of the parts before) are written so far
+        done = np.zeros(n, dtype=bool)
+        for q in range((n + piece - 1) // piece):
+            if q % parts <= p:
+                done[q * piece:(q + 1) * piece] = True
+        assert np.array_equal(out[done], want[done]) and (out[~done] == 255).all()
+    assert np.array_equal(out, want)
+    assert launches == (n + piece - 1) // piece
+    # device resident: the whole input in HBM, one launch per part
+    dev = torch.device("cuda", 0)
+    d_x = torch.zeros(pkg.required_bytes(n, W), dtype=torch.uint8, device=dev)
+    d_x[:n].copy_(torch.from_numpy(data))
+    d_l = torch.full((n,), 255, dtype=torch.uint8, device=dev)
+    s = torch.cuda.current_stream()
+    for p in range(parts):
+        assert L.x3s_search_device_part(0, d_x.data_ptr(), n, W, t, d_l.data_ptr(), s.cuda_stream, p, parts) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_l.cpu().numpy(), want)
+    for bad in ((3, 3), (-1, 2), (0, 0)):
+        assert L.x3s_search_host_part(x.ctypes.data, n, W, t, out.ctypes.data, None, bad[0], bad[1]) == pkg.X3S_ERR_ARG
+    assert L.x3s_part_positions(1 << 20) == 0
+    assert L.x3s_search_host_part(x.ctypes.data, n, 1 << 20, t, out.ctypes.data, None, 0, 1) == pkg.X3S_ERR_UNSUPP

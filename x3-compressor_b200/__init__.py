@@ -74,6 +74,14 @@ def lib() -> C.CDLL:
     L.x3s_host_register.argtypes = [C.c_void_p, C.c_size_t]
     L.x3s_host_unregister.restype = C.c_int
     L.x3s_host_unregister.argtypes = [C.c_void_p]
+    L.x3s_part_positions.restype = C.c_size_t
+    L.x3s_part_positions.argtypes = [C.c_size_t]
+    L.x3s_search_device_part.restype = C.c_int
+    L.x3s_search_device_part.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_int]
+    L.x3s_search_host_part.restype = C.c_int
+    L.x3s_search_host_part.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(Timing),
+                                       C.c_int, C.c_int]
     L.x3s_default_kernel.restype = C.c_int
     L.x3s_default_kernel.argtypes = [C.c_size_t, C.c_int, C.c_int]
     L.x3s_rank_profile.restype = C.c_int

@@ -268,6 +268,207 @@ size_t x3s_required_bytes(size_t n_positions, size_t W)
 	return x3k_required_bytes(n_positions, W);
 }
 
+/* ---- ONE input over several processes / GPUs, piece by piece in turn ------------------------------
+ * part p of `parts` takes the pieces p, p + parts, ... of x3s_part_positions(W) positions each: contiguous
+ * position ranges, each read together with the window behind it (backend.c:60-74 reads p .. p+W-2), dealt
+ * out in turn so that every part gets its share of every region of the input (the cost of a position
+ * varies 3x between the members of a mixed corpus: two contiguous halves of C5 take 7.9 and 4.4 ms). */
+static size_t part_segments(size_t W)
+{
+	const uint32_t D = distances(W);
+	if (D < 1 || D > x3k_seg_max_distances()) {
+		return 0;
+	}
+	const size_t B = x3k_seg_positions(D);
+	const char *pm = getenv("X3_PART_PIECE_KB"); /* tuning/testing knob; never changes results */
+	const size_t kb = pm != nullptr && atoi(pm) >= 1 ? (size_t)atoi(pm) : 4096;
+	const size_t segs = (kb << 10) / B;
+	return segs < 1 ? 1 : segs;
+}
+
+size_t x3s_part_positions(size_t W)
+{
+	const uint32_t D = distances(W);
+	return D >= 1 && D <= x3k_seg_max_distances() ? part_segments(W) * (size_t)x3k_seg_positions(D) : 0;
+}
+
+int x3s_search_device_part(int device, const void *d_x, size_t n_positions, size_t W, int t, void *d_lstar,
+                           void *stream, int part, int parts)
+{
+	int rc = check_params(W, t, nullptr, X3S_KERNEL_SEG);
+	if (rc != X3S_OK) {
+		return rc;
+	}
+	if (d_x == nullptr || d_lstar == nullptr || ((uintptr_t)d_x & 15) != 0) {
+		return fail(X3S_ERR_ARG, "null or misaligned device pointer");
+	}
+	if (parts < 1 || part < 0 || part >= parts) {
+		return fail(X3S_ERR_ARG, "part %d of %d", part, parts);
+	}
+	CU_TRY(cudaSetDevice(device));
+	rc = ensure_kernel_init(device);
+	if (rc != X3S_OK) {
+		return rc;
+	}
+	Scratch &sc = g_scratch[device];
+	X3SearchParams prm;
+	prm.x = (const uint8_t *)d_x;
+	prm.n = n_positions;
+	prm.D = distances(W);
+	prm.t = t;
+	prm.lstar = (uint8_t *)d_lstar;
+	prm.H = nullptr;
+	prm.tile_counter = sc.counter;
+	prm.deep = nullptr;
+	prm.ntiles = 0;
+	prm.kd = 0;
+	prm.part = (uint32_t)part;
+	prm.parts = (uint32_t)parts;
+	prm.piece_segments = (uint32_t)part_segments(W);
+	cudaStream_t st = (cudaStream_t)stream;
+	CU_TRY(cudaStreamWaitEvent(st, sc.last, 0));
+	CU_TRY(x3k_launch_seg(prm, st, nullptr));
+	CU_TRY(cudaEventRecord(sc.last, st));
+	return X3S_OK;
+}
+
+int x3s_search_host_part(const void *x, size_t n, size_t W, int t, void *lstar, x3s_timing *timing, int part, int parts)
+{
+	const auto wall0 = std::chrono::steady_clock::now();
+	int rc = check_params(W, t, nullptr, X3S_KERNEL_SEG);
+	if (rc != X3S_OK) {
+		return rc;
+	}
+	if (x == nullptr || (lstar == nullptr && n > 0)) {
+		return fail(X3S_ERR_ARG, "null host pointer");
+	}
+	if (parts < 1 || part < 0 || part >= parts) {
+		return fail(X3S_ERR_ARG, "part %d of %d", part, parts);
+	}
+	const int nvis = x3s_device_count();
+	if (nvis <= 0) {
+		return fail(X3S_ERR_CUDA, "no CUDA device visible (the search has no CPU fallback)");
+	}
+	std::lock_guard<std::mutex> lock(g_mu);
+	const int dev = g_ids.empty() ? 0 : g_ids[0];
+	if ((int)g_dev.size() < nvis) {
+		g_dev.resize(nvis);
+	}
+	DevState &ds = g_dev[dev];
+	CU_TRY(cudaSetDevice(dev));
+	if ((rc = ensure_kernel_init(dev)) != X3S_OK) {
+		return rc;
+	}
+	if (!ds.inited) {
+		CU_TRY(cudaStreamCreateWithFlags(&ds.stream, cudaStreamNonBlocking));
+		for (int i = 0; i < 4; ++i) {
+			CU_TRY(cudaEventCreate(&ds.ev[i]));
+		}
+		ds.inited = true;
+	}
+	if (!ds.pinited) {
+		for (int p = 0; p < X3S_MAX_PIECES; ++p) {
+			CU_TRY(cudaStreamCreateWithFlags(&ds.ps[p], cudaStreamNonBlocking));
+			for (int k = 0; k < 2; ++k) {
+				CU_TRY(cudaEventCreate(&ds.pev[p][k]));
+			}
+		}
+		ds.pinited = true;
+	}
+	/* the device holds the input's layout whole (this part's pieces and the windows behind them land at
+	 * their own offsets; what other parts search stays untouched), zeroed behind the reference's padding */
+	const size_t need = x3k_required_bytes(n, W), total = n + W;
+	if (need > ds.cap_x) {
+		if ((rc = grow(&ds.d_x, &ds.cap_x, need)) != X3S_OK) {
+			return rc;
+		}
+	}
+	if ((rc = grow(&ds.d_l, &ds.cap_l, n > 0 ? n : 1)) != X3S_OK) {
+		return rc;
+	}
+	const size_t PS = x3s_part_positions(W);
+	const size_t npieces = PS > 0 ? (n + PS - 1) / PS : 0;
+	std::vector<size_t> mine;
+	for (size_t q = (size_t)part; q < npieces; q += (size_t)parts) {
+		mine.push_back(q);
+	}
+	x3s_timing tm;
+	memset(&tm, 0, sizeof(tm));
+	tm.gpus = 1;
+	if (!mine.empty()) {
+		while (ds.upev.size() < 3 * mine.size()) {
+			cudaEvent_t ev = nullptr;
+			CU_TRY(cudaEventCreate(&ev));
+			ds.upev.push_back(ev);
+		}
+		Scratch &sc = g_scratch[dev];
+		cudaStream_t U = ds.stream, K[2] = {ds.ps[0], ds.ps[1]}, Cc = ds.ps[2];
+		const size_t m = mine.size();
+		CU_TRY(cudaStreamWaitEvent(U, sc.last, 0));
+		CU_TRY(cudaEventRecord(ds.ev[0], U));
+		for (int k = 0; k < 2; ++k) {
+			CU_TRY(cudaStreamWaitEvent(K[k], ds.ev[0], 0));
+		}
+		CU_TRY(cudaStreamWaitEvent(Cc, ds.ev[0], 0));
+		if (need > total) {
+			CU_TRY(cudaMemsetAsync(ds.d_x + total, 0, need - total, U));
+		}
+		const uint32_t D = distances(W);
+		for (size_t j = 0; j < m; ++j) {
+			const size_t p0 = mine[j] * PS, len = n - p0 < PS ? n - p0 : PS;
+			size_t b1 = p0 + len + W + 128; /* the piece, the window behind it, the kernel's slack */
+			if (b1 > total) b1 = total;
+			CU_TRY(cudaMemcpyAsync(ds.d_x + p0, (const uint8_t *)x + p0, b1 - p0, cudaMemcpyHostToDevice, U));
+			CU_TRY(cudaEventRecord(ds.upev[j], U));
+			/* searches on two streams in turn (a counter each): the last segments of a piece share the GPU with
+			 * the first of the next */
+			cudaStream_t Ks = K[j & 1];
+			CU_TRY(cudaStreamWaitEvent(Ks, ds.upev[j], 0));
+			X3SearchParams prm;
+			prm.x = ds.d_x + p0;
+			prm.n = len;
+			prm.D = D;
+			prm.t = t;
+			prm.lstar = ds.d_l + p0;
+			prm.H = nullptr;
+			prm.tile_counter = sc.counter + 16 * (1 + (j & 1));
+			prm.deep = nullptr;
+			prm.ntiles = 0;
+			prm.kd = 0;
+			CU_TRY(x3k_launch_seg(prm, Ks, &tm.launches));
+			CU_TRY(cudaEventRecord(ds.upev[m + j], Ks));
+			CU_TRY(cudaStreamWaitEvent(Cc, ds.upev[m + j], 0));
+			CU_TRY(cudaMemcpyAsync((uint8_t *)lstar + p0, ds.d_l + p0, len, cudaMemcpyDeviceToHost, Cc));
+			CU_TRY(cudaEventRecord(ds.upev[2 * m + j], Cc));
+		}
+		CU_TRY(cudaEventRecord(ds.ev[1], U));
+		for (int k = 0; k < 2; ++k) {
+			CU_TRY(cudaEventRecord(ds.pev[k][0], K[k]));
+			CU_TRY(cudaStreamWaitEvent(U, ds.pev[k][0], 0));
+		}
+		CU_TRY(cudaEventRecord(ds.pev[2][1], Cc));
+		CU_TRY(cudaStreamWaitEvent(U, ds.pev[2][1], 0));
+		CU_TRY(cudaEventRecord(ds.ev[3], U));
+		CU_TRY(cudaEventRecord(sc.last, U));
+		CU_TRY(cudaStreamSynchronize(U));
+		float up = 0.f, all = 0.f, kend = 0.f, ms = 0.f;
+		CU_TRY(cudaEventElapsedTime(&up, ds.ev[0], ds.upev[0]));
+		CU_TRY(cudaEventElapsedTime(&all, ds.ev[0], ds.ev[3]));
+		for (int k = 0; k < 2; ++k) {
+			CU_TRY(cudaEventElapsedTime(&ms, ds.ev[0], ds.pev[k][0]));
+			if (ms > kend) kend = ms;
+		}
+		tm.h2d_ms = up;
+		tm.kernel_ms = kend - up;
+		tm.d2h_ms = all - kend;
+	}
+	tm.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+	if (timing != nullptr) {
+		*timing = tm;
+	}
+	return X3S_OK;
+}
+
 int x3s_search_device(int device, const void *d_x, size_t n_positions, size_t W, int t, void *d_lstar,
                       void *d_H, void *stream, int variant)
 {

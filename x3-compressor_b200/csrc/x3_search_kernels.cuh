@@ -21,6 +21,9 @@ struct X3SearchParams {
 	uint8_t *deep;              /* X3K_DEEP_BYTES_PER_CTA bytes per resident CTA */
 	unsigned int ntiles;
 	int kd;                     /* dense levels: 2, 3, or 0 = choose per tile from a probe */
+	/* segment search only: this launch takes pieces part, part + parts, ... of the positions [0, n), a piece
+	 * being piece_segments segments (0 = all of [0, n): the plain search) */
+	uint32_t part = 0, parts = 1, piece_segments = 0;
 };
 
 /* Scratch the stream kernel needs: the grid it will be launched with and the

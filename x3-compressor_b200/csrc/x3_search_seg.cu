@@ -93,7 +93,8 @@ struct SegArgs {
 	unsigned long long xbytes;   /* multiple of 16 */
 	uint32_t D, B;               /* distances; positions per segment (multiple of 16) */
 	int t;
-	uint32_t nseg;
+	uint32_t nseg;               /* segments of this launch */
+	uint32_t part, parts, spp;   /* spp != 0: the launch takes pieces part, part + parts, ... of spp segments each */
 	unsigned int *ticket;        /* zeroed before the launch */
 	unsigned long long *prof;    /* NULL, or 9 counters per CTA (X3_SEG_PROF=1): cycles of load, pass 0, passes 1-3,
 	                              * level-4 groups, big groups, waves, chains, store; segments */
@@ -1309,7 +1310,15 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 		if (seg >= a.nseg) {
 			break;
 		}
-		const unsigned long long a0 = (unsigned long long)seg * a.B;
+		unsigned long long gseg = seg;
+		if (a.spp != 0u) {
+			gseg = (unsigned long long)(a.part + (seg / a.spp) * a.parts) * a.spp + seg % a.spp;
+		}
+		const unsigned long long a0 = gseg * a.B;
+		if (a0 >= a.n) {
+			__syncthreads(); /* (everybody has read the ticket before thread 0 draws the next one) */
+			continue; /* (the input's last piece may be short) */
+		}
 		c.Bs = (uint32_t)(a.n - a0 < a.B ? a.n - a0 : a.B);
 		c.M = c.Bs + a.D + 3u;
 		/* the segment's bytes: xs[k] = x[a0 - 3 + k], k in [0, M + 48); virtual zeros in front of the input */
@@ -1513,7 +1522,24 @@ cudaError_t x3k_launch_seg(const X3SearchParams &prm, cudaStream_t stream, int *
 	a.D = prm.D;
 	a.B = x3k_seg_positions(prm.D);
 	a.t = prm.t;
-	const unsigned long long nseg = (prm.n + a.B - 1) / a.B;
+	unsigned long long nseg = (prm.n + a.B - 1) / a.B;
+	a.part = 0;
+	a.parts = 1;
+	a.spp = 0;
+	if (prm.piece_segments != 0u) {
+		if (prm.parts == 0u || prm.part >= prm.parts) {
+			return cudaErrorInvalidValue;
+		}
+		const unsigned long long npieces = (nseg + prm.piece_segments - 1) / prm.piece_segments;
+		const unsigned long long mine = npieces > prm.part ? (npieces - prm.part + prm.parts - 1) / prm.parts : 0;
+		nseg = mine * prm.piece_segments;
+		a.part = prm.part;
+		a.parts = prm.parts;
+		a.spp = prm.piece_segments;
+		if (nseg == 0) {
+			return cudaSuccess;
+		}
+	}
 	if (nseg > 0xffffffffull) {
 		return cudaErrorNotSupported;
 	}
