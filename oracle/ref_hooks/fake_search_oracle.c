@@ -42,3 +42,29 @@ int x3s_search_host(const void *x, size_t n, size_t W, int t, int ngpus, int var
 	}
 	return X3S_OK;
 }
+
+/* the streamed form: the fake computes the table in pieces of 64 K positions and moves *ready on behind each,
+ * so that the shim's waiting find_best_match() is exercised on a CPU-only machine too */
+int x3s_search_host_stream(const void *x, size_t n, size_t W, int t, int ngpus, int variant, void *lstar,
+                           x3s_timing *timing, volatile size_t *ready)
+{
+	(void)ngpus; (void)variant;
+	if (ready == NULL) {
+		return X3S_ERR_ARG;
+	}
+	__atomic_store_n(ready, (size_t)0, __ATOMIC_RELEASE);
+	const size_t step = (size_t)1 << 16;
+	for (size_t p0 = 0; p0 < n; p0 += step) {
+		const size_t p1 = n - p0 < step ? n : p0 + step;
+		x3o_table_fast((const uint8_t *)x, n + W, p0, p1, W, t, NULL, NULL, (uint8_t *)lstar + p0);
+		__atomic_store_n(ready, p1, __ATOMIC_RELEASE);
+	}
+	__atomic_store_n(ready, n, __ATOMIC_RELEASE);
+	if (timing != NULL) {
+		memset(timing, 0, sizeof(*timing));
+	}
+	return X3S_OK;
+}
+
+size_t x3s_part_positions(size_t W) { (void)W; return 0; }
+int x3s_default_kernel(size_t W, int t, int want_table) { (void)W; (void)t; (void)want_table; return X3S_KERNEL_DEFAULT; }
