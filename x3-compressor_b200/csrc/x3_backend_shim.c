@@ -59,6 +59,9 @@ void x3_backend_set_dict(x3_dict_find_fn find, x3_dict_len_fn len)
 static const char *g_base = NULL;
 static size_t g_isize = 0;
 static uint8_t *g_lstar = NULL;
+static uint8_t *g_spare = NULL;       /* the last table's memory, kept for the next prepare (X3_TABLE_KEEP=1) */
+static size_t g_spare_bytes = 0;
+static size_t g_lstar_bytes = 0;
 static uint8_t *g_table = NULL;
 static int g_lstar_pinned = 0;       /* g_lstar came from x3s_host_alloc */
 static void *g_registered = NULL;    /* the caller's buffer, page-locked in place for the duration of the tables */
@@ -155,10 +158,14 @@ void x3_search_release(void)
 	}
 	if (g_lstar_pinned) {
 		x3s_host_free(g_lstar);
+	} else if (g_lstar != NULL && getenv("X3_TABLE_KEEP") != NULL && g_spare == NULL) {
+		g_spare = g_lstar; /* a host that prepares again and again skips mapping the table anew */
+		g_spare_bytes = g_lstar_bytes;
 	} else {
 		free(g_lstar);
 	}
 	g_lstar_pinned = 0;
+	g_lstar_bytes = 0;
 	g_ready = 0;
 	g_ready_seen = 0;
 	g_worker_done = 0;
@@ -233,12 +240,23 @@ void x3_search_prepare(const char *base, size_t isize)
 		/* 2 MB aligned, so that the kernel may back it with huge pages */
 		void *mem = NULL;
 		const size_t bytes = ((isize > 0 ? isize : 1) + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
-		if (posix_memalign(&mem, (size_t)2 << 20, bytes) != 0 || mem == NULL) {
-			die("out of memory");
+		if (g_spare != NULL && g_spare_bytes >= bytes) {
+			mem = g_spare;
+			g_lstar_bytes = g_spare_bytes;
+			g_spare = NULL;
+		} else {
+			free(g_spare);
+			g_spare = NULL;
+			if (posix_memalign(&mem, (size_t)2 << 20, bytes) != 0 || mem == NULL) {
+				die("out of memory");
+			}
+			if (getenv("X3_TABLE_NO_THP") == NULL) {
+				(void)madvise(mem, bytes, MADV_HUGEPAGE);
+			}
+			g_lstar_bytes = bytes;
+			fresh = 1;
 		}
-		(void)madvise(mem, bytes, MADV_HUGEPAGE);
 		g_lstar = mem;
-		fresh = 1;
 	}
 	g_base = base;
 	g_isize = isize;
