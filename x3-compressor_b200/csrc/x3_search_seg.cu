@@ -126,6 +126,18 @@ __device__ __forceinline__ uint32_t sg_gram(uint32_t e)
 	return __funnelshift_r(SG_XSW[w], SG_XSW[w + 1], (off & 3u) * 8u);
 }
 
+/* what pass K of the LSD sort needs of element e: its digit x[p+3-K] in the low byte, the K bytes behind it above
+ * (NB = K + 1 bytes from x[p+3-K]); the second word is only fetched by the lanes whose bytes straddle a word */
+template <int K>
+__device__ __forceinline__ uint32_t sg_gram_from(uint32_t e)
+{
+	const uint32_t off = SG_XS_OFF + e + 3u - (uint32_t)K;
+	const uint32_t w = off >> 2, sh = off & 3u;
+	const uint32_t lo = SG_XSW[w];
+	const uint32_t hi = sh + (uint32_t)K + 1u > 4u ? SG_XSW[w + 1] : 0u;
+	return __funnelshift_r(lo, hi, sh * 8u);
+}
+
 __device__ __forceinline__ uint32_t sg_byte(uint32_t e, uint32_t L)
 {
 	return SG_XSB[SG_XS_OFF + e + L];
@@ -447,7 +459,7 @@ __device__ __forceinline__ void sg_lsd_pass2(const SegCtx &c, unsigned long long
 		for (int h = 0; h < 2; ++h) {
 			if (blk[h] + lane < M) {
 				e_n[h] = In[blk[h] + lane];
-				g_n[h] = sg_gram(e_n[h]);
+				g_n[h] = sg_gram_from<K>(e_n[h]);
 			}
 		}
 	}
@@ -468,9 +480,9 @@ __device__ __forceinline__ void sg_lsd_pass2(const SegCtx &c, unsigned long long
 					const uint32_t e = e_n[h], g = g_n[h];
 					if (i + 32u < M) {
 						e_n[h] = In[i + 32u];
-						g_n[h] = sg_gram(e_n[h]);
+						g_n[h] = sg_gram_from<K>(e_n[h]);
 					}
-					d[h] = (g >> (8 * (3 - K))) & 255u;
+					d[h] = g & 255u;
 					/* level K on the input order: the element t+1 places further on */
 					uint32_t ef, gf;
 					if (LA32) {
@@ -485,12 +497,12 @@ __device__ __forceinline__ void sg_lsd_pass2(const SegCtx &c, unsigned long long
 						gf = 0;
 						if (i + c.la < M) {
 							ef = In[i + c.la];
-							gf = sg_gram(ef);
+							gf = sg_gram_from<K>(ef);
 						}
 					}
 					const uint32_t q = e + 1u - (uint32_t)K;   /* searched position (relative to the segment) */
 					const bool subj = valid[h] && q < c.Bs;
-					const bool pass = subj && i + c.la < M && ((g ^ gf) >> (K == 0 ? 0 : 32 - 8 * K)) == 0u && ef - e <= c.D;
+					const bool pass = subj && i + c.la < M && (((g ^ gf) & (K >= 3 ? 0xffffffffu : (1u << (8 * (K + 1))) - 1u)) >> 8) == 0u && ef - e <= c.D;
 					if (pass) {
 						SG_L8[q] = (uint8_t)K;
 					}
@@ -861,7 +873,7 @@ __device__ __forceinline__ void sg_big_level(const SegCtx &c, uint32_t s, uint32
 constexpr uint32_t SG_WHOLE = 2u;
 
 template <bool PROF>
-__device__ __forceinline__ bool sg_wave(const SegCtx &c)
+__device__ __forceinline__ bool sg_wave(const SegCtx &c, unsigned long long *gp)
 {
 	/* measurement build: cycles of the wave's parts and the wave count, behind the phase counters */
 	unsigned long long *wp = reinterpret_cast<unsigned long long *>(sg_smem + SG_SMEM) + 10;
@@ -941,6 +953,16 @@ __device__ __forceinline__ bool sg_wave(const SegCtx &c)
 	uint16_t *myh = SG_WH + warp * 256;
 	uint32_t st[8]; /* my element of round r: id | rank << 15 | byte << 23 | kept << 31 */
 	/* (1) */
+	unsigned long long st0 = 0;
+#define SG_SLAP(k)                                 \
+	if (PROF && threadIdx.x == 0) {                \
+		const unsigned long long now = clock64();  \
+		gp[40 + (k)] += now - st0;                 \
+		st0 = now;                                 \
+	}
+	if (PROF && threadIdx.x == 0) {
+		st0 = clock64();
+	}
 	if (rowon) {
 		reinterpret_cast<uint4 *>(myh)[lane] = make_uint4(0u, 0u, 0u, 0u);
 		uint32_t ef[8];
@@ -950,6 +972,7 @@ __device__ __forceinline__ bool sg_wave(const SegCtx &c)
 			st[r] = i < glen ? (uint32_t)In[i] : 0u;
 			ef[r] = i + c.la < glen ? (uint32_t)In[i + c.la] : 0xffffffu;
 		}
+		SG_SLAP(0)
 		uint32_t pmk[8];
 #pragma unroll
 		for (int r = 0; r < 8; ++r) {
@@ -959,6 +982,7 @@ __device__ __forceinline__ bool sg_wave(const SegCtx &c)
 			}
 			pmk[r] = __ballot_sync(FULL_MASK, pass);
 		}
+		SG_SLAP(1)
 		if (L < 32u) {
 			/* the last passed element in front of my row */
 			uint32_t carry = SG_NONE;
@@ -985,6 +1009,7 @@ __device__ __forceinline__ bool sg_wave(const SegCtx &c)
 					carry = In[coff - 1u];
 				}
 			}
+			SG_SLAP(2)
 			uint32_t bb[8];
 #pragma unroll
 			for (int r = 0; r < 8; ++r) {
@@ -1000,22 +1025,30 @@ __device__ __forceinline__ bool sg_wave(const SegCtx &c)
 				}
 				bb[r] = kept ? sg_byte(e, L) : 256u; /* (one value for all the others: a distinct value costs MATCH.ANY 2 cycles) */
 			}
+			SG_SLAP(3)
 #pragma unroll
 			for (int r = 0; r < 8; ++r) {
+				/* the leader of a byte value adds its lanes to the row's count with ONE shared-memory atomic and hands
+				 * the old count on: nothing to wait for between the rounds (the atomics of a warp on one address
+				 * keep their order), so the eight matches, adds and shuffles of a row overlap */
 				const uint32_t b = bb[r];
 				const bool kept = b < 256u;
 				const uint32_t peers = __match_any_sync(FULL_MASK, b);
-				const uint32_t old = kept ? (uint32_t)myh[b] : 0u;
-				__syncwarp();
+				uint32_t old = 0;
 				if (kept && (peers & lt) == 0u) {
-					myh[b] = (uint16_t)(old + __popc(peers));
+					/* (two 16-bit counts to a word: the add goes to the byte value's half) */
+					const uint32_t sh = (b & 1u) * 16u;
+					old = (atomicAdd(reinterpret_cast<uint32_t *>(myh) + (b >> 1), (uint32_t)__popc(peers) << sh) >> sh) & 0xffffu;
 				}
+				old = __shfl_sync(FULL_MASK, old, __ffs((int)peers) - 1);
 				st[r] = kept ? st[r] | ((old + __popc(peers & lt)) << 15) | (b << 23) | 0x80000000u : 0u;
-				__syncwarp();
 			}
+			SG_SLAP(4)
 		}
 	}
 	__syncthreads();
+	SG_SLAP(5)
+#undef SG_SLAP
 	SG_WLAP(1)
 	/* (2) */
 	if (rowon && L < 32u) {
@@ -1398,7 +1431,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 		}
 		SG_LAP(4)
 		/* groups above SG_CHAIN_MAX elements, wave after wave */
-		while (sg_wave<PROF>(c)) {
+		while (sg_wave<PROF>(c, a.prof + blockIdx.x * 64)) {
 		}
 		__syncthreads();
 		SG_LAP(5)
@@ -1585,6 +1618,13 @@ cudaError_t x3k_launch_seg(const X3SearchParams &prm, cudaStream_t stream, int *
 			fprintf(stderr, ";  %.1f waves per segment, cycles per wave: form %.0f  (1) %.0f  (2) %.0f  (3) %.0f\n",
 			        tot[15] / (tot[8] > 0 ? tot[8] : 1), tot[10] / (tot[15] > 0 ? tot[15] : 1), tot[11] / (tot[15] > 0 ? tot[15] : 1),
 			        tot[12] / (tot[15] > 0 ? tot[15] : 1), tot[13] / (tot[15] > 0 ? tot[15] : 1));
+			fprintf(stderr, "x3_seg_kernel: wave part (1) as warp 0 (row 0) sees it, cycles per wave: loads %.0f  test+votes %.0f  look-back %.0f  kept+bytes %.0f  match+histogram %.0f  barrier %.0f\n",
+			        (double)0 + [&]{double v=0; for (unsigned b = 0; b < grid; ++b) v += (double)h[b * 64 + 40]; return v;}() / (tot[15] > 0 ? tot[15] : 1),
+			        [&]{double v=0; for (unsigned b = 0; b < grid; ++b) v += (double)h[b * 64 + 41]; return v;}() / (tot[15] > 0 ? tot[15] : 1),
+			        [&]{double v=0; for (unsigned b = 0; b < grid; ++b) v += (double)h[b * 64 + 42]; return v;}() / (tot[15] > 0 ? tot[15] : 1),
+			        [&]{double v=0; for (unsigned b = 0; b < grid; ++b) v += (double)h[b * 64 + 43]; return v;}() / (tot[15] > 0 ? tot[15] : 1),
+			        [&]{double v=0; for (unsigned b = 0; b < grid; ++b) v += (double)h[b * 64 + 44]; return v;}() / (tot[15] > 0 ? tot[15] : 1),
+			        [&]{double v=0; for (unsigned b = 0; b < grid; ++b) v += (double)h[b * 64 + 45]; return v;}() / (tot[15] > 0 ? tot[15] : 1));
 			fprintf(stderr, "x3_seg_kernel: passes, cycles per segment (ranking / offsets / placement):");
 			for (int K = 0; K < 4; ++K) {
 				fprintf(stderr, "  K=%d %.0f / %.0f / %.0f", K, tot[16 + 4 * K] / (tot[8] > 0 ? tot[8] : 1),
