@@ -213,7 +213,13 @@ def test_pieces_dealt_out_in_turn_assemble_the_table(pkg, corpus, monkeypatch, p
                 done[q * piece:(q + 1) * piece] = True
         assert np.array_equal(out[done], want[done]) and (out[~done] == 255).all()
     assert np.array_equal(out, want)
-    assert launches == (n + piece - 1) // piece
+    # a part's pieces go in batches of max(4, min(32, m / 4)), one launch each
+    want_launches = 0
+    for p in range(parts):
+        m = len(range(p, (n + piece - 1) // piece, parts))
+        per = max(4, min(32, m // 4))
+        want_launches += (m + per - 1) // per
+    assert launches == want_launches
     # device resident: the whole input in HBM, one launch per part
     dev = torch.device("cuda", 0)
     d_x = torch.zeros(pkg.required_bytes(n, W), dtype=torch.uint8, device=dev)

@@ -281,7 +281,7 @@ static size_t part_segments(size_t W)
 	}
 	const size_t B = x3k_seg_positions(D);
 	const char *pm = getenv("X3_PART_PIECE_KB"); /* tuning/testing knob; never changes results */
-	const size_t kb = pm != nullptr && atoi(pm) >= 1 ? (size_t)atoi(pm) : 4096;
+	const size_t kb = pm != nullptr && atoi(pm) >= 1 ? (size_t)atoi(pm) : 1024;
 	const size_t segs = (kb << 10) / B;
 	return segs < 1 ? 1 : segs;
 }
@@ -414,32 +414,49 @@ int x3s_search_host_part(const void *x, size_t n, size_t W, int t, void *lstar, 
 			CU_TRY(cudaMemsetAsync(ds.d_x + total, 0, need - total, U));
 		}
 		const uint32_t D = distances(W);
-		for (size_t j = 0; j < m; ++j) {
-			const size_t p0 = mine[j] * PS, len = n - p0 < PS ? n - p0 : PS;
-			size_t b1 = p0 + len + W + 128; /* the piece, the window behind it, the kernel's slack */
-			if (b1 > total) b1 = total;
-			CU_TRY(cudaMemcpyAsync(ds.d_x + p0, (const uint8_t *)x + p0, b1 - p0, cudaMemcpyHostToDevice, U));
-			CU_TRY(cudaEventRecord(ds.upev[j], U));
-			/* searches on two streams in turn (a counter each): the last segments of a piece share the GPU with
-			 * the first of the next */
-			cudaStream_t Ks = K[j & 1];
-			CU_TRY(cudaStreamWaitEvent(Ks, ds.upev[j], 0));
+		/* batches of pieces: a batch is uploaded piece by piece, searched by ONE launch (the kernel maps the
+		 * launch's tickets to the batch's pieces) on one of two streams in turn -- so that the last segments of a
+		 * batch share the GPU with the first of the next -- and copied back piece by piece */
+		size_t per = m / 4;
+		if (per < 4) per = 4;
+		if (per > 32) per = 32;
+		const char *pb = getenv("X3_PART_BATCH"); /* tuning/testing knob; never changes results */
+		if (pb != nullptr && atoi(pb) >= 1) per = (size_t)atoi(pb);
+		size_t nb = 0;
+		for (size_t j0 = 0; j0 < m; j0 += per, ++nb) {
+			const size_t j1 = j0 + per < m ? j0 + per : m;
+			for (size_t j = j0; j < j1; ++j) {
+				const size_t p0 = mine[j] * PS, len = n - p0 < PS ? n - p0 : PS;
+				size_t b1 = p0 + len + W + 128; /* the piece, the window behind it, the kernel's slack */
+				if (b1 > total) b1 = total;
+				CU_TRY(cudaMemcpyAsync(ds.d_x + p0, (const uint8_t *)x + p0, b1 - p0, cudaMemcpyHostToDevice, U));
+			}
+			CU_TRY(cudaEventRecord(ds.upev[nb], U));
+			cudaStream_t Ks = K[nb & 1];
+			CU_TRY(cudaStreamWaitEvent(Ks, ds.upev[nb], 0));
 			X3SearchParams prm;
-			prm.x = ds.d_x + p0;
-			prm.n = len;
+			prm.x = ds.d_x;
+			prm.n = n;
 			prm.D = D;
 			prm.t = t;
-			prm.lstar = ds.d_l + p0;
+			prm.lstar = ds.d_l;
 			prm.H = nullptr;
-			prm.tile_counter = sc.counter + 16 * (1 + (j & 1));
+			prm.tile_counter = sc.counter + 16 * (1 + (nb & 1));
 			prm.deep = nullptr;
 			prm.ntiles = 0;
 			prm.kd = 0;
+			prm.part = (uint32_t)part;
+			prm.parts = (uint32_t)parts;
+			prm.piece_segments = (uint32_t)part_segments(W);
+			prm.piece_first = (uint32_t)j0;
+			prm.piece_count = (uint32_t)(j1 - j0);
 			CU_TRY(x3k_launch_seg(prm, Ks, &tm.launches));
-			CU_TRY(cudaEventRecord(ds.upev[m + j], Ks));
-			CU_TRY(cudaStreamWaitEvent(Cc, ds.upev[m + j], 0));
-			CU_TRY(cudaMemcpyAsync((uint8_t *)lstar + p0, ds.d_l + p0, len, cudaMemcpyDeviceToHost, Cc));
-			CU_TRY(cudaEventRecord(ds.upev[2 * m + j], Cc));
+			CU_TRY(cudaEventRecord(ds.upev[m + nb], Ks));
+			CU_TRY(cudaStreamWaitEvent(Cc, ds.upev[m + nb], 0));
+			for (size_t j = j0; j < j1; ++j) {
+				const size_t p0 = mine[j] * PS, len = n - p0 < PS ? n - p0 : PS;
+				CU_TRY(cudaMemcpyAsync((uint8_t *)lstar + p0, ds.d_l + p0, len, cudaMemcpyDeviceToHost, Cc));
+			}
 		}
 		CU_TRY(cudaEventRecord(ds.ev[1], U));
 		for (int k = 0; k < 2; ++k) {
@@ -452,7 +469,7 @@ int x3s_search_host_part(const void *x, size_t n, size_t W, int t, void *lstar, 
 		CU_TRY(cudaEventRecord(sc.last, U));
 		CU_TRY(cudaStreamSynchronize(U));
 		float up = 0.f, all = 0.f, kend = 0.f, ms = 0.f;
-		CU_TRY(cudaEventElapsedTime(&up, ds.ev[0], ds.upev[0]));
+		CU_TRY(cudaEventElapsedTime(&up, ds.ev[0], ds.upev[0])); /* (the first batch uploaded) */
 		CU_TRY(cudaEventElapsedTime(&all, ds.ev[0], ds.ev[3]));
 		for (int k = 0; k < 2; ++k) {
 			CU_TRY(cudaEventElapsedTime(&ms, ds.ev[0], ds.pev[k][0]));

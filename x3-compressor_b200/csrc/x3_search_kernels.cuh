@@ -24,6 +24,7 @@ struct X3SearchParams {
 	/* segment search only: this launch takes pieces part, part + parts, ... of the positions [0, n), a piece
 	 * being piece_segments segments (0 = all of [0, n): the plain search) */
 	uint32_t part = 0, parts = 1, piece_segments = 0;
+	uint32_t piece_first = 0, piece_count = 0; /* of the part's own pieces: the launch takes [first, first + count) (count 0 = all) */
 };
 
 /* Scratch the stream kernel needs: the grid it will be launched with and the

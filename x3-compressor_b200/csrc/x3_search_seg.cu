@@ -94,7 +94,8 @@ struct SegArgs {
 	uint32_t D, B;               /* distances; positions per segment (multiple of 16) */
 	int t;
 	uint32_t nseg;               /* segments of this launch */
-	uint32_t part, parts, spp;   /* spp != 0: the launch takes pieces part, part + parts, ... of spp segments each */
+	uint32_t part, parts, spp;   /* spp != 0: the launch takes pieces part, part + parts, ... of spp segments each, */
+	uint32_t k0;                 /* from the part's k0-th piece on */
 	unsigned int *ticket;        /* zeroed before the launch */
 	unsigned long long *prof;    /* NULL, or 9 counters per CTA (X3_SEG_PROF=1): cycles of load, pass 0, passes 1-3,
 	                              * level-4 groups, big groups, waves, chains, store; segments */
@@ -1345,7 +1346,7 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 		}
 		unsigned long long gseg = seg;
 		if (a.spp != 0u) {
-			gseg = (unsigned long long)(a.part + (seg / a.spp) * a.parts) * a.spp + seg % a.spp;
+			gseg = (unsigned long long)(a.part + (a.k0 + seg / a.spp) * a.parts) * a.spp + seg % a.spp;
 		}
 		const unsigned long long a0 = gseg * a.B;
 		if (a0 >= a.n) {
@@ -1559,12 +1560,21 @@ cudaError_t x3k_launch_seg(const X3SearchParams &prm, cudaStream_t stream, int *
 	a.part = 0;
 	a.parts = 1;
 	a.spp = 0;
+	a.k0 = 0;
 	if (prm.piece_segments != 0u) {
 		if (prm.parts == 0u || prm.part >= prm.parts) {
 			return cudaErrorInvalidValue;
 		}
 		const unsigned long long npieces = (nseg + prm.piece_segments - 1) / prm.piece_segments;
-		const unsigned long long mine = npieces > prm.part ? (npieces - prm.part + prm.parts - 1) / prm.parts : 0;
+		unsigned long long mine = npieces > prm.part ? (npieces - prm.part + prm.parts - 1) / prm.parts : 0;
+		a.k0 = 0;
+		if (prm.piece_count != 0u) {
+			a.k0 = prm.piece_first;
+			mine = mine > prm.piece_first ? mine - prm.piece_first : 0;
+			if (mine > prm.piece_count) {
+				mine = prm.piece_count;
+			}
+		}
 		nseg = mine * prm.piece_segments;
 		a.part = prm.part;
 		a.parts = prm.parts;
