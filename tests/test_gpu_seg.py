@@ -213,12 +213,11 @@ def test_pieces_dealt_out_in_turn_assemble_the_table(pkg, corpus, monkeypatch, p
                 done[q * piece:(q + 1) * piece] = True
         assert np.array_equal(out[done], want[done]) and (out[~done] == 255).all()
     assert np.array_equal(out, want)
-    # a part's pieces go in batches of max(4, min(32, m / 4)), one launch each
+    # a part's pieces go in batches of 4, one launch each
     want_launches = 0
     for p in range(parts):
         m = len(range(p, (n + piece - 1) // piece, parts))
-        per = max(4, min(32, m // 4))
-        want_launches += (m + per - 1) // per
+        want_launches += (m + 3) // 4
     assert launches == want_launches
     # device resident: the whole input in HBM, one launch per part
     dev = torch.device("cuda", 0)

@@ -417,9 +417,7 @@ int x3s_search_host_part(const void *x, size_t n, size_t W, int t, void *lstar, 
 		/* batches of pieces: a batch is uploaded piece by piece, searched by ONE launch (the kernel maps the
 		 * launch's tickets to the batch's pieces) on one of two streams in turn -- so that the last segments of a
 		 * batch share the GPU with the first of the next -- and copied back piece by piece */
-		size_t per = m / 4;
-		if (per < 4) per = 4;
-		if (per > 32) per = 32;
+		size_t per = 4; /* (measured on C5, 2 and 8 parts: 2 pieces per launch 7.7 / 2.3 ms, 4: 6.3 / 1.8, 8: 6.4 / 2.0, 26: 7.2 / 2.8) */
 		const char *pb = getenv("X3_PART_BATCH"); /* tuning/testing knob; never changes results */
 		if (pb != nullptr && atoi(pb) >= 1) per = (size_t)atoi(pb);
 		size_t nb = 0;
