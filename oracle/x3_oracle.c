@@ -3,7 +3,7 @@
  *
  * TEST INFRASTRUCTURE ONLY (see x3_oracle.h).  Parity status: PINNED against the
  * compiled, unmodified reference (oracle/Makefile -> oracle/_ref/libx3ref.so,
- * checked by tests/test_oracle_vs_ref.py).
+ * checked by tests/test_oracle.py).
  */
 #include "x3_oracle.h"
 

@@ -9,7 +9,7 @@
  * Parity status: PINNED.  The reference holds no golden vectors for this path
  * (SURVEY.md section 4), so the oracle is pinned against the reference itself:
  * oracle/Makefile compiles the unmodified /root/reference sources into
- * oracle/_ref/ and tests/test_oracle_vs_ref.py checks every function below
+ * oracle/_ref/ and tests/test_oracle.py checks every function below
  * against the compiled reference find_best_match() (reference backend.c:56-100),
  * with an empty and with a live dictionary.
  *

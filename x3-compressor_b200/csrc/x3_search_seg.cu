@@ -487,12 +487,13 @@ __device__ __forceinline__ void sg_lsd_pass2(const SegCtx &c, unsigned long long
 					/* level K on the input order: the element t+1 places further on */
 					uint32_t ef, gf;
 					if (LA32) {
+						/* lane j wants the element la places on: lane (j + la) & 31 of this round while j + la < 32,
+						 * of the next round otherwise -- so every lane s serves exactly one other, with this round's
+						 * element when s >= la and the next round's when s < la: one shuffle per value */
 						const int sl = (lane + (int)c.la) & 31;
-						const uint32_t e1 = __shfl_sync(FULL_MASK, e, sl), e2 = __shfl_sync(FULL_MASK, e_n[h], sl);
-						const uint32_t g1 = __shfl_sync(FULL_MASK, g, sl), g2 = __shfl_sync(FULL_MASK, g_n[h], sl);
-						const bool here = lane + (int)c.la < 32;
-						ef = here ? e1 : e2;
-						gf = here ? g1 : g2;
+						const bool mine_now = (uint32_t)lane >= c.la;
+						ef = __shfl_sync(FULL_MASK, mine_now ? e : e_n[h], sl);
+						gf = __shfl_sync(FULL_MASK, mine_now ? g : g_n[h], sl);
 					} else {
 						ef = 0;
 						gf = 0;

@@ -3,7 +3,10 @@
  *
  * Same interface as the reference's main() (reference x3.c:460-702): options
  * "zdfkht:w:m:n:x", 0/1/2 file arguments, ".x3" suffix handling, refusal to
- * overwrite without -f, banner and report on stderr.  Compression calls the GPU
+ * overwrite without -f, banner and report on stderr.  The help text, the switch over
+ * the file arguments and the report's printf lines follow x3.c:465-548,662-693 closely
+ * ON PURPOSE: those strings and that format are the drop-in contract of the CLI
+ * (tests/test_host_x3.py: test_report_matches_reference, test_cli_behaviour).  Compression calls the GPU
  * search once (x3_search_prepare, the hook of INTEGRATION.md section 1) and then
  * runs the sequential pass of x3_codec.c; the stream is byte-identical to the
  * reference's for the same input and flags.  Decompression needs no GPU.
