@@ -96,6 +96,7 @@ struct SegArgs {
 	uint32_t nseg;               /* segments of this launch */
 	uint32_t part, parts, spp;   /* spp != 0: the launch takes pieces part, part + parts, ... of spp segments each, */
 	uint32_t k0;                 /* from the part's k0-th piece on */
+	uint32_t split_first, split_k, split_B; /* tickets from split_first on are split_k-ths of a segment (split_B positions) */
 	unsigned int *ticket;        /* zeroed before the launch */
 	unsigned long long *prof;    /* NULL, or 9 counters per CTA (X3_SEG_PROF=1): cycles of load, pass 0, passes 1-3,
 	                              * level-4 groups, big groups, waves, chains, store; segments */
@@ -1345,16 +1346,30 @@ __global__ void __launch_bounds__(SG_THREADS, 1) x3_seg_kernel(SegArgs a)
 		if (seg >= a.nseg) {
 			break;
 		}
-		unsigned long long gseg = seg;
-		if (a.spp != 0u) {
-			gseg = (unsigned long long)(a.part + (a.k0 + seg / a.spp) * a.parts) * a.spp + seg % a.spp;
+		/* the launch's last, partly filled wave of segments (and every segment of a launch that has fewer
+		 * segments than SMs) is dealt out in split_k-ths: more SMs finish it in less time */
+		uint32_t lseg = seg, sub = 0, nsub = 1;
+		if (seg >= a.split_first) {
+			lseg = a.split_first + (seg - a.split_first) / a.split_k;
+			sub = (seg - a.split_first) % a.split_k;
+			nsub = a.split_k;
 		}
-		const unsigned long long a0 = gseg * a.B;
+		unsigned long long gseg = lseg;
+		if (a.spp != 0u) {
+			gseg = (unsigned long long)(a.part + (a.k0 + lseg / a.spp) * a.parts) * a.spp + lseg % a.spp;
+		}
+		const unsigned long long a0 = gseg * a.B + (unsigned long long)sub * a.split_B;
 		if (a0 >= a.n) {
 			__syncthreads(); /* (everybody has read the ticket before thread 0 draws the next one) */
 			continue; /* (the input's last piece may be short) */
 		}
-		c.Bs = (uint32_t)(a.n - a0 < a.B ? a.n - a0 : a.B);
+		{
+			unsigned long long a1 = gseg * a.B + (sub + 1u == nsub ? a.B : (unsigned long long)(sub + 1u) * a.split_B);
+			if (a1 > a.n) {
+				a1 = a.n;
+			}
+			c.Bs = (uint32_t)(a1 - a0);
+		}
 		c.M = c.Bs + a.D + 3u;
 		/* the segment's bytes: xs[k] = x[a0 - 3 + k], k in [0, M + 48); virtual zeros in front of the input */
 		{
@@ -1587,11 +1602,36 @@ cudaError_t x3k_launch_seg(const X3SearchParams &prm, cudaStream_t stream, int *
 	if (nseg > 0xffffffffull) {
 		return cudaErrorNotSupported;
 	}
-	a.nseg = (uint32_t)nseg;
+	unsigned grid;
+	{
+		const char *ns = getenv("X3_SEG_NO_SPLIT"); /* tuning/testing knob; never changes results */
+		const uint32_t S = (uint32_t)sms, ns32 = (uint32_t)nseg;
+		uint32_t k = 1, first = ns32, tickets = ns32;
+		if (ns == nullptr && a.B >= 256u) {
+			if (ns32 >= S) {
+				const uint32_t full = ns32 / S * S, rem = ns32 - full;
+				if (rem > 0 && rem * 2u <= S) {
+					k = S / rem < 4u ? S / rem : 4u;
+					first = full;
+					tickets = full + rem * k;
+				}
+			} else {
+				k = S / ns32 < 4u ? S / ns32 : 4u;
+				if (k > 1u) {
+					first = 0;
+					tickets = ns32 * k;
+				}
+			}
+		}
+		a.split_first = first;
+		a.split_k = k;
+		a.split_B = (a.B / k) & ~15u;
+		a.nseg = tickets;
+		grid = tickets < S ? tickets : S;
+	}
 	a.ticket = prm.tile_counter;
 	a.prof = nullptr;
 	if ((e = cudaMemsetAsync(a.ticket, 0, sizeof(unsigned int), stream)) != cudaSuccess) return e;
-	const unsigned grid = nseg < (unsigned long long)sms ? (unsigned)nseg : (unsigned)sms;
 	const bool prof = getenv("X3_SEG_PROF") != nullptr; /* measurement knob: cycles per phase, printed */
 	if (prof) {
 		if ((e = cudaMalloc((void **)&a.prof, (size_t)grid * 512)) != cudaSuccess) return e;
