@@ -645,7 +645,7 @@ int search_host_impl(const void *x, size_t n, size_t W, int t, int ngpus, int va
 		const bool rank = H == nullptr && kind == 1;
 		if (kind == 2 && getenv("X3_HOST_PIECES") == nullptr) {
 			/* Segment search, piece by piece: the upload runs ahead on ds.stream, a piece (a whole number of
-			 * segments; 32 MB between page-locked buffers, 16 MB otherwise, X3_SEG_PIECE_MB overrides) is
+			 * segments, 16 MB; X3_SEG_PIECE_MB overrides) is
 			 * searched on a second stream as soon as the bytes it reads -- its own and the window behind
 			 * them -- have arrived, and its Lstar goes back on a third while the next pieces are searched.
 			 * Pageable buffers (what the backend.h drop-in gets from the reference's main, x3.c:579) take the
@@ -655,7 +655,7 @@ int search_host_impl(const void *x, size_t n, size_t W, int t, int ngpus, int va
 			const bool x_pinned = host_pinned(x), l_pinned = host_pinned(lstar);
 			const size_t B = x3k_seg_positions(D);
 			const char *pm = getenv("X3_SEG_PIECE_MB");
-			const size_t mb = pm != nullptr && atoi(pm) >= 1 ? (size_t)atoi(pm) : (x_pinned && l_pinned ? 32 : 16);
+			const size_t mb = pm != nullptr && atoi(pm) >= 1 ? (size_t)atoi(pm) : 16; /* (C5, page-locked: 32 MB pieces 13.9 ms host to host, 16 MB 12.7, 8 MB 14.1) */
 			size_t PS = ((mb << 20) / B) * B;
 			if (PS < B) PS = B;
 			const size_t nps = (np + PS - 1) / PS;
@@ -675,11 +675,14 @@ int search_host_impl(const void *x, size_t n, size_t W, int t, int ngpus, int va
 					CU_TRY(cudaEventCreate(&ev));
 					ds.upev.push_back(ev);
 				}
-				cudaStream_t U = ds.stream, K = ds.ps[0], Cc = ds.ps[1];
+				/* searches on two streams in turn (a counter each): the last segments of a piece share the GPU with the
+				 * first of the next */
+				cudaStream_t U = ds.stream, K2[2] = {ds.ps[0], ds.ps[2]}, Cc = ds.ps[1];
 				Scratch &sc = g_scratch[dev];
 				CU_TRY(cudaStreamWaitEvent(U, sc.last, 0));
 				CU_TRY(cudaEventRecord(ds.ev[0], U));
-				CU_TRY(cudaStreamWaitEvent(K, ds.ev[0], 0));
+				CU_TRY(cudaStreamWaitEvent(K2[0], ds.ev[0], 0));
+				CU_TRY(cudaStreamWaitEvent(K2[1], ds.ev[0], 0));
 				CU_TRY(cudaStreamWaitEvent(Cc, ds.ev[0], 0));
 				/* the follower: piece q is taken home (pageable table) or waited for (page-locked table: the copy
 				 * is queued by this thread) once this thread has queued its search */
@@ -745,6 +748,7 @@ int search_host_impl(const void *x, size_t n, size_t W, int t, int ngpus, int va
 						ce = upload(up++);
 					}
 					if (ce != cudaSuccess) return bail(ce);
+					cudaStream_t K = K2[q & 1];
 					if ((ce = cudaStreamWaitEvent(K, ds.upev[last], 0)) != cudaSuccess) return bail(ce);
 					X3SearchParams prm;
 					prm.x = ds.d_x + p0;
@@ -753,7 +757,7 @@ int search_host_impl(const void *x, size_t n, size_t W, int t, int ngpus, int va
 					prm.t = t;
 					prm.lstar = ds.d_l + p0;
 					prm.H = nullptr;
-					prm.tile_counter = sc.counter;
+					prm.tile_counter = sc.counter + 16 * (1 + (q & 1));
 					prm.deep = nullptr;
 					prm.ntiles = 0;
 					prm.kd = 0;
@@ -767,12 +771,13 @@ int search_host_impl(const void *x, size_t n, size_t W, int t, int ngpus, int va
 					fc.queued.store(q + 1, std::memory_order_release);
 				}
 				if ((ce = cudaEventRecord(ds.ev[1], U)) != cudaSuccess) return bail(ce);
-				if ((ce = cudaEventRecord(ds.pev[0][0], K)) != cudaSuccess) return bail(ce);
-				if ((ce = cudaEventRecord(ds.pev[1][0], K)) != cudaSuccess) return bail(ce);
+				if ((ce = cudaEventRecord(ds.pev[0][0], K2[0])) != cudaSuccess) return bail(ce);
+				if ((ce = cudaEventRecord(ds.pev[1][0], K2[1])) != cudaSuccess) return bail(ce);
 				if (l_pinned) {
 					if ((ce = cudaEventRecord(ds.pev[0][1], Cc)) != cudaSuccess) return bail(ce);
 				}
 				if ((ce = cudaStreamWaitEvent(U, ds.pev[0][0], 0)) != cudaSuccess) return bail(ce);
+				if ((ce = cudaStreamWaitEvent(U, ds.pev[1][0], 0)) != cudaSuccess) return bail(ce);
 				if (l_pinned) {
 					if ((ce = cudaStreamWaitEvent(U, ds.pev[0][1], 0)) != cudaSuccess) return bail(ce);
 				}
