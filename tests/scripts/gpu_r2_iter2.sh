@@ -6,7 +6,7 @@ mkdir -p $OUT
 timeout 150 python tests/gpu_seg_check.py small > $OUT/r2_seg_small.log 2>&1 || { echo "small ladder failed or hung"; tail -3 $OUT/r2_seg_small.log; exit 1; }
 tail -1 $OUT/r2_seg_small.log; grep MISMATCH $OUT/r2_seg_small.log | head -10
 timeout 100 python tests/gpu_seg_kinds.py 6 10 > $OUT/r2_seg_kinds.log 2>&1; cat $OUT/r2_seg_kinds.log
-X3_SEG_PROF=1 timeout 100 python tests/gpu_seg_kinds.py 6 10 2>&1 | grep x3_seg_kernel | awk 'NR%3==0' > $OUT/r2_seg_phases.log; cat $OUT/r2_seg_phases.log
+X3_SEG_PROF=1 timeout 100 python tests/gpu_seg_kinds.py 6 10 2>&1 | grep x3_seg_kernel | awk 'NR%9>=7 || NR%9==0' > $OUT/r2_seg_phases.log; cat $OUT/r2_seg_phases.log
 timeout 200 python tests/gpu_seg_check.py big > $OUT/r2_seg_big.log 2>&1; grep seg $OUT/r2_seg_big.log
 if [ "${SEG_RACE:-0}" = "1" ]; then
 timeout 900 compute-sanitizer --tool racecheck --racecheck-report analysis --print-limit 10 python tests/gpu_quick.py 60000 8192 6 nocheck C5 > $OUT/r2_seg_racecheck.log 2>&1

@@ -556,8 +556,8 @@ __device__ __forceinline__ void sg_lsd_pass2(const SegCtx &c, unsigned long long
 	if (PROF && K == 1 && (threadIdx.x & 31) == 0) {
 		/* measurement build: how long each warp spent in the level-1 ranking: the slowest (24) and the sum (25) */
 		const unsigned long long dur = clock64() - wstart;
-		atomicMax(&gp[24], dur);
-		atomicAdd(&gp[25], dur);
+		atomicMax(&gp[46], dur);
+		atomicAdd(&gp[47], dur);
 	}
 	__syncthreads();
 	if (K == 1) {
@@ -1685,7 +1685,8 @@ cudaError_t x3k_launch_seg(const X3SearchParams &prm, cudaStream_t stream, int *
 			 * other 31, which the production build does not show: its whole segment takes less than this build's passes;
 			 * read the per-warp mean for that pass) */
 			fprintf(stderr, ";  level-1 ranking per warp: mean %.0f, slowest warp of a CTA %.0f;",
-			        tot[25] / 32.0 / (tot[8] > 0 ? tot[8] : 1), tot[24] / grid);
+			        [&]{double v=0; for (unsigned b = 0; b < grid; ++b) v += (double)h[b * 64 + 47]; return v;}() / 32.0 / (tot[8] > 0 ? tot[8] : 1),
+			        [&]{double v=0; for (unsigned b = 0; b < grid; ++b) v += (double)h[b * 64 + 46]; return v;}() / grid);
 			fprintf(stderr, "  as thread 0 saw it %.0f, %.0f rare positions marked per segment\n", tot[19] / (tot[8] > 0 ? tot[8] : 1),
 			        tot[23] / (tot[8] > 0 ? tot[8] : 1));
 		}
