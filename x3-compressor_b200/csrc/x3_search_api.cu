@@ -131,6 +131,8 @@ int ensure_kernel_init(int device)
 	if (device < 0 || device >= 64) {
 		return fail(X3S_ERR_ARG, "device index %d out of range", device);
 	}
+	static std::mutex init_mu; /* x3s_search_device / _part take no other lock: two threads' first calls on one device */
+	std::lock_guard<std::mutex> lock(init_mu);
 	if (!g_kernel_inited[device]) {
 		Scratch &sc = g_scratch[device];
 		CU_TRY(cudaMalloc((void **)&sc.counter, 256));
