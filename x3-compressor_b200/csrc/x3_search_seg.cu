@@ -13,24 +13,34 @@
  *   levels 1-4  four stable counting sorts of all M elements on the bytes x[p+3], x[p+2], x[p+1],
  *             x[p] (LSD).  After the pass on x[p+j] the order is by (x[p+j..p+3], p): the
  *             level-(4-j) order of the positions q = p + j, so the NEXT pass tests that level
- *             while it reads its input (look-ahead of t+1 by warp shuffles), and the positions
- *             with a rare first byte (c1 <= t followers: tc* = c1 - 1 < t) are settled by
- *             walking those followers (Lstar = min LCP32, 0 when c1 < 2: backend.c:76-78).
+ *             while it reads its input (look-ahead of t+1 by one warp shuffle per value).  Ranking
+ *             inside a round: the lanes with lane 0's digit by one vote, the others by shared-memory
+ *             atomicOr into a mask row (MATCH.ANY costs 2 cycles per distinct value, SM-wide); two
+ *             sub-blocks per warp in flight; offsets by all 1024 threads.  The positions with a rare
+ *             first byte (c1 <= t followers: tc* = c1 - 1 < t) are marked in a bitmap and settled
+ *             behind the ranking, every thread taking its share, by walking those followers
+ *             (Lstar = min LCP32, 0 when c1 < 2: backend.c:76-78).
  *   level >= 4  the array is a set of GROUPS (runs of equal L-grams in position order).  A group
  *             with fewer than t+2 elements can never pass again and is dropped.  A group is
  *             tested, pruned to the elements within D behind a passed one (the only followers
- *             that can matter deeper down), and split by the next byte x[p+L] with a stable
- *             counting sort inside its own index range.  Groups are independent: warps take them
- *             from a shared-memory queue and follow one child themselves (no CTA barrier below
- *             level 4); groups larger than SG_SMALL elements are handled by the whole CTA first.
+ *             that can matter deeper down; any superset gives the same table), and split by the
+ *             next byte x[p+L] with a stable counting sort inside its own index range.  Groups are
+ *             independent; by size: up to 256 elements one warp follows the group down to the
+ *             level where it ends (CHAINS: registers, a shared-memory queue, no CTA barrier); up
+ *             to 7 936 elements WAVES of up to 32 rows of 256 elements, one warp per row, four
+ *             CTA barriers per level; above that the whole CTA, one group at a time.  A group
+ *             that does not change at a level (all kept, one next byte) JUMPS to the level where
+ *             its bytes first differ.
  *   store     Lstar of the B positions, kept in shared memory (the deepest level passed so far).
  *
  * HBM traffic is the algorithmic minimum: every input byte read once (plus the D-byte halo per
  * segment: (B+D)/B = 1.33 at the default window), every Lstar byte written once.  One launch per
  * search, no level reports to the host, no chained scans between CTAs; a persistent grid of one
- * CTA per SM draws segments from a counter.  Any t >= SG_TMIN (queue capacity M / (t+2)), any
- * t above; other parameters go to the rank search.  Lstar only (the 32-bin table H is the
- * brute-force kernels' job).  tests/seg_model.py states the same rules in numpy.
+ * CTA per SM draws segments from a counter (the last, partly filled wave in thirds or quarters of
+ * a segment; a launch may also take every parts-th PIECE of the input: x3s_search_device_part).
+ * Any t >= x3k_seg_min_t() (queue capacity M / (t+2)); other parameters go to the rank search.
+ * Lstar only (the 32-bin table H is the brute-force kernels' job).  tests/seg_model.py states the
+ * same rules in numpy; DESIGN.md section 4.1 has the measurements.
  */
 #include "x3_search_device.cuh"
 
